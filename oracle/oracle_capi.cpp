@@ -1,0 +1,243 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see moptimizer_oracle.hpp header).
+// C interface over the restated reference so that pytest (ctypes) and bench.py's
+// cpu_baseline / `--impl reference` legs can drive it.  Never loaded by the product.
+#include <chrono>
+#include <cstring>
+
+#include "moptimizer_oracle.hpp"
+
+using namespace oracle;
+
+extern "C" {
+
+enum { ORC_P2P = 0, ORC_EXP_CURVE = 1, ORC_MICHAELIS_MENTEN = 2, ORC_PINHOLE = 3, ORC_POWELL = 4,
+       ORC_POINT_DIST = 5 };
+enum { ORC_LOSS_NONE = 0, ORC_LOSS_GM = 1, ORC_LOSS_HUBER = 2 };
+
+struct orc_cost {
+  int model;
+  int variant;  // P2PJacobian for ORC_P2P
+  int P, O, n;
+  int jac_mode;  // JacobianMode
+  int loss;
+  double loss_param;
+  const double* cov;     // O*O column-major, or NULL for identity
+  const void* a;         // data stream A (model dependent), dtype `data_f32 ? float : double`
+  const void* b;         // data stream B
+  int data_f32;          // 1 if a/b are float arrays
+  const double* consts;  // pinhole: K (12, row-major) then C (16, row-major)
+  int cost_threads;      // threads for computeCost's parallel reduce (>=1)
+  int float_carry;       // emulate the oneTBB float-identity quirk in computeCost
+};
+
+}  // extern "C"
+
+namespace {
+
+template <class S>
+struct Holder {
+  std::vector<S> a_store, b_store;
+  const S* a = nullptr;
+  const S* b = nullptr;
+  Cost<S> cost;
+};
+
+template <class S>
+const S* adopt(const void* p, bool is_f32, size_t count, std::vector<S>& store) {
+  if (!p || count == 0) return nullptr;
+  if (is_f32 == std::is_same<S, float>::value) return static_cast<const S*>(p);
+  store.resize(count);
+  if (is_f32) {
+    const float* f = static_cast<const float*>(p);
+    for (size_t i = 0; i < count; ++i) store[i] = S(f[i]);
+  } else {
+    const double* d = static_cast<const double*>(p);
+    for (size_t i = 0; i < count; ++i) store[i] = S(d[i]);
+  }
+  return store.data();
+}
+
+template <class S>
+std::unique_ptr<Holder<S>> build(const orc_cost& c) {
+  auto h = std::make_unique<Holder<S>>();
+  size_t na = 0, nb = 0;
+  switch (c.model) {
+    case ORC_P2P:
+    case ORC_POINT_DIST: na = nb = size_t(c.n) * 3; break;
+    case ORC_EXP_CURVE:
+    case ORC_MICHAELIS_MENTEN: na = nb = size_t(c.n); break;
+    case ORC_PINHOLE: na = size_t(c.n) * 3; nb = size_t(c.n) * 2; break;
+    default: break;
+  }
+  h->a = adopt<S>(c.a, c.data_f32 != 0, na, h->a_store);
+  h->b = adopt<S>(c.b, c.data_f32 != 0, nb, h->b_store);
+  Cost<S>& k = h->cost;
+  switch (c.model) {
+    case ORC_P2P: k.model = std::make_shared<Point2Point<S>>(h->a, h->b, c.variant); break;
+    case ORC_POINT_DIST: k.model = std::make_shared<PointDist<S>>(h->a, h->b); break;
+    case ORC_EXP_CURVE: k.model = std::make_shared<ExpCurve<S>>(h->a, h->b); break;
+    case ORC_MICHAELIS_MENTEN: k.model = std::make_shared<MichaelisMenten<S>>(h->a, h->b); break;
+    case ORC_POWELL: k.model = std::make_shared<Powell<S>>(); break;
+    case ORC_PINHOLE: {
+      S K[12], C[16];
+      for (int i = 0; i < 12; ++i) K[i] = S(c.consts[i]);
+      for (int i = 0; i < 16; ++i) C[i] = S(c.consts[12 + i]);
+      k.model = std::make_shared<Pinhole<S>>(h->a, h->b, K, C);
+      break;
+    }
+    default: return nullptr;
+  }
+  switch (c.loss) {
+    case ORC_LOSS_NONE: k.loss = std::make_shared<NoLoss<S>>(); break;
+    case ORC_LOSS_GM: k.loss = std::make_shared<GemanMcClure<S>>(S(c.loss_param)); break;
+    case ORC_LOSS_HUBER: k.loss = std::make_shared<Huber<S>>(S(c.loss_param)); break;
+    default: return nullptr;
+  }
+  k.P = c.P;
+  k.O = c.O;
+  k.n = c.n;
+  k.jac_mode = c.jac_mode;
+  k.cost_threads = c.cost_threads < 1 ? 1 : c.cost_threads;
+  k.float_carry = c.float_carry != 0;
+  k.C.assign(size_t(c.O) * c.O, S(0));
+  for (int i = 0; i < c.O; ++i) k.C[i + size_t(i) * c.O] = S(1);
+  if (c.cov)
+    for (int i = 0; i < c.O * c.O; ++i) k.C[i] = S(c.cov[i]);
+  if (c.P > CostComputation<S>::kMaxP || c.O > CostComputation<S>::kMaxO) return nullptr;
+  return h;
+}
+
+template <class S>
+int linearize_t(const orc_cost* c, const double* x, double* H, double* b, double* sum,
+                int nthreads) {
+  auto h = build<S>(*c);
+  if (!h) return 1;
+  const int P = c->P;
+  std::vector<S> xs(P), Hs(size_t(P) * P), bs(P);
+  for (int i = 0; i < P; ++i) xs[i] = S(x[i]);
+  S s;
+  if (nthreads > 1) {
+    CostComputation<S> cc(P, c->O);
+    s = cc.parallelLinearize(xs.data(), h->cost.C.data(), *h->cost.loss, Hs.data(), bs.data(),
+                             *h->cost.model, c->n, c->jac_mode, nthreads);
+  } else {
+    s = h->cost.linearize(xs.data(), Hs.data(), bs.data());
+  }
+  for (int i = 0; i < P * P; ++i) H[i] = double(Hs[i]);
+  for (int i = 0; i < P; ++i) b[i] = double(bs[i]);
+  *sum = double(s);
+  return 0;
+}
+
+template <class S>
+int cost_t(const orc_cost* c, const double* x, double* sum, int parallel) {
+  auto h = build<S>(*c);
+  if (!h) return 1;
+  std::vector<S> xs(c->P > 0 ? c->P : 1);
+  for (int i = 0; i < c->P; ++i) xs[i] = S(x[i]);
+  CostComputation<S> cc(c->P, c->O);
+  S s = parallel ? cc.parallelComputeCost(xs.data(), *h->cost.model, c->n, h->cost.cost_threads,
+                                          h->cost.float_carry)
+                 : cc.computeCost(xs.data(), *h->cost.model, c->n);
+  *sum = double(s);
+  return 0;
+}
+
+template <class S>
+int lm_t(const orc_cost* cs, int ncosts, int P, int max_it, int lm_it, double* x, int* status,
+         int* executed, double* trace, int max_trace, int* ntrace) {
+  std::vector<std::unique_ptr<Holder<S>>> hs;
+  std::vector<Cost<S>*> costs;
+  for (int i = 0; i < ncosts; ++i) {
+    hs.push_back(build<S>(cs[i]));
+    if (!hs.back()) return 1;
+    costs.push_back(&hs.back()->cost);
+  }
+  std::vector<S> xs(P);
+  for (int i = 0; i < P; ++i) xs[i] = S(x[i]);
+  std::vector<TraceEntry> tr;
+  Status st = lm_minimize<S>(costs, P, max_it, lm_it, xs.data(), executed, &tr);
+  for (int i = 0; i < P; ++i) x[i] = double(xs[i]);
+  *status = int(st);
+  int nt = 0;
+  for (auto& e : tr) {
+    if (nt >= max_trace) break;
+    double* t = trace + size_t(nt) * 8;
+    t[0] = e.outer_it; t[1] = e.k; t[2] = e.y0; t[3] = e.yi; t[4] = e.rho; t[5] = e.lambda;
+    t[6] = e.nu; t[7] = e.accepted;
+    ++nt;
+  }
+  *ntrace = nt;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// scalar: 0 = float, 1 = double (the reference's two instantiations, src/*.cpp tails).
+int orc_linearize(const orc_cost* c, int scalar, const double* x, double* H, double* b,
+                  double* sum, int nthreads) {
+  return scalar ? linearize_t<double>(c, x, H, b, sum, nthreads)
+                : linearize_t<float>(c, x, H, b, sum, nthreads);
+}
+
+int orc_compute_cost(const orc_cost* c, int scalar, const double* x, double* sum, int parallel) {
+  return scalar ? cost_t<double>(c, x, sum, parallel) : cost_t<float>(c, x, sum, parallel);
+}
+
+// trace: max_trace rows of 8 doubles {outer_it, k, y0, yi, rho, lambda, nu, accepted}.
+int orc_lm_minimize(const orc_cost* costs, int ncosts, int scalar, int P, int max_it, int lm_it,
+                    double* x, int* status, int* executed, double* trace, int max_trace,
+                    int* ntrace) {
+  return scalar ? lm_t<double>(costs, ncosts, P, max_it, lm_it, x, status, executed, trace,
+                               max_trace, ntrace)
+                : lm_t<float>(costs, ncosts, P, max_it, lm_it, x, status, executed, trace,
+                              max_trace, ntrace);
+}
+
+int orc_ldlt_solve(int n, const double* A, const double* rhs, double* out) {
+  ldlt_solve<double>(n, A, rhs, out);
+  return 0;
+}
+
+int orc_so3_convert6dof(const double* x, double* T16_rowmajor) {
+  so3_convert6dof<double>(x, T16_rowmajor);
+  return 0;
+}
+
+int orc_so3_left_jacobian_full(const double* w, double* J9_rowmajor) {
+  so3_left_jacobian_full<double>(w, J9_rowmajor);
+  return 0;
+}
+
+// Timed loops for bench.py (cpu_baseline / --impl reference): runs `reps` linearizations
+// and returns the elapsed seconds of the loop only (model construction excluded).
+double orc_time_linearize(const orc_cost* c, int scalar, const double* x, int nthreads, int reps,
+                          double* H, double* b, double* sum) {
+  if (!scalar) return -1.0;
+  auto h = build<double>(*c);
+  if (!h) return -1.0;
+  const int P = c->P;
+  std::vector<double> Hs(size_t(P) * P), bs(P);
+  double s = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < reps; ++r) {
+    if (nthreads > 1) {
+      CostComputation<double> cc(P, c->O);
+      s = cc.parallelLinearize(x, h->cost.C.data(), *h->cost.loss, Hs.data(), bs.data(),
+                               *h->cost.model, c->n, c->jac_mode, nthreads);
+    } else {
+      s = h->cost.linearize(x, Hs.data(), bs.data());
+    }
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  std::memcpy(H, Hs.data(), sizeof(double) * Hs.size());
+  std::memcpy(b, bs.data(), sizeof(double) * bs.size());
+  *sum = s;
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int orc_hardware_concurrency() { return int(std::thread::hardware_concurrency()); }
+
+}  // extern "C"
