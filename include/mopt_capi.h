@@ -1,0 +1,231 @@
+/*
+ * mopt_capi.h — C ABI of the B200-native linearization / Levenberg-Marquardt hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `extern "C"`, int status returns,
+ * no exceptions and no C++/torch types cross it.  The reference (Marcus-Forte/moptimizer_0)
+ * has no FFI of its own; its boundary for this path is the C++ operator API
+ *     CostFunctionBase<Scalar>::{update, computeCost, linearize}      include/moptimizer/cost_function.h:37-50
+ *     CostFunction{Analytical,Numerical}Dynamic                         src/cost_function_*_dyn.cpp:19-30
+ *     CostComputation::{computeHessian, computeHessianNumerical,
+ *                       computeCost, parallelComputeCost}               include/moptimizer/linearization.h:36-158
+ *     LevenbergMarquadtDynamic<Scalar>::minimize                        src/levenberg_marquadt_dyn.cpp:34-119
+ * and every entry point below names the reference function it replaces.  The C++ classes in
+ * include/moptimizer/ (same names and signatures as the reference) call these functions;
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * All `file:line` citations are relative to the reference repository root.
+ *
+ * Threading: one host thread per context.  All device work of a context is issued on the
+ * context's own CUDA stream; calls that return results to host memory synchronise that stream.
+ */
+#ifndef MOPT_CAPI_H
+#define MOPT_CAPI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOPT_MAX_PARAMETERS 16 /* P: parameters per problem (n x n device solve)              */
+#define MOPT_MAX_OUTPUTS 4     /* O: residual dimension                                       */
+#define MOPT_MAX_COSTS 8       /* cost terms summed by one LM problem (optimizer.h:58 addCost) */
+#define MOPT_MAX_TRACE 1024    /* LM trial records kept in a report                           */
+#define MOPT_NCCL_ID_BYTES 128
+
+#if defined(__GNUC__)
+#define MOPT_API __attribute__((visibility("default")))
+#else
+#define MOPT_API
+#endif
+
+typedef struct mopt_ctx mopt_ctx;     /* one GPU (+ optional communicator rank)            */
+typedef struct mopt_store mopt_store; /* device-buffer residual store: planar data streams */
+
+typedef enum mopt_status {
+  MOPT_OK = 0,
+  MOPT_ERR_INVALID_ARGUMENT = 1,
+  MOPT_ERR_CUDA = 2,
+  MOPT_ERR_COMM = 3,
+  MOPT_ERR_UNSUPPORTED = 4,
+  MOPT_ERR_OUT_OF_MEMORY = 5
+} mopt_status;
+
+/* include/moptimizer/types.h:6-12 — same numeric values. */
+typedef enum mopt_optimization_status {
+  MOPT_CONVERGED = 0,
+  MOPT_MAXIMUM_ITERATIONS_REACHED = 1,
+  MOPT_SMALL_DELTA = 2,
+  MOPT_NUMERIC_ERROR = 3,
+  MOPT_FATAL_ERROR = 4
+} mopt_optimization_status;
+
+typedef enum mopt_dtype { MOPT_F32 = 0, MOPT_F64 = 1 } mopt_dtype;
+
+/* Builtin device models.  IBaseModel's virtual f / f_df (include/moptimizer/model.h:33,42) cannot
+ * be called from a kernel, so the workloads the reference defines in its tests are compiled in. */
+typedef enum mopt_model {
+  /* r = T(x) p - q, x = [t, omega]; P=6, O=3.  tst/point2point.cpp:24-84.  data A = src xyz, B = tgt xyz */
+  MOPT_MODEL_POINT2POINT = 0,
+  /* r = y - exp(x0 t + x1); P=2, O=1.  tst/curve_fitting.cpp:81-98.  A = t, B = y */
+  MOPT_MODEL_EXP_CURVE = 1,
+  /* r = y - x0 t / (x1 + t); P=2, O=1.  tst/test_models.h:8-19, tst/differentiation.cpp:16-41.  A = t, B = y */
+  MOPT_MODEL_MICHAELIS_MENTEN = 2,
+  /* r = pix - proj(K T(x) C P); P=6, O=2.  tst/camera_calibration.cpp:12-57.  A = XYZ, B = uv;
+   * consts = K (3x4 row-major, 12) then C (4x4 row-major, 16) */
+  MOPT_MODEL_PINHOLE = 3,
+  /* Powell's singular function; P=4, O=4, no data.  tst/powell.cpp:22-59 */
+  MOPT_MODEL_POWELL = 4,
+  /* r = p - q, no parameters; P=0, O=3, cost only.  tst/parallel.cpp:12-32 */
+  MOPT_MODEL_POINT_DIST = 5,
+  MOPT_MODEL_COUNT_
+} mopt_model;
+
+/* Which Jacobian the linearization uses. */
+typedef enum mopt_jacobian {
+  MOPT_JAC_ANALYTICAL = 0, /* computeHessian,          linearization.h:126-158 (model f_df) */
+  MOPT_JAC_FORWARD = 1,    /* computeHessianNumerical, linearization.h:65-124 (reference: forward difference) */
+  MOPT_JAC_CENTRAL = 2     /* same steps h_j, (r(x+h)-r(x-h))/2h — north-star addition */
+} mopt_jacobian;
+
+/* Analytical Jacobian form of MOPT_MODEL_POINT2POINT (ignored by other models). */
+typedef enum mopt_p2p_variant {
+  MOPT_P2P_EXACT = 0,           /* [I | -[R p]x J_l(omega)] — exact for the additive update of levenberg_marquadt_dyn.cpp:83 */
+  MOPT_P2P_REFTEST = 1,         /* [I | -[p]x], row-major as linearization.h:17-18 requires (tst/point2point.cpp:72-75) */
+  MOPT_P2P_REFTEST_COLMAJOR = 2 /* same values written column-major, bit-faithful to tst/point2point.cpp:18,71 */
+} mopt_p2p_variant;
+
+/* loss_function/loss_function.h:20-23, loss_function/geman_mcclure.h:7-19; Huber is new. */
+typedef enum mopt_loss {
+  MOPT_LOSS_NONE = 0,
+  MOPT_LOSS_GEMAN_MCCLURE = 1, /* w = th^2 / (e2 + th)^2,            loss_param = th */
+  MOPT_LOSS_HUBER = 2          /* w = 1 if e2 <= k^2 else k/sqrt(e2), loss_param = k  */
+} mopt_loss;
+
+/* One cost term: what CostFunction{Analytical,Numerical}Dynamic holds besides the data
+ * (cost_function.h:52-58, cost_function_*_dyn.h:28-31). */
+typedef struct mopt_problem {
+  int32_t model;          /* mopt_model */
+  int32_t variant;        /* mopt_p2p_variant */
+  int32_t num_parameters; /* P */
+  int32_t num_outputs;    /* O */
+  int32_t jacobian;       /* mopt_jacobian */
+  int32_t compute_dtype;  /* mopt_dtype: arithmetic of residual/Jacobian evaluation (the reference's Scalar);
+                             accumulation across residuals is always fp64 */
+  int32_t loss;           /* mopt_loss */
+  int32_t has_covariance; /* 0: identity (src/cost_function_*_dyn.cpp:14-15) */
+  double loss_param;
+  double covariance[MOPT_MAX_OUTPUTS * MOPT_MAX_OUTPUTS]; /* O x O column-major, symmetric (setCovariance, cost_function.h:38-40) */
+  double consts[32];                                       /* model constants, see mopt_model */
+} mopt_problem;
+
+/* Optimizer knobs: optimizer.h:19,33-37, levenberg_marquadt_dyn.cpp:9,16, levenberg_marquadt_dyn.h:22-24. */
+typedef struct mopt_lm_options {
+  int32_t max_iterations;    /* default 15 */
+  int32_t lm_max_iterations; /* default 3  */
+  double lambda_factor;      /* default 1e-9 */
+  int32_t scalar_dtype;      /* mopt_dtype of the LM arithmetic (lambda, rho, solve): the reference's Scalar */
+  int32_t speculative;       /* 1: every trial pass evaluates cost AND H,b at x+delta so an accepted step needs
+                                no second pass (valid while model->update(x) is a no-op); 0: reference pass order */
+} mopt_lm_options;
+
+typedef struct mopt_lm_trial {
+  int32_t outer_iteration, k, accepted, reserved;
+  double y0, yi, rho, lambda, nu;
+} mopt_lm_trial;
+
+typedef struct mopt_lm_report {
+  int32_t status;              /* mopt_optimization_status */
+  int32_t executed_iterations; /* Optimizer::getExecutedIterations, optimizer.h:44 */
+  int32_t num_trials;
+  int32_t num_passes;          /* full passes over the residuals executed on the device */
+  double final_cost;           /* last accepted sum r^T r */
+  mopt_lm_trial trials[MOPT_MAX_TRACE];
+} mopt_lm_report;
+
+/* Synthetic workloads generated on the device by a counter-based hash of (seed, global index);
+ * the generator is specified bit-exactly in include/mopt_synth.h so a host can reproduce it. */
+typedef struct mopt_synth {
+  uint64_t seed;
+  int64_t first_index; /* global index of this store's element 0 (rank offset when sharded) */
+  double gt[MOPT_MAX_PARAMETERS]; /* ground-truth parameters */
+  double lo[3], hi[3]; /* p2p: source box; curve: t range lo[0]..hi[0] over n_total; pinhole: frustum box */
+  int64_t n_total;     /* curve: t_i = lo + (hi-lo) * i / n_total */
+  double noise_sigma;  /* approx. Gaussian (Irwin-Hall 4) noise added to B */
+  double outlier_fraction, outlier_range; /* fraction of elements whose B gets U(-range, range) added */
+} mopt_synth;
+
+/* ---- library ------------------------------------------------------------------------------- */
+MOPT_API const char* mopt_last_error(void);        /* text of the calling thread's last failure */
+MOPT_API const char* mopt_version(void);
+MOPT_API int mopt_device_count(int* count);
+
+/* ---- context ------------------------------------------------------------------------------- */
+MOPT_API int mopt_ctx_create(int device, mopt_ctx** out);
+/* Sharded operation: one context per process/GPU.  `nccl_unique_id` is MOPT_NCCL_ID_BYTES bytes obtained
+ * from mopt_comm_unique_id() on rank 0 and broadcast by the host (e.g. torch.distributed).  After this,
+ * linearize / compute_cost / lm_minimize return the sum over all ranks' stores (one fp64 all-reduce of
+ * P(P+1)/2 + P + 1 values per pass), identical on every rank. */
+MOPT_API int mopt_ctx_create_sharded(int device, int rank, int world_size, const void* nccl_unique_id, mopt_ctx** out);
+MOPT_API int mopt_comm_unique_id(void* out_id);
+MOPT_API int mopt_ctx_destroy(mopt_ctx* ctx);
+MOPT_API int mopt_ctx_synchronize(mopt_ctx* ctx);
+/* cudaStream_t of the context as an integer (for CUDA-event timing by the caller). */
+MOPT_API int mopt_ctx_stream(mopt_ctx* ctx, uint64_t* out_stream);
+/* Tuning: CTAs per SM / threads per CTA of the pass kernels (0 = default). */
+MOPT_API int mopt_ctx_set_launch(mopt_ctx* ctx, int ctas_per_sm, int threads);
+
+/* ---- device-buffer residual store ---------------------------------------------------------- */
+/* Replaces the caller-owned std::vector data the reference models point into
+ * (tst/point2point.cpp:82-83, tst/curve_fitting.cpp:95, tst/camera_calibration.cpp:46-47). */
+MOPT_API int mopt_store_create(mopt_ctx* ctx, int model, int dtype, int64_t n, mopt_store** out);
+MOPT_API int mopt_store_destroy(mopt_store* store);
+MOPT_API int mopt_store_size(const mopt_store* store, int64_t* n);
+/* Copy `count` elements of data group `group` (0 = A, 1 = B, see mopt_model) from a host AoS array into
+ * elements [first, first+count).  Element i's components are host[(i*host_stride) + c], c < ncomp(group);
+ * host_stride = 0 means packed (= ncomp).  Converts host_dtype -> store dtype on the device. */
+MOPT_API int mopt_store_upload(mopt_store* store, int group, const void* host, int host_dtype, int64_t host_stride,
+                      int64_t first, int64_t count);
+MOPT_API int mopt_store_download(mopt_store* store, int group, void* host, int host_dtype, int64_t first, int64_t count);
+MOPT_API int mopt_store_generate(mopt_store* store, const mopt_synth* desc);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+/* CostFunction*Dynamic::linearize (src/cost_function_*_dyn.cpp:25-30) -> computeHessian /
+ * computeHessianNumerical (linearization.h:65-158).  H is P x P full symmetric (column-major ==
+ * row-major), b is P, *sum = sum r^T r (unweighted).  x, H, b, sum are host pointers. */
+MOPT_API int mopt_linearize(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x, double* H,
+                   double* b, double* sum);
+/* CostFunction*Dynamic::computeCost (src/cost_function_*_dyn.cpp:19-22) -> parallelComputeCost
+ * (linearization.h:49-63). */
+MOPT_API int mopt_compute_cost(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x, double* sum);
+/* Same as mopt_linearize but asynchronous and device-resident: x is read from / (H upper-packed, b, sum)
+ * written to device memory owned by the context (`mopt_ctx_result` fetches them).  Used for timing the
+ * kernel without host round trips. */
+MOPT_API int mopt_linearize_async(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x);
+MOPT_API int mopt_ctx_result(mopt_ctx* ctx, int num_parameters, double* H, double* b, double* sum);
+
+/* End-to-end convenience: upload host AoS data (group A and B) into `store` and linearize, with the
+ * host->device copies chunked and overlapped with the device work. */
+MOPT_API int mopt_upload_and_linearize(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const void* host_a,
+                              const void* host_b, int host_dtype, int64_t count, const double* x, double* H,
+                              double* b, double* sum);
+
+/* LevenbergMarquadtDynamic<Scalar>::minimize (src/levenberg_marquadt_dyn.cpp:34-119) over `n_costs` cost
+ * terms (addCost, optimizer.h:58), entirely on the device: linearization passes, the damped P x P LDL^T
+ * solve, gain ratio and accept/reject never round-trip through the host.  x is in/out (host pointer). */
+MOPT_API int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, const mopt_problem* problems,
+                     const mopt_lm_options* options, double* x, mopt_lm_report* report);
+MOPT_API void mopt_lm_default_options(mopt_lm_options* options);
+
+/* ---- small host-side math kept for API parity (src/so3.cpp:7-19,43-57; delta.h:11-16) -------- */
+MOPT_API int mopt_so3_convert6dof(const double* x, double* T16_rowmajor);
+MOPT_API int mopt_ldlt_solve(int n, const double* A_colmajor, const double* rhs, double* out);
+
+/* Pinned host memory for callers that want full-speed uploads. */
+MOPT_API int mopt_host_alloc(void** ptr, uint64_t bytes);
+MOPT_API int mopt_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOPT_CAPI_H */

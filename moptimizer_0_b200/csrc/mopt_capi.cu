@@ -1,0 +1,587 @@
+// C ABI implementation (include/mopt_capi.h): contexts, the host-driven linearize / cost passes,
+// the device-resident Levenberg-Marquardt driver and the optional NCCL shard reduction.
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "mopt_internal.h"
+
+using namespace mopt;
+
+// ------------------------------------------------------------------------------ errors ----
+namespace {
+thread_local std::string g_last_error;
+}
+namespace mopt {
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+int store_upload_async(mopt_store* st, int group, const void* host, int host_dtype, int64_t host_stride, int64_t first,
+                       int64_t count);
+}  // namespace mopt
+
+// -------------------------------------------------------------------------------- NCCL ----
+// Resolved at run time (dlopen) so the library has no link-time NCCL dependency and shares the
+// copy already loaded by the host process (e.g. the one bundled with torch) when there is one.
+namespace {
+struct NcclApi {
+  typedef struct ncclComm* comm_t;
+  struct unique_id { char internal[MOPT_NCCL_ID_BYTES]; };
+  int (*GetUniqueId)(unique_id*) = nullptr;
+  int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
+  int (*CommDestroy)(comm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {getenv("MOPT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+      if (!n) continue;
+      h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) {
+      api.why = std::string("cannot dlopen libnccl: ") + (dlerror() ? dlerror() : "?");
+      return;
+    }
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+    if (!api.ok) api.why = "libnccl is missing required symbols";
+  });
+  return api;
+}
+constexpr int kNcclFloat64 = 8;  // ncclFloat64 / ncclDouble (nccl.h)
+constexpr int kNcclSum = 0;      // ncclSum
+
+#define MOPT_NCCL_TRY(expr)                                                                       \
+  do {                                                                                            \
+    int _r = (expr);                                                                              \
+    if (_r != 0) {                                                                                \
+      set_last_error(std::string(#expr) + " failed: " + nccl().GetErrorString(_r));               \
+      return MOPT_ERR_COMM;                                                                       \
+    }                                                                                             \
+  } while (0)
+}  // namespace
+
+// ----------------------------------------------------------------------------- kernels ----
+namespace {
+
+// model->setup(x) for one cost slot (and its finite-difference perturbations).  x travels as a
+// kernel argument, so back-to-back asynchronous calls need no staging buffer.
+struct XArg {
+  double v[kMaxP];
+};
+__global__ void setup_kernel(CostSlot* slot, XArg x) { setup_cost(slot->cost, x.v, &slot->pb, threadIdx.x, blockDim.x); }
+
+struct LmInit {
+  int P, n_costs, max_it, lm_max_it, speculative, scalar_f32;
+  double lambda_factor;
+  double x0[kMaxP];
+};
+
+// levenberg_marquadt_dyn.cpp:15-26 (prepare) + the first setup(x0).
+__global__ void lm_init_kernel(LmState* st, CostSlot* slots, LmInit in) {
+  if (threadIdx.x == 0) {
+    st->P = in.P; st->n_costs = in.n_costs; st->max_it = in.max_it; st->lm_max_it = in.lm_max_it;
+    st->speculative = in.speculative; st->scalar_f32 = in.scalar_f32; st->lambda_factor = in.lambda_factor;
+    for (int i = 0; i < kMaxP; ++i) {
+      const double v = i < in.P ? (in.scalar_f32 ? double(float(in.x0[i])) : in.x0[i]) : 0.0;
+      st->x[i] = v; st->xi[i] = v; st->x_eval[i] = v; st->delta[i] = 0.0;
+    }
+    st->lambda = -1.0; st->nu = 2.0;
+    st->it = 0; st->k = 0; st->phase = LM_PHASE_LIN; st->status = MOPT_MAXIMUM_ITERATIONS_REACHED;
+    st->done = 0; st->executed = 0; st->num_trials = 0; st->num_passes = 0;
+    st->pass_mode = PASS_LINEARIZE;
+    for (int i = 0; i < kPackedMax; ++i) st->cur.v[i] = 0.0;
+  }
+  __syncthreads();
+  for (int c = 0; c < in.n_costs; ++c) setup_cost(slots[c].cost, st->x_eval, &slots[c].pb, threadIdx.x, blockDim.x);
+}
+
+// One optimizer transition between passes; also publishes the done flag of this slot to the host.
+__global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* slots, int* flag) {
+  __shared__ int s_act;
+  if (threadIdx.x == 0) s_act = st->scalar_f32 ? lm_step_thread<float>(st, trial) : lm_step_thread<double>(st, trial);
+  __syncthreads();
+  if (s_act) {
+    const int nc = st->n_costs;
+    for (int c = 0; c < nc; ++c) setup_cost(slots[c].cost, st->x_eval, &slots[c].pb, threadIdx.x, blockDim.x);
+  }
+  if (threadIdx.x == 0) *flag = st->done;
+}
+
+__global__ void ldlt_test_kernel(int n, double* A, const double* rhs, double* out) { ldlt_solve_dev<double>(n, A, rhs, out); }
+
+}  // namespace
+
+// ----------------------------------------------------------------------------- helpers ----
+namespace {
+
+int validate_problem(const mopt_store* st, const mopt_problem* p, bool need_linearize) {
+  MOPT_REQUIRE(st && p, "null store/problem");
+  MOPT_REQUIRE(p->model == st->model, "problem.model differs from the store's model");
+  const ModelShape sh = model_shape(p->model);
+  MOPT_REQUIRE(sh.P >= 0, "unknown model kind");
+  MOPT_REQUIRE(p->num_parameters == sh.P, "num_parameters does not match the builtin model");
+  MOPT_REQUIRE(p->num_outputs == sh.O, "num_outputs does not match the builtin model");
+  MOPT_REQUIRE(p->compute_dtype == MOPT_F32 || p->compute_dtype == MOPT_F64, "bad compute dtype");
+  MOPT_REQUIRE(p->loss >= MOPT_LOSS_NONE && p->loss <= MOPT_LOSS_HUBER, "unknown loss kind");
+  MOPT_REQUIRE(p->jacobian >= MOPT_JAC_ANALYTICAL && p->jacobian <= MOPT_JAC_CENTRAL, "unknown jacobian mode");
+  if (need_linearize) {
+    MOPT_REQUIRE(sh.P > 0, "this model has no parameters; only mopt_compute_cost is defined for it");
+    if (p->jacobian == MOPT_JAC_ANALYTICAL && !sh.has_analytical) {
+      // BaseModel::f_df throws for Jacobian-free models (include/moptimizer/model.h:66-70)
+      set_last_error("Non implemented non-jacobian model function `f_df` being used.");
+      return MOPT_ERR_UNSUPPORTED;
+    }
+  }
+  if (p->model == MOPT_MODEL_POINT2POINT)
+    MOPT_REQUIRE(p->variant >= MOPT_P2P_EXACT && p->variant <= MOPT_P2P_REFTEST_COLMAJOR, "unknown point2point variant");
+  if (p->has_covariance) {
+    const int O = sh.O;
+    for (int r = 0; r < O; ++r)
+      for (int c = 0; c < r; ++c)
+        if (p->covariance[r + c * O] != p->covariance[c + r * O]) {
+          set_last_error("covariance must be symmetric (only the upper triangle of H is accumulated)");
+          return MOPT_ERR_UNSUPPORTED;
+        }
+  }
+  return MOPT_OK;
+}
+
+void fill_cost(const mopt_problem* p, CostDev* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->model = p->model; c->variant = p->variant; c->P = p->num_parameters; c->O = p->num_outputs;
+  c->jacobian = p->jacobian; c->loss = p->loss; c->has_cov = p->has_covariance ? 1 : 0;
+  c->compute_dtype = p->compute_dtype; c->loss_param = p->loss_param;
+  const int O = p->num_outputs;
+  for (int i = 0; i < O * O; ++i) c->cov[i] = p->has_covariance ? p->covariance[i] : ((i % (O + 1) == 0) ? 1.0 : 0.0);
+  std::memcpy(c->consts, p->consts, sizeof(c->consts));
+}
+
+// Copy the cost constants of slot `i` to the device unless they are already there.
+int stage_cost(mopt_ctx* ctx, int i, const mopt_problem* p) {
+  CostDev c;
+  fill_cost(p, &c);
+  if (ctx->cached_valid[i] && std::memcmp(&c, &ctx->cached_cost[i], sizeof(c)) == 0) return MOPT_OK;
+  // h_slot is reused as a pinned bounce buffer: wait until earlier copies from it have been consumed
+  MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->h_slot->cost = c;
+  MOPT_CUDA_TRY(cudaMemcpyAsync(&ctx->d_slots[i].cost, &ctx->h_slot->cost, sizeof(CostDev), cudaMemcpyHostToDevice, ctx->stream));
+  MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->cached_cost[i] = c;
+  ctx->cached_valid[i] = true;
+  return MOPT_OK;
+}
+
+PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate, int mode_override) {
+  PassArgs a;
+  std::memset(&a, 0, sizeof(a));
+  for (int s = 0; s < kMaxStreams; ++s) a.streams.p[s] = st->streams[s];
+  a.n = st->n;
+  a.pb = &ctx->d_slots[slot].pb;
+  a.cost = &ctx->d_slots[slot].cost;
+  a.partials = ctx->d_partials;
+  a.ticket = ctx->d_ticket;
+  a.out = ctx->d_trial;
+  a.accumulate = accumulate;
+  a.mode_ptr = &ctx->d_lm->pass_mode;
+  a.mode_override = mode_override;
+  return a;
+}
+
+int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int slot, int accumulate, int mode_override) {
+  const PassArgs a = make_args(ctx, st, slot, accumulate, mode_override);
+  PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm};
+  if (p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL)
+    return launch_p2p_moment(L, st->dtype, p->compute_dtype, p->loss, p->variant == MOPT_P2P_EXACT, a);
+  return launch_dense(L, p->model, p->jacobian != MOPT_JAC_ANALYTICAL, st->dtype, p->compute_dtype, a);
+}
+
+int allreduce_trial(mopt_ctx* ctx, int P) {
+  if (ctx->world <= 1) return MOPT_OK;
+  MOPT_NCCL_TRY(nccl().AllReduce(ctx->d_trial, ctx->d_trial, size_t(packed_size(P)), kNcclFloat64, kNcclSum,
+                                 static_cast<NcclApi::comm_t>(ctx->nccl_comm), ctx->stream));
+  return MOPT_OK;
+}
+
+void unpack_result(const PassResult& r, int P, double* H, double* b, double* sum) {
+  if (H)
+    for (int i = 0; i < P; ++i)
+      for (int j = i; j < P; ++j) {
+        const double v = r.v[tri_index(P, i, j)];
+        H[i + j * P] = v;
+        H[j + i * P] = v;
+      }
+  if (b)
+    for (int i = 0; i < P; ++i) b[i] = r.v[P * (P + 1) / 2 + i];
+  if (sum) *sum = r.v[packed_size(P) - 1];
+}
+
+int enqueue_pass(mopt_ctx* ctx, mopt_store* st, const mopt_problem* p, const double* x, int mode) {
+  MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
+  MOPT_TRY(stage_cost(ctx, 0, p));
+  const int P = p->num_parameters;
+  XArg xa;
+  std::memset(&xa, 0, sizeof(xa));
+  if (P > 0) {
+    MOPT_REQUIRE(x != nullptr, "null parameter vector");
+    for (int i = 0; i < P; ++i) xa.v[i] = x[i];
+  }
+  setup_kernel<<<1, 32, 0, ctx->stream>>>(&ctx->d_slots[0], xa);
+  MOPT_CUDA_TRY(cudaGetLastError());
+  MOPT_TRY(launch_pass(ctx, st, p, 0, 0, mode));
+  MOPT_TRY(allreduce_trial(ctx, P));
+  return MOPT_OK;
+}
+
+int fetch_result(mopt_ctx* ctx, int P, double* H, double* b, double* sum) {
+  MOPT_CUDA_TRY(cudaMemcpyAsync(ctx->h_result, ctx->d_trial, sizeof(double) * packed_size(P), cudaMemcpyDeviceToHost, ctx->stream));
+  MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  unpack_result(*ctx->h_result, P, H, b, sum);
+  return MOPT_OK;
+}
+
+int ctx_alloc(mopt_ctx* ctx) {
+  MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  MOPT_CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+  ctx->num_sms = prop.multiProcessorCount;
+  MOPT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  MOPT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_partials, sizeof(double) * 32 * kMaxGrid));
+  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
+  MOPT_CUDA_TRY(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
+  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_trial, sizeof(PassResult)));
+  MOPT_CUDA_TRY(cudaMemset(ctx->d_trial, 0, sizeof(PassResult)));
+  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_slots, sizeof(CostSlot) * MOPT_MAX_COSTS));
+  MOPT_CUDA_TRY(cudaMemset(ctx->d_slots, 0, sizeof(CostSlot) * MOPT_MAX_COSTS));
+  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_lm, sizeof(LmState)));
+  MOPT_CUDA_TRY(cudaMemset(ctx->d_lm, 0, sizeof(LmState)));
+  MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_result, sizeof(PassResult), cudaHostAllocDefault));
+  MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_lm, sizeof(LmState), cudaHostAllocDefault));
+  MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_slot, sizeof(CostSlot), cudaHostAllocDefault));
+  ctx->flags_capacity = 4096;
+  MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_flags, sizeof(int) * ctx->flags_capacity, cudaHostAllocMapped));
+  MOPT_CUDA_TRY(cudaHostGetDevicePointer(&ctx->d_flags, ctx->h_flags, 0));
+  for (int i = 0; i < 2; ++i) {
+    MOPT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+    MOPT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+    MOPT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_batch[i], cudaEventDisableTiming));
+  }
+  return MOPT_OK;
+}
+
+}  // namespace
+
+// ============================================================================== C ABI ====
+extern "C" {
+
+const char* mopt_last_error(void) { return g_last_error.c_str(); }
+const char* mopt_version(void) { return "moptimizer_0_b200 0.1 (sm_100a)"; }
+
+int mopt_device_count(int* count) {
+  MOPT_REQUIRE(count, "null count");
+  MOPT_CUDA_TRY(cudaGetDeviceCount(count));
+  return MOPT_OK;
+}
+
+int mopt_ctx_create(int device, mopt_ctx** out) {
+  MOPT_REQUIRE(out, "null out");
+  mopt_ctx* ctx = new mopt_ctx();
+  ctx->device = device;
+  const int s = ctx_alloc(ctx);
+  if (s != MOPT_OK) {
+    delete ctx;
+    return s;
+  }
+  *out = ctx;
+  return MOPT_OK;
+}
+
+int mopt_comm_unique_id(void* out_id) {
+  MOPT_REQUIRE(out_id, "null out_id");
+  if (!nccl().ok) {
+    set_last_error(nccl().why);
+    return MOPT_ERR_COMM;
+  }
+  NcclApi::unique_id id;
+  MOPT_NCCL_TRY(nccl().GetUniqueId(&id));
+  std::memcpy(out_id, &id, MOPT_NCCL_ID_BYTES);
+  return MOPT_OK;
+}
+
+int mopt_ctx_create_sharded(int device, int rank, int world_size, const void* nccl_unique_id, mopt_ctx** out) {
+  MOPT_REQUIRE(out && nccl_unique_id, "null out/unique id");
+  MOPT_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad rank/world_size");
+  MOPT_TRY(mopt_ctx_create(device, out));
+  mopt_ctx* ctx = *out;
+  ctx->rank = rank;
+  ctx->world = world_size;
+  if (world_size > 1) {
+    if (!nccl().ok) {
+      set_last_error(nccl().why);
+      mopt_ctx_destroy(ctx);
+      *out = nullptr;
+      return MOPT_ERR_COMM;
+    }
+    NcclApi::unique_id id;
+    std::memcpy(&id, nccl_unique_id, MOPT_NCCL_ID_BYTES);
+    NcclApi::comm_t comm = nullptr;
+    const int r = nccl().CommInitRank(&comm, world_size, id, rank);
+    if (r != 0) {
+      set_last_error(std::string("ncclCommInitRank failed: ") + nccl().GetErrorString(r));
+      mopt_ctx_destroy(ctx);
+      *out = nullptr;
+      return MOPT_ERR_COMM;
+    }
+    ctx->nccl_comm = comm;
+  }
+  return MOPT_OK;
+}
+
+int mopt_ctx_destroy(mopt_ctx* ctx) {
+  if (!ctx) return MOPT_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->nccl_comm) nccl().CommDestroy(static_cast<NcclApi::comm_t>(ctx->nccl_comm));
+  cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trial);
+  cudaFree(ctx->d_slots); cudaFree(ctx->d_lm);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
+    if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+    if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+    if (ctx->ev_batch[i]) cudaEventDestroy(ctx->ev_batch[i]);
+  }
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->h_lm) cudaFreeHost(ctx->h_lm);
+  if (ctx->h_slot) cudaFreeHost(ctx->h_slot);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return MOPT_OK;
+}
+
+int mopt_ctx_synchronize(mopt_ctx* ctx) {
+  MOPT_REQUIRE(ctx, "null ctx");
+  MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
+  MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MOPT_OK;
+}
+
+int mopt_ctx_stream(mopt_ctx* ctx, uint64_t* out_stream) {
+  MOPT_REQUIRE(ctx && out_stream, "null ctx/out");
+  *out_stream = reinterpret_cast<uint64_t>(ctx->stream);
+  return MOPT_OK;
+}
+
+int mopt_ctx_set_launch(mopt_ctx* ctx, int ctas_per_sm, int threads) {
+  MOPT_REQUIRE(ctx, "null ctx");
+  MOPT_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 8, "ctas_per_sm must be in [0, 8]");
+  ctx->ctas_per_sm = ctas_per_sm;
+  ctx->threads = threads;
+  return MOPT_OK;
+}
+
+int mopt_linearize(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x, double* H, double* b,
+                   double* sum) {
+  MOPT_REQUIRE(ctx && store && store->ctx == ctx, "store does not belong to this context");
+  MOPT_TRY(validate_problem(store, problem, true));
+  MOPT_TRY(enqueue_pass(ctx, store, problem, x, PASS_LINEARIZE));
+  return fetch_result(ctx, problem->num_parameters, H, b, sum);
+}
+
+int mopt_compute_cost(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x, double* sum) {
+  MOPT_REQUIRE(ctx && store && store->ctx == ctx, "store does not belong to this context");
+  MOPT_TRY(validate_problem(store, problem, false));
+  MOPT_TRY(enqueue_pass(ctx, store, problem, x, PASS_COST));
+  return fetch_result(ctx, problem->num_parameters, nullptr, nullptr, sum);
+}
+
+int mopt_linearize_async(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x) {
+  MOPT_REQUIRE(ctx && store && store->ctx == ctx, "store does not belong to this context");
+  MOPT_TRY(validate_problem(store, problem, true));
+  return enqueue_pass(ctx, store, problem, x, PASS_LINEARIZE);
+}
+
+int mopt_ctx_result(mopt_ctx* ctx, int num_parameters, double* H, double* b, double* sum) {
+  MOPT_REQUIRE(ctx, "null ctx");
+  MOPT_REQUIRE(num_parameters >= 0 && num_parameters <= kMaxP, "bad num_parameters");
+  MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
+  return fetch_result(ctx, num_parameters, H, b, sum);
+}
+
+int mopt_upload_and_linearize(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const void* host_a,
+                              const void* host_b, int host_dtype, int64_t count, const double* x, double* H, double* b,
+                              double* sum) {
+  MOPT_REQUIRE(ctx && store && store->ctx == ctx, "store does not belong to this context");
+  MOPT_TRY(validate_problem(store, problem, true));
+  MOPT_REQUIRE(count == store->n, "count must equal the store size");
+  MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
+  MOPT_TRY(store_upload_async(store, 0, host_a, host_dtype, 0, 0, count));
+  MOPT_TRY(store_upload_async(store, 1, host_b, host_dtype, 0, 0, count));
+  MOPT_TRY(enqueue_pass(ctx, store, problem, x, PASS_LINEARIZE));
+  return fetch_result(ctx, problem->num_parameters, H, b, sum);
+}
+
+void mopt_lm_default_options(mopt_lm_options* o) {
+  if (!o) return;
+  o->max_iterations = 15;       // optimizer.h:19
+  o->lm_max_iterations = 3;     // levenberg_marquadt_dyn.cpp:9
+  o->lambda_factor = 1e-9;      // levenberg_marquadt_dyn.cpp:16
+  o->scalar_dtype = MOPT_F64;
+  o->speculative = 1;
+}
+
+int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, const mopt_problem* problems,
+                     const mopt_lm_options* options, double* x, mopt_lm_report* report) {
+  MOPT_REQUIRE(ctx && stores && problems && x && report, "null argument");
+  if (n_costs <= 0) {
+    // Optimizer::checkCosts, optimizer.h:48-54
+    set_last_error("No cost function added!");
+    return MOPT_ERR_INVALID_ARGUMENT;
+  }
+  MOPT_REQUIRE(n_costs <= MOPT_MAX_COSTS, "too many cost terms");
+  mopt_lm_options opt;
+  if (options) opt = *options; else mopt_lm_default_options(&opt);
+  MOPT_REQUIRE(opt.max_iterations >= 0, "Optimization::max_iterations cannot be less than 0.");  // optimizer.h:34-35
+  MOPT_REQUIRE(opt.lm_max_iterations >= 0, "lm_max_iterations cannot be negative");
+  const int P = problems[0].num_parameters;
+  MOPT_REQUIRE(P > 0 && P <= kMaxP, "bad num_parameters");
+  for (int c = 0; c < n_costs; ++c) {
+    MOPT_REQUIRE(stores[c] && stores[c]->ctx == ctx, "store does not belong to this context");
+    MOPT_TRY(validate_problem(stores[c], &problems[c], true));
+    MOPT_REQUIRE(problems[c].num_parameters == P, "all cost terms must share the parameter vector");
+  }
+  MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
+  std::memset(report, 0, sizeof(*report));
+  if (opt.max_iterations == 0) {
+    report->status = MOPT_MAXIMUM_ITERATIONS_REACHED;
+    return MOPT_OK;
+  }
+  for (int c = 0; c < n_costs; ++c) MOPT_TRY(stage_cost(ctx, c, &problems[c]));
+
+  LmInit in;
+  std::memset(&in, 0, sizeof(in));
+  in.P = P; in.n_costs = n_costs; in.max_it = opt.max_iterations; in.lm_max_it = opt.lm_max_iterations;
+  in.speculative = opt.speculative ? 1 : 0; in.scalar_f32 = (opt.scalar_dtype == MOPT_F32) ? 1 : 0;
+  in.lambda_factor = opt.lambda_factor;
+  for (int i = 0; i < P; ++i) in.x0[i] = x[i];
+  lm_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_slots, in);
+  MOPT_CUDA_TRY(cudaGetLastError());
+
+  // Passes are enqueued in batches, always one batch ahead of the one whose done flag is being
+  // awaited, so the device never idles on the host; every rank reads the flag of the same slot,
+  // so all ranks stop after the same number of (collective-bearing) slots.
+  const int64_t max_slots64 = int64_t(opt.max_iterations) * (int64_t(opt.lm_max_iterations) + 1) + 2;
+  const int max_slots = int(max_slots64 < ctx->flags_capacity ? max_slots64 : ctx->flags_capacity);
+  const int kBatch = 2;
+  int enq = 0;
+  auto enqueue_batch = [&](int par, int* last_slot) -> int {
+    *last_slot = -1;
+    for (int s = 0; s < kBatch && enq < max_slots; ++s, ++enq) {
+      ctx->h_flags[enq] = 0;
+      for (int c = 0; c < n_costs; ++c) MOPT_TRY(launch_pass(ctx, stores[c], &problems[c], c, c > 0 ? 1 : 0, -1));
+      MOPT_TRY(allreduce_trial(ctx, P));
+      lm_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_trial, ctx->d_slots, ctx->d_flags + enq);
+      MOPT_CUDA_TRY(cudaGetLastError());
+      *last_slot = enq;
+    }
+    if (*last_slot >= 0) MOPT_CUDA_TRY(cudaEventRecord(ctx->ev_batch[par], ctx->stream));
+    return MOPT_OK;
+  };
+  int par = 0, cur_last = -1, next_last = -1;
+  MOPT_TRY(enqueue_batch(par, &cur_last));
+  while (cur_last >= 0) {
+    MOPT_TRY(enqueue_batch(par ^ 1, &next_last));  // keep one batch in flight behind the awaited one
+    MOPT_CUDA_TRY(cudaEventSynchronize(ctx->ev_batch[par]));
+    if (reinterpret_cast<volatile int*>(ctx->h_flags)[cur_last] != 0) break;
+    par ^= 1;
+    cur_last = next_last;
+  }
+  MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+
+  // fetch the final state
+  LmState* hs = ctx->h_lm;
+  MOPT_CUDA_TRY(cudaMemcpyAsync(hs, ctx->d_lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
+  MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (!hs->done) {
+    set_last_error("internal error: the LM state machine did not terminate within its slot budget");
+    return MOPT_ERR_CUDA;
+  }
+  for (int i = 0; i < P; ++i) x[i] = hs->x[i];
+  report->status = hs->status;
+  report->executed_iterations = hs->executed;
+  report->num_trials = hs->num_trials < MOPT_MAX_TRACE ? hs->num_trials : MOPT_MAX_TRACE;
+  report->num_passes = hs->num_passes;
+  report->final_cost = hs->cur.v[packed_size(P) - 1];
+  std::memcpy(report->trials, hs->trials, sizeof(mopt_lm_trial) * size_t(report->num_trials));
+  return MOPT_OK;
+}
+
+int mopt_so3_convert6dof(const double* x, double* T) {
+  MOPT_REQUIRE(x && T, "null argument");
+  // src/so3.cpp:7-19,43-57 (host-side helper kept for API parity; the device copy is so3_exp_dev)
+  const double w[3] = {x[3], x[4], x[5]};
+  const double n = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (n > 10.0 * 2.220446049250313e-16) {
+    const double a[3] = {w[0] / n, w[1] / n, w[2] / n};
+    const double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+    const double s = std::sin(n), c = std::cos(n);
+    for (int r = 0; r < 3; ++r)
+      for (int col = 0; col < 3; ++col) {
+        double kk = 0;
+        for (int k = 0; k < 3; ++k) kk += K[r * 3 + k] * K[k * 3 + col];
+        R[r * 3 + col] += s * K[r * 3 + col] + (1.0 - c) * kk;
+      }
+  }
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) T[r * 4 + c] = R[r * 3 + c];
+    T[r * 4 + 3] = x[r];
+  }
+  T[12] = T[13] = T[14] = 0.0;
+  T[15] = 1.0;
+  return MOPT_OK;
+}
+
+// Runs the DEVICE LDL^T (the one the LM step kernel uses) on one thread; for tests.
+int mopt_ldlt_solve(int n, const double* A, const double* rhs, double* out) {
+  MOPT_REQUIRE(n >= 1 && n <= kMaxP && A && rhs && out, "bad argument");
+  double *dA = nullptr, *dr = nullptr, *dout = nullptr;
+  MOPT_CUDA_TRY(cudaMalloc(&dA, sizeof(double) * n * n));
+  MOPT_CUDA_TRY(cudaMalloc(&dr, sizeof(double) * n));
+  MOPT_CUDA_TRY(cudaMalloc(&dout, sizeof(double) * n));
+  MOPT_CUDA_TRY(cudaMemcpy(dA, A, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+  MOPT_CUDA_TRY(cudaMemcpy(dr, rhs, sizeof(double) * n, cudaMemcpyHostToDevice));
+  ldlt_test_kernel<<<1, 1>>>(n, dA, dr, dout);
+  MOPT_CUDA_TRY(cudaGetLastError());
+  MOPT_CUDA_TRY(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dr); cudaFree(dout);
+  return MOPT_OK;
+}
+
+int mopt_host_alloc(void** ptr, uint64_t bytes) {
+  MOPT_REQUIRE(ptr, "null ptr");
+  MOPT_CUDA_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return MOPT_OK;
+}
+
+int mopt_host_free(void* ptr) {
+  if (ptr) MOPT_CUDA_TRY(cudaFreeHost(ptr));
+  return MOPT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Host-side internals shared by the translation units of libmopt_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "mopt_common.cuh"
+#include "mopt_lm.cuh"
+#include "mopt_models.cuh"
+#include "mopt_pass.cuh"
+
+struct mopt_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  // pass plumbing
+  double* d_partials = nullptr;      // [kPackedMaxRaw][kMaxGrid]
+  unsigned int* d_ticket = nullptr;
+  mopt::PassResult* d_trial = nullptr;
+  mopt::CostSlot* d_slots = nullptr; // [MOPT_MAX_COSTS]
+  mopt::LmState* d_lm = nullptr;
+  // pinned host mirrors
+  mopt::PassResult* h_result = nullptr;
+  mopt::LmState* h_lm = nullptr;
+  mopt::CostSlot* h_slot = nullptr;  // staging for cost constants
+  int* h_flags = nullptr;            // per-slot done flags written by lm_step_kernel (mapped)
+  int* d_flags = nullptr;            // device alias of h_flags
+  int flags_capacity = 0;
+  mopt::CostDev cached_cost[MOPT_MAX_COSTS];
+  bool cached_valid[MOPT_MAX_COSTS] = {false};
+  // upload staging (device, double buffered) + events
+  void* d_stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  cudaEvent_t ev_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_batch[2] = {nullptr, nullptr};
+  // launch tuning
+  int ctas_per_sm = 0;
+  int threads = 0;
+  // sharding
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+struct mopt_store {
+  mopt_ctx* ctx = nullptr;
+  int model = 0;
+  int dtype = 0;
+  int64_t n = 0;
+  int nstreams = 0;
+  void* streams[mopt::kMaxStreams] = {nullptr};
+};
+
+namespace mopt {
+
+struct PassLaunch {
+  cudaStream_t stream;
+  int num_sms;
+  int ctas_per_sm;  // 0 = occupancy-derived default
+};
+
+// mopt_pass_p2p.cu
+int launch_p2p_moment(const PassLaunch& L, int store_dtype, int compute_dtype, int loss, bool qrot, const PassArgs& a);
+// mopt_pass_dense.cu
+int launch_dense(const PassLaunch& L, int model, bool numeric, int store_dtype, int compute_dtype, const PassArgs& a);
+
+int pick_grid(const void* kernel, int threads, const PassLaunch& L, int64_t work_items);
+
+}  // namespace mopt

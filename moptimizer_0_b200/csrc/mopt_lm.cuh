@@ -1,0 +1,234 @@
+// Device-resident Levenberg-Marquardt state machine.
+// Restates LevenbergMarquadtDynamic<Scalar>::minimize (src/levenberg_marquadt_dyn.cpp:34-119) as a
+// one-warp kernel that runs between pass kernels: it consumes the packed (H, b, sum) a pass wrote,
+// decides accept / reject / terminate, solves the damped system with an LDL^T restated from
+// Eigen::LDLT (pivoted, Eigen 3.4 Cholesky/LDLT.h), proposes x + delta, runs model setup for it and
+// sets the control word the next pass kernel obeys.  No host round trip per iteration.
+#pragma once
+
+#include "mopt_common.cuh"
+#include "mopt_setup.cuh"
+
+namespace mopt {
+
+enum LmPhase : int { LM_PHASE_LIN = 0, LM_PHASE_TRIAL = 1 };
+
+struct CostSlot {
+  CostDev cost;
+  ParamBlock pb;
+};
+
+struct LmState {
+  // configuration (written by lm_init_kernel)
+  int P, n_costs, max_it, lm_max_it, speculative, scalar_f32;
+  double lambda_factor;
+  // optimizer state
+  double x[kMaxP], xi[kMaxP], delta[kMaxP], x_eval[kMaxP];
+  PassResult cur;  // accepted linearization at x
+  double lambda, nu;
+  int it, k, phase, status, done, executed, num_trials, num_passes;
+  int pass_mode;  // PassMode control word read by the pass kernels
+  int pad_;
+  mopt_lm_trial trials[MOPT_MAX_TRACE];
+};
+
+#ifdef __CUDACC__
+
+// Eigen 3.4 LDLT restated: in-place L D L^T of the lower triangle with symmetric diagonal pivoting
+// (largest |a_kk|), left-looking column update; solve x = P^T L^-T D^+ L^-1 P b, D^+ with tolerance
+// numeric_limits::min().  A column-major n x n (overwritten), n <= kMaxP.
+template <typename S>
+__device__ inline void ldlt_solve_dev(int n, S* A, const S* rhs, S* out) {
+  int tr[kMaxP];
+  S tmp[kMaxP], y[kMaxP];
+#define MOPT_A(r, c) A[(r) + (c) * n]
+  bool zero_matrix = false;
+  for (int k = 0; k < n && !zero_matrix; ++k) {
+    int piv = k;
+    S best = fabs(MOPT_A(k, k));
+    for (int i = k + 1; i < n; ++i) {
+      const S v = fabs(MOPT_A(i, i));
+      if (v > best) { best = v; piv = i; }
+    }
+    tr[k] = piv;
+    if (piv != k) {
+      for (int c = 0; c < k; ++c) { const S t = MOPT_A(k, c); MOPT_A(k, c) = MOPT_A(piv, c); MOPT_A(piv, c) = t; }
+      for (int r = piv + 1; r < n; ++r) { const S t = MOPT_A(r, k); MOPT_A(r, k) = MOPT_A(r, piv); MOPT_A(r, piv) = t; }
+      { const S t = MOPT_A(k, k); MOPT_A(k, k) = MOPT_A(piv, piv); MOPT_A(piv, piv) = t; }
+      for (int i = k + 1; i < piv; ++i) { const S t = MOPT_A(i, k); MOPT_A(i, k) = MOPT_A(piv, i); MOPT_A(piv, i) = t; }
+    }
+    if (k > 0) {
+      for (int c = 0; c < k; ++c) tmp[c] = MOPT_A(c, c) * MOPT_A(k, c);
+      S s = S(0);
+      for (int c = 0; c < k; ++c) s += MOPT_A(k, c) * tmp[c];
+      MOPT_A(k, k) -= s;
+      for (int r = k + 1; r < n; ++r) {
+        S t = S(0);
+        for (int c = 0; c < k; ++c) t += MOPT_A(r, c) * tmp[c];
+        MOPT_A(r, k) -= t;
+      }
+    }
+    const S akk = MOPT_A(k, k);
+    const bool valid = fabs(akk) > S(0);
+    if (k == 0 && !valid) {
+      for (int j = 0; j < n; ++j) tr[j] = j;
+      zero_matrix = true;
+      break;
+    }
+    if (valid)
+      for (int r = k + 1; r < n; ++r) MOPT_A(r, k) /= akk;
+  }
+  for (int i = 0; i < n; ++i) y[i] = rhs[i];
+  for (int k = 0; k < n; ++k) { const S t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < r; ++c) y[r] -= MOPT_A(r, c) * y[c];
+  const S tol = (sizeof(S) == 4) ? S(1.17549435e-38) : S(2.2250738585072014e-308);
+  for (int i = 0; i < n; ++i) y[i] = (fabs(MOPT_A(i, i)) > tol) ? y[i] / MOPT_A(i, i) : S(0);
+  for (int r = n - 1; r >= 0; --r)
+    for (int c = r + 1; c < n; ++c) y[r] -= MOPT_A(c, r) * y[c];
+  for (int k = n - 1; k >= 0; --k) { const S t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+  for (int i = 0; i < n; ++i) out[i] = y[i];
+#undef MOPT_A
+}
+
+template <typename S>
+__device__ inline S scalar_eps() { return (sizeof(S) == 4) ? S(1.1920928955078125e-07) : S(2.220446049250313e-16); }
+
+// include/moptimizer/optimizer.h:26-29
+template <typename S>
+__device__ inline bool is_cost_small(S c) { return fabs(c) < S(8) * scalar_eps<S>(); }
+
+__device__ inline void lm_finish(LmState* st, int status) {
+  st->status = status;
+  st->executed = st->it;
+  st->done = 1;
+  st->pass_mode = PASS_SKIP;
+}
+
+// Solve (H + lambda diag(H)) delta = -b (levenberg_marquadt_dyn.cpp:65,78-80), xi = x + delta (:83).
+template <typename S>
+__device__ inline void lm_solve_propose(LmState* st) {
+  const int P = st->P;
+  S A[kMaxP * kMaxP], nb[kMaxP], d[kMaxP];
+  for (int r = 0; r < P; ++r)
+    for (int c = r; c < P; ++c) {
+      const S h = S(st->cur.v[tri_index(P, r, c)]);
+      A[r + c * P] = h;
+      A[c + r * P] = h;
+    }
+  const S lam = S(st->lambda);
+  for (int i = 0; i < P; ++i) A[i + i * P] = A[i + i * P] + lam * A[i + i * P];
+  for (int i = 0; i < P; ++i) nb[i] = -S(st->cur.v[P * (P + 1) / 2 + i]);
+  ldlt_solve_dev<S>(P, A, nb, d);
+  for (int i = 0; i < P; ++i) {
+    st->delta[i] = double(d[i]);
+    const S xi = S(st->x[i]) + d[i];
+    st->xi[i] = double(xi);
+    st->x_eval[i] = double(xi);
+  }
+  st->phase = LM_PHASE_TRIAL;
+  st->pass_mode = st->speculative ? PASS_LINEARIZE : PASS_COST;
+}
+
+// One transition of the optimizer.  Returns 1 if a new evaluation point x_eval was set (the caller then
+// runs model setup for every cost), 0 if the optimization ended.
+template <typename S>
+__device__ inline int lm_step_thread(LmState* st, const PassResult* trial) {
+  if (st->done) return 0;
+  const int P = st->P;
+  const int npk = packed_size(P);
+  st->num_passes += 1;
+  if (st->phase == LM_PHASE_LIN) {
+    for (int i = 0; i < npk; ++i) st->cur.v[i] = trial->v[i];
+  } else {
+    const S yi = S(trial->v[npk - 1]);
+    const S y0 = S(st->cur.v[npk - 1]);
+    if (isnan(yi)) {  // :88-91
+      lm_finish(st, MOPT_NUMERIC_ERROR);
+      return 0;
+    }
+    const S lam = S(st->lambda);
+    S den = S(0);
+    for (int i = 0; i < P; ++i) {
+      const S d = S(st->delta[i]);
+      den += d * (lam * d - S(st->cur.v[P * (P + 1) / 2 + i]));
+    }
+    const S rho = (y0 - yi) / den;  // :93
+    if (st->num_trials < MOPT_MAX_TRACE) {
+      mopt_lm_trial& t = st->trials[st->num_trials];
+      t.outer_iteration = st->it; t.k = st->k; t.accepted = !(rho < S(0)); t.reserved = 0;
+      t.y0 = double(y0); t.yi = double(yi); t.rho = double(rho); t.lambda = st->lambda; t.nu = st->nu;
+    }
+    st->num_trials += 1;
+    if (rho < S(0)) {  // :97-110 (a NaN rho compares false and is accepted, as in the reference)
+      S m = S(0);
+      for (int i = 0; i < P; ++i) m = fmax(m, fabs(S(st->delta[i])));
+      if (m < sqrt(scalar_eps<S>())) {  // isDeltaSmall, delta.h:11-16
+        lm_finish(st, is_cost_small<S>(yi) ? MOPT_CONVERGED : MOPT_SMALL_DELTA);
+        return 0;
+      }
+      st->lambda = double(S(st->nu) * lam);
+      st->nu = double(S(2) * S(st->nu));
+      st->k += 1;
+      if (st->k < st->lm_max_it) {
+        lm_solve_propose<S>(st);
+        return 1;
+      }
+      // inner tries exhausted: the outer loop re-linearizes at the unchanged x (identical H, b, y0)
+      st->it += 1;
+      if (st->it >= st->max_it) {
+        lm_finish(st, MOPT_MAXIMUM_ITERATIONS_REACHED);
+        return 0;
+      }
+    } else {  // :112-114
+      for (int i = 0; i < P; ++i) st->x[i] = st->xi[i];
+      const double f = fmax(1.0 / 3.0, 1.0 - pow(double(S(2) * rho - S(1)), 3.0));
+      st->lambda = double(S(double(lam) * f));
+      st->it += 1;
+      if (st->it >= st->max_it) {
+        if (st->speculative)
+          for (int i = 0; i < npk; ++i) st->cur.v[i] = trial->v[i];
+        else
+          st->cur.v[npk - 1] = trial->v[npk - 1];
+        lm_finish(st, MOPT_MAXIMUM_ITERATIONS_REACHED);
+        return 0;
+      }
+      if (st->speculative) {
+        for (int i = 0; i < npk; ++i) st->cur.v[i] = trial->v[i];
+      } else {
+        st->cur.v[npk - 1] = trial->v[npk - 1];
+        for (int i = 0; i < P; ++i) st->x_eval[i] = st->x[i];
+        st->phase = LM_PHASE_LIN;
+        st->pass_mode = PASS_LINEARIZE;
+        return 1;
+      }
+    }
+  }
+  // start of an outer iteration (:62-77) with (H, b, y0) = cur
+  for (;;) {
+    const S y0 = S(st->cur.v[npk - 1]);
+    if (is_cost_small<S>(y0)) {
+      lm_finish(st, MOPT_CONVERGED);
+      return 0;
+    }
+    if (st->lambda < 0.0) {
+      S mx = S(0);
+      for (int i = 0; i < P; ++i) mx = fmax(mx, fabs(S(st->cur.v[tri_index(P, i, i)])));
+      st->lambda = double(S(st->lambda_factor) * mx);
+    }
+    st->nu = 2.0;
+    st->k = 0;
+    if (st->lm_max_it > 0) {
+      lm_solve_propose<S>(st);
+      return 1;
+    }
+    st->it += 1;
+    if (st->it >= st->max_it) {
+      lm_finish(st, MOPT_MAXIMUM_ITERATIONS_REACHED);
+      return 0;
+    }
+  }
+}
+
+#endif  // __CUDACC__
+}  // namespace mopt

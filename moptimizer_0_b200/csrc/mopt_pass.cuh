@@ -1,0 +1,471 @@
+// Pass kernels: one full sweep over a store's residuals, fused
+//   residual -> (analytical | finite-difference) Jacobian -> robust-loss weight ->
+//   upper-triangular H / b / sum(r^T r) accumulation in registers ->
+//   warp (transposing shuffle) -> CTA (shared memory) -> grid (last-CTA-done) reduction.
+// Replaces the loops of CostComputation::{computeHessian, computeHessianNumerical, computeCost,
+// parallelComputeCost} (include/moptimizer/linearization.h:36-158).
+#pragma once
+
+#include "mopt_common.cuh"
+
+namespace mopt {
+
+struct PassArgs {
+  StreamPtrs streams;
+  int64_t n;                 // residuals in this store (this rank's shard)
+  const ParamBlock* pb;      // setup(x) result (device)
+  const CostDev* cost;       // cost constants (device)
+  double* partials;          // [nraw][gridDim.x] per-CTA partial sums
+  unsigned int* ticket;      // last-CTA-done counter (self-resetting)
+  PassResult* out;           // packed (H upper, b, sum)
+  int accumulate;            // 1: out += this pass (second and later cost terms)
+  const int* mode_ptr;       // device control word (PassMode), used when mode_override < 0
+  int mode_override;
+};
+
+#ifdef __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// CTA + grid reduction shared by all pass kernels.
+//   lane_val[ch]: this warp's total of raw sum (ch*32 + owner index), held by the owner lane
+//   NRAW raw sums; V = values per transposing-reduce chunk (power of two <= 32)
+// After the call, in the LAST CTA only, s_tot[0..NRAW) holds the grid totals (fp64) and the
+// function returns true for every thread of that CTA.
+template <int NRAW, int V, int NCH, int THREADS>
+__device__ __forceinline__ bool grid_reduce(const double (&lane_val)[NCH], const PassArgs& a, double* s_tot,
+                                            double* s_warp /* [THREADS/32][NCH*V] */) {
+  constexpr int NW = THREADS / 32;
+  constexpr int SHIFT = 5 - Log2<V>::value;  // owner lane of index i is (i << SHIFT)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ bool s_last;
+  if ((lane & ((1 << SHIFT) - 1)) == 0) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) s_warp[warp * (NCH * V) + ch * V + (lane >> SHIFT)] = lane_val[ch];
+  }
+  __syncthreads();
+  const int G = gridDim.x;
+  for (int i = threadIdx.x; i < NRAW; i += THREADS) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += s_warp[w * (NCH * V) + i];
+    a.partials[size_t(i) * G + blockIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(a.ticket, 1u);
+    s_last = (t == unsigned(G - 1));
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  // fixed-order reduction of the G per-CTA partials: lanes stride over CTAs, xor-butterfly combine
+  for (int i = warp; i < NRAW; i += NW) {
+    const volatile double* p = a.partials + size_t(i) * G;
+    double s = 0.0;
+    for (int c = lane; c < G; c += 32) s += p[c];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += shfl_xor(s, o);
+    if (lane == 0) s_tot[i] = s;
+  }
+  if (threadIdx.x == 0) *a.ticket = 0u;  // ready for the next launch (stream-ordered)
+  __syncthreads();
+  return true;
+}
+
+// =============================================================================================
+// Point-to-point, analytical Jacobian: moment kernel.
+//
+// Every analytical Jacobian of this model is affine in a 3-vector q (q = R p for the exact form,
+// q = p for the reference-test forms):  J = J0 + q_x J1 + q_y J2 + q_z J3.  Hence
+//   H = sum w J^T C J  and  b = sum w J^T C r
+// are linear in the 23 moments
+//   Sw, Sw q (3), Sw q q^T (6), Sw r (3), Sw q r^T (9), S r^T r (1)
+// which is all the streaming loop accumulates (~50 FMA per correspondence instead of ~110 for the
+// dense 3x6 update); the last CTA assembles the packed 6x6 H and b from them in fp64.
+// Raw layout: [0]=Sw [1..3]=Swq [4..9]=Swqq(xx,xy,xz,yy,yz,zz) [10..12]=Swr [13..21]=Swqr(row q, col r) [22]=Se2
+// =============================================================================================
+constexpr int kP2PRaw = 23;
+
+template <typename CT, int LOSS, bool QROT>
+__device__ __forceinline__ void p2p_moments(const CT (&R)[9], const CT (&t)[3], CT lossp, CT px, CT py, CT pz,
+                                            CT yx, CT yy, CT yz, CT (&acc)[32]) {
+  // q = R p ; r = (q + t) - y          (tst/point2point.cpp:41-44)
+  const CT q0 = fma(R[0], px, fma(R[1], py, R[2] * pz));
+  const CT q1 = fma(R[3], px, fma(R[4], py, R[5] * pz));
+  const CT q2 = fma(R[6], px, fma(R[7], py, R[8] * pz));
+  const CT r0 = (q0 + t[0]) - yx;
+  const CT r1 = (q1 + t[1]) - yy;
+  const CT r2 = (q2 + t[2]) - yz;
+  const CT e2 = fma(r0, r0, fma(r1, r1, r2 * r2));
+  const CT w = loss_weight<CT>(LOSS, lossp, e2);
+  const CT a0 = QROT ? q0 : px, a1 = QROT ? q1 : py, a2 = QROT ? q2 : pz;
+  const CT w0 = w * a0, w1 = w * a1, w2 = w * a2;
+  acc[0] += w;
+  acc[1] += w0; acc[2] += w1; acc[3] += w2;
+  acc[4] = fma(w0, a0, acc[4]); acc[5] = fma(w0, a1, acc[5]); acc[6] = fma(w0, a2, acc[6]);
+  acc[7] = fma(w1, a1, acc[7]); acc[8] = fma(w1, a2, acc[8]); acc[9] = fma(w2, a2, acc[9]);
+  acc[10] = fma(w, r0, acc[10]); acc[11] = fma(w, r1, acc[11]); acc[12] = fma(w, r2, acc[12]);
+  acc[13] = fma(w0, r0, acc[13]); acc[14] = fma(w0, r1, acc[14]); acc[15] = fma(w0, r2, acc[15]);
+  acc[16] = fma(w1, r0, acc[16]); acc[17] = fma(w1, r1, acc[17]); acc[18] = fma(w1, r2, acc[18]);
+  acc[19] = fma(w2, r0, acc[19]); acc[20] = fma(w2, r1, acc[20]); acc[21] = fma(w2, r2, acc[21]);
+  acc[22] += e2;
+}
+
+template <typename CT>
+__device__ __forceinline__ void p2p_cost_only(const CT (&R)[9], const CT (&t)[3], CT px, CT py, CT pz, CT yx,
+                                              CT yy, CT yz, CT (&acc)[32]) {
+  const CT r0 = (fma(R[0], px, fma(R[1], py, R[2] * pz)) + t[0]) - yx;
+  const CT r1 = (fma(R[3], px, fma(R[4], py, R[5] * pz)) + t[1]) - yy;
+  const CT r2 = (fma(R[6], px, fma(R[7], py, R[8] * pz)) + t[2]) - yz;
+  acc[22] += fma(r0, r0, fma(r1, r1, r2 * r2));
+}
+
+// Assemble packed (H upper, b, sum) of the 6-parameter problem from the 23 moment totals.
+__device__ inline void p2p_assemble(const double* tot, const ParamBlock* pb, const CostDev* cost, PassResult* out,
+                                    int accumulate, int tid, int nthreads) {
+  constexpr int P = 6;
+  // augmented moment matrix Mt (4x4, q~ = (1, q)) and St (4x3) = sum w q~ r^T
+  double Mt[4][4], St[4][3], C[9];
+  Mt[0][0] = tot[0];
+  for (int k = 0; k < 3; ++k) Mt[0][k + 1] = Mt[k + 1][0] = tot[1 + k];
+  Mt[1][1] = tot[4]; Mt[1][2] = Mt[2][1] = tot[5]; Mt[1][3] = Mt[3][1] = tot[6];
+  Mt[2][2] = tot[7]; Mt[2][3] = Mt[3][2] = tot[8]; Mt[3][3] = tot[9];
+  for (int m = 0; m < 3; ++m) St[0][m] = tot[10 + m];
+  for (int k = 0; k < 3; ++k)
+    for (int m = 0; m < 3; ++m) St[k + 1][m] = tot[13 + k * 3 + m];
+  for (int i = 0; i < 9; ++i) C[i] = cost->has_cov ? cost->cov[i] : ((i % 4 == 0) ? 1.0 : 0.0);
+  const int npk = packed_size(P);
+  for (int e = tid; e < npk; e += nthreads) {
+    double val = 0.0;
+    if (e < P * (P + 1) / 2) {
+      // decode (i, j) of the packed upper triangle
+      int i = 0, rem = e;
+      while (rem >= P - i) { rem -= P - i; ++i; }
+      const int j = i + rem;
+      for (int k = 0; k < 4; ++k)
+        for (int l = 0; l < 4; ++l) {
+          double s = 0.0;
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) s += pb->jaff[k][a * 6 + i] * C[a + 3 * b] * pb->jaff[l][b * 6 + j];
+          val += Mt[k][l] * s;
+        }
+    } else if (e < npk - 1) {
+      const int i = e - P * (P + 1) / 2;
+      for (int k = 0; k < 4; ++k)
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) val += pb->jaff[k][a * 6 + i] * C[a + 3 * b] * St[k][b];
+    } else {
+      val = tot[22];
+    }
+    out->v[e] = accumulate ? out->v[e] + val : val;
+  }
+}
+
+template <typename ST, typename CT, int LOSS, bool QROT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArgs a) {
+  const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
+  if (mode == PASS_SKIP) return;
+  constexpr int VEC = VecOf<ST>::N;
+  constexpr bool kFp32Acc = (sizeof(CT) == 4);
+  constexpr int FLUSH_ROUNDS = 8;  // fp32 partials are folded into fp64 every 8*VEC residuals/thread
+
+  __shared__ double s_warp[(THREADS / 32) * 32];
+  __shared__ double s_tot[32];
+
+  CT R[9], t[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = CT(a.pb->sets[0][i]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t[i] = CT(a.pb->sets[0][9 + i]);
+  const CT lossp = CT(a.cost->loss_param);
+
+  const ST* __restrict__ sx = static_cast<const ST*>(a.streams.p[0]);
+  const ST* __restrict__ sy = static_cast<const ST*>(a.streams.p[1]);
+  const ST* __restrict__ sz = static_cast<const ST*>(a.streams.p[2]);
+  const ST* __restrict__ tx = static_cast<const ST*>(a.streams.p[3]);
+  const ST* __restrict__ ty = static_cast<const ST*>(a.streams.p[4]);
+  const ST* __restrict__ tz = static_cast<const ST*>(a.streams.p[5]);
+
+  CT acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = CT(0);
+  double dacc[1] = {0.0};
+
+  const int64_t ngroups = a.n / VEC;
+  const int64_t stride = int64_t(gridDim.x) * THREADS;
+  const int64_t full_rounds = ngroups / stride;
+  const int64_t g0 = int64_t(blockIdx.x) * THREADS + threadIdx.x;
+
+  auto flush = [&]() {
+    const CT v = warp_reduce_transpose<32>(acc);
+    dacc[0] += double(v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = CT(0);
+  };
+
+  auto do_group = [&](int64_t g) {
+    CT px[VEC], py[VEC], pz[VEC], qx[VEC], qy[VEC], qz[VEC];
+    load_vec<ST, CT>(sx, g, px); load_vec<ST, CT>(sy, g, py); load_vec<ST, CT>(sz, g, pz);
+    load_vec<ST, CT>(tx, g, qx); load_vec<ST, CT>(ty, g, qy); load_vec<ST, CT>(tz, g, qz);
+    if (mode == PASS_COST) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) p2p_cost_only<CT>(R, t, px[e], py[e], pz[e], qx[e], qy[e], qz[e], acc);
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e)
+        p2p_moments<CT, LOSS, QROT>(R, t, lossp, px[e], py[e], pz[e], qx[e], qy[e], qz[e], acc);
+    }
+  };
+
+  int since_flush = 0;
+  int64_t r = 0;
+  // two grid-stride rounds per iteration: 12 independent 16-byte loads in flight per thread
+  for (; r + 1 < full_rounds; r += 2) {
+    CT px[2][VEC], py[2][VEC], pz[2][VEC], qx[2][VEC], qy[2][VEC], qz[2][VEC];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t g = g0 + (r + u) * stride;
+      load_vec<ST, CT>(sx, g, px[u]); load_vec<ST, CT>(sy, g, py[u]); load_vec<ST, CT>(sz, g, pz[u]);
+      load_vec<ST, CT>(tx, g, qx[u]); load_vec<ST, CT>(ty, g, qy[u]); load_vec<ST, CT>(tz, g, qz[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (mode == PASS_COST) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          p2p_cost_only<CT>(R, t, px[u][e], py[u][e], pz[u][e], qx[u][e], qy[u][e], qz[u][e], acc);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          p2p_moments<CT, LOSS, QROT>(R, t, lossp, px[u][e], py[u][e], pz[u][e], qx[u][e], qy[u][e], qz[u][e], acc);
+      }
+    }
+    if (kFp32Acc) {
+      since_flush += 2;
+      if (since_flush >= FLUSH_ROUNDS) {
+        flush();
+        since_flush = 0;
+      }
+    }
+  }
+  for (; r < full_rounds; ++r) do_group(g0 + r * stride);
+  {  // ragged last round + scalar tail (n % VEC residuals)
+    const int64_t g = g0 + full_rounds * stride;
+    if (g < ngroups) do_group(g);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      for (int64_t i = ngroups * VEC; i < a.n; ++i) {
+        if (mode == PASS_COST)
+          p2p_cost_only<CT>(R, t, CT(sx[i]), CT(sy[i]), CT(sz[i]), CT(tx[i]), CT(ty[i]), CT(tz[i]), acc);
+        else
+          p2p_moments<CT, LOSS, QROT>(R, t, lossp, CT(sx[i]), CT(sy[i]), CT(sz[i]), CT(tx[i]), CT(ty[i]), CT(tz[i]), acc);
+      }
+    }
+  }
+  flush();
+
+  if (!grid_reduce<kP2PRaw, 32, 1, THREADS>(dacc, a, s_tot, s_warp)) return;
+  if (mode == PASS_COST) {
+    if (threadIdx.x == 0) {
+      const int e = packed_size(6) - 1;
+      a.out->v[e] = a.accumulate ? a.out->v[e] + s_tot[22] : s_tot[22];
+    }
+  } else {
+    p2p_assemble(s_tot, a.pb, a.cost, a.out, a.accumulate, threadIdx.x, THREADS);
+  }
+}
+
+// =============================================================================================
+// Generic dense pass kernel for any builtin model: analytical (model f_df) or finite-difference
+// Jacobian in registers, optional O x O covariance, packed upper-triangular accumulation.
+// Raw layout == packed layout: H upper (row-major), b, sum.
+// =============================================================================================
+template <class M, typename ST, typename CT, bool NUMERIC, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArgs a) {
+  const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
+  if (mode == PASS_SKIP) return;
+  constexpr int P = M::P, O = M::O, NS = M::NS;
+  constexpr int VEC = VecOf<ST>::N;
+  constexpr int NRAW = P * (P + 1) / 2 + P + 1;
+  constexpr int V = next_pow2(NRAW);
+  static_assert(V <= 32, "dense_pass_kernel: packed size must fit one transposing-reduce chunk");
+  constexpr bool kFp32Acc = (sizeof(CT) == 4);
+  constexpr int FLUSH_ROUNDS = 8;
+  constexpr int NSETS = 1 + 2 * (P > 0 ? P : 0);
+  constexpr int SETN = M::SETN > 0 ? M::SETN : 1;
+
+  __shared__ double s_warp[(THREADS / 32) * V];
+  __shared__ double s_tot[V];
+  __shared__ CT s_sets[NSETS][SETN];
+  __shared__ CT s_invh[P > 0 ? P : 1];
+  __shared__ CT s_cov[O * O];
+
+  const int jac = a.cost->jacobian;
+  const bool central = (jac == MOPT_JAC_CENTRAL);
+  const int nsets = !NUMERIC ? 1 : (central ? 1 + 2 * P : 1 + P);
+  for (int i = threadIdx.x; i < nsets * SETN; i += THREADS) s_sets[i / SETN][i % SETN] = CT(a.pb->sets[i / SETN][i % SETN]);
+  for (int i = threadIdx.x; i < P; i += THREADS)
+    s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
+  const bool has_cov = a.cost->has_cov != 0;
+  for (int i = threadIdx.x; i < O * O; i += THREADS) s_cov[i] = CT(a.cost->cov[i]);
+  const int loss = a.cost->loss;
+  const CT lossp = CT(a.cost->loss_param);
+  __syncthreads();
+
+  const ST* __restrict__ sp[NS > 0 ? NS : 1];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) sp[s] = static_cast<const ST*>(a.streams.p[s]);
+
+  CT acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = CT(0);
+  double dacc[1] = {0.0};
+
+  auto flush = [&]() {
+    const CT v = warp_reduce_transpose<V>(acc);
+    dacc[0] += double(v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = CT(0);
+  };
+
+  // one residual: e[] = its NS stream values
+  auto do_elem = [&](const CT (&e)[NS > 0 ? NS : 1]) {
+    CT r[O];
+    if (mode == PASS_COST) {
+      M::template residual<CT>(s_sets[0], e, r);
+      CT e2 = CT(0);
+#pragma unroll
+      for (int o = 0; o < O; ++o) e2 = fma(r[o], r[o], e2);
+      acc[NRAW - 1] += e2;
+      return;
+    }
+    CT J[O * (P > 0 ? P : 1)];
+    if (NUMERIC) {
+      M::template residual<CT>(s_sets[0], e, r);
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        CT rp[O];
+        M::template residual<CT>(s_sets[1 + j], e, rp);  // perturbed f's bool is ignored, linearization.h:104
+        if (central) {
+          CT rm[O];
+          M::template residual<CT>(s_sets[1 + P + j], e, rm);
+#pragma unroll
+          for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - rm[o]) * s_invh[j];
+        } else {
+#pragma unroll
+          for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - r[o]) * s_invh[j];
+        }
+      }
+    } else {
+      M::template residual_jacobian<CT>(s_sets[0], e, r, J);
+    }
+    CT e2 = CT(0);
+#pragma unroll
+    for (int o = 0; o < O; ++o) e2 = fma(r[o], r[o], e2);
+    const CT w = loss_weight<CT>(loss, lossp, e2);
+    // CJ = C J, Cr = C r  (identity unless setCovariance was called)
+    CT CJ[O * (P > 0 ? P : 1)], Cr[O];
+    if (has_cov) {
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        CT s = CT(0);
+#pragma unroll
+        for (int k = 0; k < O; ++k) s = fma(s_cov[o + k * O], r[k], s);
+        Cr[o] = s;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          CT sj = CT(0);
+#pragma unroll
+          for (int k = 0; k < O; ++k) sj = fma(s_cov[o + k * O], J[k * P + p], sj);
+          CJ[o * P + p] = sj;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        Cr[o] = r[o];
+#pragma unroll
+        for (int p = 0; p < P; ++p) CJ[o * P + p] = J[o * P + p];
+      }
+    }
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      CT wj[O];
+#pragma unroll
+      for (int o = 0; o < O; ++o) wj[o] = w * J[o * P + i];
+#pragma unroll
+      for (int j = i; j < P; ++j) {
+        CT s = acc[idx];
+#pragma unroll
+        for (int o = 0; o < O; ++o) s = fma(wj[o], CJ[o * P + j], s);
+        acc[idx] = s;
+        ++idx;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      CT s = acc[idx];
+#pragma unroll
+      for (int o = 0; o < O; ++o) s = fma(w * J[o * P + i], Cr[o], s);
+      acc[idx] = s;
+      ++idx;
+    }
+    acc[NRAW - 1] += e2;
+  };
+
+  auto do_group = [&](int64_t g) {
+    CT vals[NS > 0 ? NS : 1][VEC];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) load_vec<ST, CT>(sp[s], g, vals[s]);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      CT e[NS > 0 ? NS : 1];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) e[s] = vals[s][v];
+      do_elem(e);
+    }
+  };
+
+  if constexpr (NS == 0) {
+    // data-free model (Powell): `n` identical residual blocks evaluated by thread 0
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      CT e[1] = {CT(0)};
+      for (int64_t i = 0; i < a.n; ++i) do_elem(e);
+    }
+  } else {
+    const int64_t ngroups = a.n / VEC;
+    const int64_t stride = int64_t(gridDim.x) * THREADS;
+    const int64_t full_rounds = ngroups / stride;
+    const int64_t g0 = int64_t(blockIdx.x) * THREADS + threadIdx.x;
+    int since_flush = 0;
+    for (int64_t r = 0; r < full_rounds; ++r) {
+      do_group(g0 + r * stride);
+      if (kFp32Acc && ++since_flush >= FLUSH_ROUNDS) {
+        flush();
+        since_flush = 0;
+      }
+    }
+    const int64_t g = g0 + full_rounds * stride;
+    if (g < ngroups) do_group(g);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      for (int64_t i = ngroups * VEC; i < a.n; ++i) {
+        CT e[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) e[s] = CT(sp[s][i]);
+        do_elem(e);
+      }
+    }
+  }
+  flush();
+
+  if (!grid_reduce<NRAW, V, 1, THREADS>(dacc, a, s_tot, s_warp)) return;
+  if (mode == PASS_COST) {
+    if (threadIdx.x == 0) a.out->v[NRAW - 1] = a.accumulate ? a.out->v[NRAW - 1] + s_tot[NRAW - 1] : s_tot[NRAW - 1];
+  } else {
+    for (int i = threadIdx.x; i < NRAW; i += THREADS) a.out->v[i] = a.accumulate ? a.out->v[i] + s_tot[i] : s_tot[i];
+  }
+}
+
+#endif  // __CUDACC__
+}  // namespace mopt

@@ -1,0 +1,54 @@
+// Instantiations + dispatch of the generic dense pass kernel (mopt_pass.cuh).
+#include "mopt_internal.h"
+
+namespace mopt {
+namespace {
+
+constexpr int kThreads = 256;
+
+template <class M, typename ST, typename CT, bool NUMERIC>
+int launch_one(const PassLaunch& L, const PassArgs& a) {
+  auto kern = dense_pass_kernel<M, ST, CT, NUMERIC, kThreads, 1>;
+  const int64_t groups = (M::NS == 0) ? 1 : a.n / VecOf<ST>::N;
+  const int grid = pick_grid(reinterpret_cast<const void*>(kern), kThreads, L, groups);
+  kern<<<grid, kThreads, 0, L.stream>>>(a);
+  MOPT_CUDA_TRY(cudaGetLastError());
+  return MOPT_OK;
+}
+
+template <class M, bool NUMERIC>
+int launch_types(const PassLaunch& L, int store_dtype, int compute_dtype, const PassArgs& a) {
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F32) return launch_one<M, float, float, NUMERIC>(L, a);
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F64) return launch_one<M, float, double, NUMERIC>(L, a);
+  if (store_dtype == MOPT_F64 && compute_dtype == MOPT_F64) return launch_one<M, double, double, NUMERIC>(L, a);
+  set_last_error("store dtype f64 with compute dtype f32 is not supported");
+  return MOPT_ERR_UNSUPPORTED;
+}
+
+template <class M>
+int launch_model(const PassLaunch& L, bool numeric, int store_dtype, int compute_dtype, const PassArgs& a) {
+  if (numeric) return launch_types<M, true>(L, store_dtype, compute_dtype, a);
+  if (!M::HAS_JAC) {
+    // cost-only passes of Jacobian-free models still come through here with numeric == false
+    return launch_types<M, true>(L, store_dtype, compute_dtype, a);
+  }
+  return launch_types<M, false>(L, store_dtype, compute_dtype, a);
+}
+
+}  // namespace
+
+int launch_dense(const PassLaunch& L, int model, bool numeric, int store_dtype, int compute_dtype, const PassArgs& a) {
+  switch (model) {
+    case MOPT_MODEL_POINT2POINT: return launch_model<P2PModel>(L, numeric, store_dtype, compute_dtype, a);
+    case MOPT_MODEL_EXP_CURVE: return launch_model<ExpCurveModel>(L, numeric, store_dtype, compute_dtype, a);
+    case MOPT_MODEL_MICHAELIS_MENTEN: return launch_model<MichaelisMentenModel>(L, numeric, store_dtype, compute_dtype, a);
+    case MOPT_MODEL_PINHOLE: return launch_model<PinholeModel>(L, numeric, store_dtype, compute_dtype, a);
+    case MOPT_MODEL_POWELL: return launch_model<PowellModel>(L, numeric, store_dtype, compute_dtype, a);
+    case MOPT_MODEL_POINT_DIST: return launch_model<PointDistModel>(L, true, store_dtype, compute_dtype, a);
+    default:
+      set_last_error("unknown model kind");
+      return MOPT_ERR_INVALID_ARGUMENT;
+  }
+}
+
+}  // namespace mopt

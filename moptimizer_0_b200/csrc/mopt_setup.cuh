@@ -1,0 +1,168 @@
+// Device-side `model->setup(x)` (include/moptimizer/model.h:19-22) for the builtin models and
+// for every finite-difference perturbation of x (linearization.h:78-95): turns the parameter
+// vector into the small constant block the pass kernels consume.  Runs on one warp, in fp64,
+// either as its own tiny kernel (host-driven linearize) or inside the LM step kernel.
+#pragma once
+
+#include "mopt_common.cuh"
+
+namespace mopt {
+
+// src/so3.cpp:43-57 — Rodrigues, guard `norm > 10 eps`.  R row-major.
+template <typename S>
+__device__ inline void so3_exp_dev(const double w[3], double R[9]) {
+  const double n = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  const double eps = (sizeof(S) == 4) ? 1.1920928955078125e-07 : 2.220446049250313e-16;
+  if (n > 10.0 * eps) {
+    const double a0 = w[0] / n, a1 = w[1] / n, a2 = w[2] / n;
+    const double K[9] = {0.0, -a2, a1, a2, 0.0, -a0, -a1, a0, 0.0};
+    double sn, cs;
+    sincos(n, &sn, &cs);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        double kk = 0.0;
+        for (int k = 0; k < 3; ++k) kk += K[r * 3 + k] * K[k * 3 + c];
+        R[r * 3 + c] += sn * K[r * 3 + c] + (1.0 - cs) * kk;
+      }
+  }
+}
+
+// Closed-form left Jacobian of SO(3): I + (1-cos)/th^2 [w]x + (th-sin)/th^3 [w]x^2.
+__device__ inline void so3_left_jacobian_dev(const double w[3], double J[9]) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double th = sqrt(th2);
+  double A, B;
+  if (th2 < 1e-8) {
+    A = 0.5 - th2 / 24.0;
+    B = 1.0 / 6.0 - th2 / 120.0;
+  } else {
+    A = (1.0 - cos(th)) / th2;
+    B = (th - sin(th)) / (th2 * th);
+  }
+  const double K[9] = {0.0, -w[2], w[1], w[2], 0.0, -w[0], -w[1], w[0], 0.0};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double kk = 0.0;
+      for (int k = 0; k < 3; ++k) kk += K[r * 3 + k] * K[k * 3 + c];
+      J[r * 3 + c] = (r == c ? 1.0 : 0.0) + A * K[r * 3 + c] + B * kk;
+    }
+}
+
+// One parameter set for model `c.model` at parameters xs[0..P).
+__device__ inline void setup_one_set(const CostDev& c, const double* xs, double* set) {
+  for (int i = 0; i < kSetSize; ++i) set[i] = 0.0;
+  switch (c.model) {
+    case MOPT_MODEL_POINT2POINT: {
+      // so3::convert6DOFParameterToMatrix, src/so3.cpp:7-19: x = [t, omega]
+      const double w[3] = {xs[3], xs[4], xs[5]};
+      if (c.compute_dtype == MOPT_F32) so3_exp_dev<float>(w, set); else so3_exp_dev<double>(w, set);
+      set[9] = xs[0]; set[10] = xs[1]; set[11] = xs[2];
+      break;
+    }
+    case MOPT_MODEL_PINHOLE: {
+      // tst/camera_calibration.cpp:33,37: M = (K * T(x)) * C, 3x4 row-major
+      double R[9];
+      const double w[3] = {xs[3], xs[4], xs[5]};
+      if (c.compute_dtype == MOPT_F32) so3_exp_dev<float>(w, R); else so3_exp_dev<double>(w, R);
+      double T[16];
+      for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 3; ++k) T[r * 4 + k] = R[r * 3 + k];
+        T[r * 4 + 3] = xs[r];
+      }
+      T[12] = T[13] = T[14] = 0.0; T[15] = 1.0;
+      const double* K = c.consts;
+      const double* C = c.consts + 12;
+      double KT[12];
+      for (int r = 0; r < 3; ++r)
+        for (int col = 0; col < 4; ++col) {
+          double s = 0.0;
+          for (int k = 0; k < 4; ++k) s += K[r * 4 + k] * T[k * 4 + col];
+          KT[r * 4 + col] = s;
+        }
+      for (int r = 0; r < 3; ++r)
+        for (int col = 0; col < 4; ++col) {
+          double s = 0.0;
+          for (int k = 0; k < 4; ++k) s += KT[r * 4 + k] * C[k * 4 + col];
+          set[r * 4 + col] = s;
+        }
+      break;
+    }
+    default:  // parameter-only models: the set is x itself
+      for (int i = 0; i < c.P; ++i) set[i] = xs[i];
+      break;
+  }
+}
+
+// Affine decomposition of the point2point analytical Jacobian, J(q) = J0 + q_x J1 + q_y J2 + q_z J3
+// (each 3x6 row-major), for the three variants of mopt_p2p_variant.
+__device__ inline void setup_p2p_affine(const CostDev& c, const double* x, double jaff[4][18]) {
+  double Jl[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (c.variant == MOPT_P2P_EXACT) {
+    const double w[3] = {x[3], x[4], x[5]};
+    so3_left_jacobian_dev(w, Jl);
+  }
+  // -[q]x = q_x E1 + q_y E2 + q_z E3
+  const double E[3][9] = {{0, 0, 0, 0, 0, 1, 0, -1, 0}, {0, 0, -1, 0, 0, 0, 1, 0, 0}, {0, 1, 0, -1, 0, 0, 0, 0, 0}};
+  double tru[4][18];
+  for (int k = 0; k < 4; ++k)
+    for (int i = 0; i < 18; ++i) tru[k][i] = 0.0;
+  for (int r = 0; r < 3; ++r) tru[0][r * 6 + r] = 1.0;
+  for (int k = 0; k < 3; ++k)
+    for (int r = 0; r < 3; ++r)
+      for (int col = 0; col < 3; ++col) {
+        double s = 0.0;
+        for (int m = 0; m < 3; ++m) s += E[k][r * 3 + m] * Jl[m * 3 + col];
+        tru[k + 1][r * 6 + 3 + col] = s;
+      }
+  for (int k = 0; k < 4; ++k)
+    for (int idx = 0; idx < 18; ++idx) {
+      if (c.variant == MOPT_P2P_REFTEST_COLMAJOR) {
+        // tst/point2point.cpp:18,71: Map<Matrix<S,3,6>> is column-major, so true element (r,c) was
+        // written at buffer[c*3+r]; linearization.h:17-18 then reads buffer[r'*6+c'] as J(r',c').
+        const int cc = idx / 3, rr = idx % 3;
+        jaff[k][idx] = tru[k][rr * 6 + cc];
+      } else {
+        jaff[k][idx] = tru[k][idx];
+      }
+    }
+}
+
+// Whole ParamBlock for one cost at x.  Call with at least one full warp; lane j builds set j.
+// Emulates the reference's Scalar for the step: with compute_dtype F32 x_j, h_j and x_j +- h_j are
+// rounded to float exactly as `float` arithmetic would (linearization.h:78-89).
+__device__ inline void setup_cost(const CostDev& c, const double* x, ParamBlock* pb, int lane, int nlanes) {
+  const int P = c.P;
+  const bool f32 = (c.compute_dtype == MOPT_F32);
+  const int nsets = (c.jacobian == MOPT_JAC_ANALYTICAL) ? 1 : (c.jacobian == MOPT_JAC_FORWARD ? 1 + P : 1 + 2 * P);
+  for (int s = lane; s < nsets; s += nlanes) {
+    double xs[kMaxP];
+    for (int i = 0; i < P; ++i) xs[i] = f32 ? double(float(x[i])) : x[i];
+    if (s > 0) {
+      const int j = (s - 1) % P;
+      const bool minus = (s - 1) >= P;
+      double h;
+      if (f32) {
+        const float ms = sqrtf(1.1920928955078125e-07f);
+        float hf = ms * fabsf(float(x[j]));
+        if (hf == 0.0f) hf = ms;
+        h = double(hf);
+        xs[j] = double(minus ? float(x[j]) - hf : float(x[j]) + hf);
+      } else {
+        const double ms = sqrt(2.220446049250313e-16);
+        h = ms * fabs(x[j]);
+        if (h == 0.0) h = ms;
+        xs[j] = minus ? x[j] - h : x[j] + h;
+      }
+      if (!minus) pb->h[j] = h;
+    }
+    setup_one_set(c, xs, pb->sets[s]);
+  }
+  if (lane == 0) {
+    for (int i = 0; i < P; ++i) pb->x[i] = x[i];
+    if (c.model == MOPT_MODEL_POINT2POINT && c.jacobian == MOPT_JAC_ANALYTICAL) setup_p2p_affine(c, x, pb->jaff);
+  }
+}
+
+}  // namespace mopt

@@ -1,0 +1,346 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU oracle
+on identical inputs.  Tolerances (BASELINE.json north_star):
+  * H, b: <= 1e-5 relative (max-abs difference over max-abs value); fp64-compute paths are held
+    to 1e-10.  sum r^T r likewise.
+  * final LM parameters: <= 1e-6; same iteration count and accept/reject sequence.
+Each test names the reference test it mirrors.  Run with `-m gpu` on a B200."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as orc
+from tests.common import FX, camera_consts, fachada, rel_err
+
+pytestmark = pytest.mark.gpu
+
+capi = None
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    global capi
+    from moptimizer_0_b200 import capi as _capi
+    capi = _capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def p2p_store(ctx, src, tgt, dtype):
+    st = capi.Store(ctx, capi.MODEL_POINT2POINT, src.shape[0], dtype)
+    st.upload(0, src)
+    st.upload(1, tgt)
+    return st
+
+
+def oracle_data(src, tgt, store_dtype):
+    """The oracle sees exactly what the device stores: fp32-rounded values for an fp32 store."""
+    if store_dtype == 0:
+        return src.astype(np.float32).astype(np.float64), tgt.astype(np.float32).astype(np.float64)
+    return src, tgt
+
+
+X_TEST = [[0.0] * 6, [1.0, 2.0, 3.0, 0.2, -0.3, 0.4], [10.4, 10.1, 0.0, 0.38, 0.31, 0.55]]
+
+
+# ---- tst/point2point.cpp:142-189: analytical linearization, all Jacobian variants -------------
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("store_dtype,compute_dtype,tol", [(1, 1, 1e-10), (0, 1, 1e-10), (0, 0, 1e-5)])
+def test_p2p_analytical_matches_oracle(ctx, variant, store_dtype, compute_dtype, tol):
+    src, tgt, _, _ = fachada()
+    st = p2p_store(ctx, src, tgt, store_dtype)
+    osrc, otgt = oracle_data(src, tgt, store_dtype)
+    n = src.shape[0]
+    for x in X_TEST:
+        prob = capi.make_problem(capi.MODEL_POINT2POINT, capi.JAC_ANALYTICAL, compute_dtype, variant=variant)
+        H, b, s = ctx.linearize(st, prob, x)
+        oc = orc.Cost(orc.P2P, 6, 3, n, a=osrc, b=otgt, jac_mode=orc.JAC_ANALYTICAL, variant=variant)
+        Ho, bo, so = orc.linearize(oc, x)
+        assert rel_err(H, Ho) < tol, (variant, x, rel_err(H, Ho))
+        assert rel_err(b, bo) < tol, (variant, x, rel_err(b, bo))
+        assert abs(s - so) <= tol * abs(so)
+        assert ctx.compute_cost(st, prob, x) == pytest.approx(so, rel=tol)
+    st.close()
+
+
+@pytest.mark.parametrize("loss,param", [(1, 50.0), (2, 3.0), (2, 0.5)])
+@pytest.mark.parametrize("store_dtype,compute_dtype,tol", [(1, 1, 1e-10), (0, 0, 1e-5)])
+def test_p2p_robust_loss_and_covariance(ctx, loss, param, store_dtype, compute_dtype, tol):
+    src, tgt, _, _ = fachada()
+    st = p2p_store(ctx, src, tgt, store_dtype)
+    osrc, otgt = oracle_data(src, tgt, store_dtype)
+    n = src.shape[0]
+    x = [9.5, 10.0, 0.3, 0.35, 0.3, 0.5]
+    cov = np.array([[2.0, 0.3, 0.1], [0.3, 1.5, -0.2], [0.1, -0.2, 0.7]])
+    for cv in (None, 0.5 * np.eye(3), cov):
+        prob = capi.make_problem(capi.MODEL_POINT2POINT, capi.JAC_ANALYTICAL, compute_dtype, loss=loss,
+                                 loss_param=param, covariance=cv)
+        H, b, s = ctx.linearize(st, prob, x)
+        oc = orc.Cost(orc.P2P, 6, 3, n, a=osrc, b=otgt, jac_mode=orc.JAC_ANALYTICAL, loss=loss, loss_param=param,
+                      cov=cv)
+        Ho, bo, so = orc.linearize(oc, x)
+        assert rel_err(H, Ho) < tol and rel_err(b, bo) < tol and abs(s - so) <= tol * abs(so)
+    st.close()
+
+
+# ---- numerical Jacobians (linearization.h:65-124), fp64 compute --------------------------------
+@pytest.mark.parametrize("jac", [1, 2])
+@pytest.mark.parametrize("store_dtype", [0, 1])
+def test_p2p_numerical_matches_oracle(ctx, jac, store_dtype):
+    src, tgt, _, _ = fachada()
+    st = p2p_store(ctx, src, tgt, store_dtype)
+    osrc, otgt = oracle_data(src, tgt, store_dtype)
+    n = src.shape[0]
+    for x in X_TEST:
+        prob = capi.make_problem(capi.MODEL_POINT2POINT, jac, capi.F64)
+        H, b, s = ctx.linearize(st, prob, x)
+        Ho, bo, so = orc.linearize(orc.Cost(orc.P2P, 6, 3, n, a=osrc, b=otgt, jac_mode=jac), x)
+        # finite differences amplify rounding by 1/h ~ 7e7: agreement to ~1e-7 is what fp64 allows
+        assert rel_err(H, Ho) < 1e-6 and rel_err(b, bo) < 1e-6 and abs(s - so) <= 1e-10 * abs(so)
+    st.close()
+
+
+def curve_store(ctx, dtype, lo=0, hi=67):
+    t = np.array(FX["curve"]["t"][lo:hi])
+    y = np.array(FX["curve"]["y"][lo:hi])
+    st = capi.Store(ctx, capi.MODEL_EXP_CURVE, len(t), dtype)
+    st.upload(0, t)
+    st.upload(1, y)
+    return st, t, y
+
+
+@pytest.mark.parametrize("jac", [0, 1, 2])
+def test_curve_linearization_matches_oracle(ctx, jac):
+    st, t, y = curve_store(ctx, capi.F64)
+    for x in ([0.0, 0.0], [0.29, 0.13], [1.2, 2.0]):
+        H, b, s = ctx.linearize(st, capi.make_problem(capi.MODEL_EXP_CURVE, jac, capi.F64), x)
+        Ho, bo, so = orc.linearize(orc.Cost(orc.EXP_CURVE, 2, 1, 67, a=t, b=y, jac_mode=jac), x)
+        tol = 1e-10 if jac == 0 else 1e-6
+        assert rel_err(H, Ho) < tol and rel_err(b, bo) < tol and abs(s - so) <= 1e-10 * abs(so)
+    st.close()
+
+
+# ---- tst/curve_fitting.cpp:101-147 -----------------------------------------------------------
+@pytest.mark.parametrize("x0,iters,tol", [([0.0, 0.0], 15, 5e-5), ([1.2, 2.0], 50, 1e-4)])
+@pytest.mark.parametrize("speculative", [True, False])
+def test_curve_fitting_lm(ctx, x0, iters, tol, speculative):
+    st, t, y = curve_store(ctx, capi.F64)
+    prob = capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_FORWARD, capi.F64)
+    r = ctx.lm_minimize([st], [prob], x0, max_iterations=iters, speculative=speculative)
+    assert np.allclose(r.x, FX["curve"]["expected"], atol=tol)
+    ro = orc.lm_minimize([orc.Cost(orc.EXP_CURVE, 2, 1, 67, a=t, b=y, jac_mode=orc.JAC_FORWARD)], x0, iters)
+    assert np.allclose(r.x, ro.x, atol=1e-6)
+    # the accept/reject sequence agrees while steps are decided by more than rounding (SURVEY hard part 5)
+    k = min(len(r.sequence), len(ro.sequence))
+    decisive = [i for i in range(k) if abs(ro.trace[i, 2] - ro.trace[i, 3]) > 1e-9 * ro.trace[i, 2]]
+    cut = (decisive[-1] + 1) if decisive else 0
+    assert r.sequence[:cut] == ro.sequence[:cut]
+    st.close()
+
+
+# ---- tst/multiple_objectives.cpp:102-132 -----------------------------------------------------
+def test_split_cost_lm(ctx):
+    s_all, _, _ = curve_store(ctx, capi.F64)
+    s_a, _, _ = curve_store(ctx, capi.F64, 0, 30)
+    s_b, _, _ = curve_store(ctx, capi.F64, 30, 67)
+    prob = capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_FORWARD, capi.F64)
+    single = ctx.lm_minimize([s_all], [prob], [0.0, 0.0])
+    multi = ctx.lm_minimize([s_a, s_b], [prob, prob], [0.0, 0.0])
+    assert np.allclose(multi.x, single.x, atol=5e-8)
+    assert np.allclose(multi.x, FX["curve"]["expected"], atol=5e-5)
+    for s in (s_all, s_a, s_b):
+        s.close()
+
+
+# ---- tst/camera_calibration.cpp:101-122 ------------------------------------------------------
+@pytest.mark.parametrize("x0,iters", [([0.0] * 6, 15), (FX["camera"]["bad_x0"], 50)])
+def test_camera_calibration_lm(ctx, x0, iters):
+    pts = np.array(FX["camera"]["points"])
+    pix = np.array(FX["camera"]["pixels"])
+    st = capi.Store(ctx, capi.MODEL_PINHOLE, 5, capi.F64)
+    st.upload(0, pts)
+    st.upload(1, pix)
+    prob = capi.make_problem(capi.MODEL_PINHOLE, capi.JAC_FORWARD, capi.F64, consts=camera_consts())
+    H, b, s = ctx.linearize(st, prob, x0)
+    oc = orc.Cost(orc.PINHOLE, 6, 2, 5, a=pts, b=pix, consts=camera_consts(), jac_mode=orc.JAC_FORWARD)
+    Ho, bo, so = orc.linearize(oc, x0)
+    assert rel_err(H, Ho) < 1e-6 and rel_err(b, bo) < 1e-6 and abs(s - so) <= 1e-10 * abs(so)
+    r = ctx.lm_minimize([st], [prob], x0, max_iterations=iters)
+    assert np.allclose(r.x, FX["camera"]["ceres_solution"], atol=5e-5)
+    ro = orc.lm_minimize([oc], x0, iters)
+    assert np.allclose(r.x, ro.x, atol=1e-6)
+    st.close()
+
+
+# ---- tst/simple_model.cpp, tst/loss_function.cpp, tst/covariance.cpp (float) ------------------
+def mm_store(ctx, n=7, dtype=0):
+    t = np.array(FX["michaelis_menten"]["t%d" % n], dtype=np.float32)
+    y = np.array(FX["michaelis_menten"]["y%d" % n], dtype=np.float32)
+    st = capi.Store(ctx, capi.MODEL_MICHAELIS_MENTEN, n, dtype)
+    st.upload(0, t)
+    st.upload(1, y)
+    return st, t, y
+
+
+@pytest.mark.parametrize("x0", [[0.9, 0.2], [1.9, 1.5]])
+@pytest.mark.parametrize("loss,param", [(0, 0.0), (1, 100.0)])
+def test_simple_model_float_lm(ctx, x0, loss, param):
+    st, _, _ = mm_store(ctx)
+    prob = capi.make_problem(capi.MODEL_MICHAELIS_MENTEN, capi.JAC_FORWARD, capi.F32, loss=loss, loss_param=param)
+    r = ctx.lm_minimize([st], [prob], x0, scalar_dtype=capi.F32)
+    assert np.allclose(r.x, FX["michaelis_menten"]["expected"], atol=0.01)
+    st.close()
+
+
+def test_covariance_scaling_float(ctx):
+    st, t, y = mm_store(ctx)
+    x0 = [1.9, 1.5]
+    H, b, _ = ctx.linearize(st, capi.make_problem(capi.MODEL_MICHAELIS_MENTEN, capi.JAC_FORWARD, capi.F32), x0)
+    Hi, bi, _ = ctx.linearize(st, capi.make_problem(capi.MODEL_MICHAELIS_MENTEN, capi.JAC_FORWARD, capi.F32,
+                                                    covariance=np.eye(1)), x0)
+    Hc, bc, _ = ctx.linearize(st, capi.make_problem(capi.MODEL_MICHAELIS_MENTEN, capi.JAC_FORWARD, capi.F32,
+                                                    covariance=np.array([[0.5]])), x0)
+    assert np.max(np.abs(H - Hi)) < 1e-5 and np.max(np.abs(b - bi)) < 1e-5
+    assert np.max(np.abs(Hc - 0.5 * H)) < 1e-5 and np.max(np.abs(bc - 0.5 * b)) < 1e-5
+    # and against the float oracle (finite differences in fp32: ~1e-3 relative is all either can promise)
+    Ho, bo, _ = orc.linearize(orc.Cost(orc.MICHAELIS_MENTEN, 2, 1, 7, a=t, b=y, jac_mode=orc.JAC_FORWARD), x0, orc.F32)
+    assert rel_err(H, Ho) < 5e-3 and rel_err(b, bo) < 5e-3
+    st.close()
+
+
+# ---- tst/differentiation.cpp:47-77,134-161 ---------------------------------------------------
+def test_differentiation_simple_model_and_powell(ctx):
+    st, t, y = mm_store(ctx, 9, capi.F64)
+    x0 = [0.9, 0.2]
+    Ha, ba, sa = ctx.linearize(st, capi.make_problem(capi.MODEL_MICHAELIS_MENTEN, capi.JAC_ANALYTICAL, capi.F64), x0)
+    Hn, _, sn = ctx.linearize(st, capi.make_problem(capi.MODEL_MICHAELIS_MENTEN, capi.JAC_FORWARD, capi.F64), x0)
+    assert np.max(np.abs(Ha - Hn)) < 5e-3 and abs(sa - sn) < 1e-4
+    t64, y64 = t.astype(np.float64), y.astype(np.float64)
+    Ho, bo, so = orc.linearize(orc.Cost(orc.MICHAELIS_MENTEN, 2, 1, 9, a=t64, b=y64, jac_mode=orc.JAC_ANALYTICAL), x0)
+    assert rel_err(Ha, Ho) < 1e-10 and rel_err(ba, bo) < 1e-10 and abs(sa - so) <= 1e-10 * so
+    st.close()
+    ps = capi.Store(ctx, capi.MODEL_POWELL, 1, capi.F64)
+    xp = [3.0, -1.0, 0.0, 4.0]
+    Hpa, bpa, spa = ctx.linearize(ps, capi.make_problem(capi.MODEL_POWELL, capi.JAC_ANALYTICAL, capi.F64), xp)
+    Hpn, _, _ = ctx.linearize(ps, capi.make_problem(capi.MODEL_POWELL, capi.JAC_FORWARD, capi.F64), xp)
+    assert np.max(np.abs(Hpa - Hpn)) < 1e-4
+    Hpo, bpo, spo = orc.linearize(orc.Cost(orc.POWELL, 4, 4, 1, jac_mode=orc.JAC_ANALYTICAL), xp)
+    assert rel_err(Hpa, Hpo) < 1e-12 and rel_err(bpa, bpo) < 1e-12 and spa == pytest.approx(spo, rel=1e-12)
+    ps.close()
+
+
+# ---- tst/powell.cpp:62-136 -------------------------------------------------------------------
+@pytest.mark.parametrize("cov", [None, 0.01 * np.eye(4)])
+def test_powell_lm(ctx, cov):
+    ps = capi.Store(ctx, capi.MODEL_POWELL, 1, capi.F64)
+    prob = capi.make_problem(capi.MODEL_POWELL, capi.JAC_FORWARD, capi.F64, covariance=cov)
+    r = ctx.lm_minimize([ps], [prob], [3.0, -1.0, 0.0, 4.0], max_iterations=25)
+    assert np.all(np.abs(r.x) < 5e-5)
+    ro = orc.lm_minimize([orc.Cost(orc.POWELL, 4, 4, 1, jac_mode=orc.JAC_FORWARD, cov=cov)], [3, -1, 0, 4], 25)
+    assert r.status == ro.status and r.executed_iterations == ro.executed_iterations
+    assert r.sequence == ro.sequence and np.allclose(r.x, ro.x, atol=1e-6)
+    ps.close()
+
+
+# ---- tst/point2point.cpp:192-217 + north-star LM parity --------------------------------------
+@pytest.mark.parametrize("jac,variant", [(1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("speculative", [True, False])
+def test_p2p_lm_trace_matches_oracle_fp64(ctx, jac, variant, speculative):
+    src, tgt, _, _ = fachada()
+    n = src.shape[0]
+    st = p2p_store(ctx, src, tgt, capi.F64)
+    prob = capi.make_problem(capi.MODEL_POINT2POINT, jac, capi.F64, variant=variant)
+    r = ctx.lm_minimize([st], [prob], [0.0] * 6, max_iterations=50, speculative=speculative)
+    oc = orc.Cost(orc.P2P, 6, 3, n, a=src, b=tgt, jac_mode=jac, variant=variant, cost_threads=4)
+    ro = orc.lm_minimize([oc], [0.0] * 6, max_iterations=50)
+    assert r.status == ro.status == "CONVERGED"
+    assert r.executed_iterations == ro.executed_iterations
+    assert r.sequence == ro.sequence
+    assert np.allclose(r.x, ro.x, atol=1e-6)
+    assert np.allclose(r.trace[:, 2], ro.trace[:, 2], rtol=1e-5)   # y0 per trial
+    assert np.allclose(r.trace[:, 5], ro.trace[:, 5], rtol=1e-5)   # lambda per trial
+    if speculative:
+        assert r.num_passes == len(r.sequence) + 1
+    st.close()
+
+
+def test_p2p_lm_fp32_store_reaches_ground_truth(ctx):
+    src, tgt, _, _ = fachada()
+    st = p2p_store(ctx, src, tgt, capi.F32)
+    prob = capi.make_problem(capi.MODEL_POINT2POINT, capi.JAC_ANALYTICAL, capi.F32, loss=capi.LOSS_HUBER, loss_param=1.0)
+    r = ctx.lm_minimize([st], [prob], [0.0] * 6, max_iterations=50)
+    osrc, otgt = oracle_data(src, tgt, 0)
+    oc = orc.Cost(orc.P2P, 6, 3, src.shape[0], a=osrc, b=otgt, jac_mode=orc.JAC_ANALYTICAL, loss=orc.LOSS_HUBER,
+                  loss_param=1.0, cost_threads=4)
+    ro = orc.lm_minimize([oc], [0.0] * 6, max_iterations=50)
+    assert np.allclose(r.x, ro.x, atol=2e-6)
+    assert np.allclose(r.x, [10.5, 10.2, 0.1, 0.3899450238, 0.3154200672, 0.5496221593], atol=1e-5)
+    # same decisions while the cost decrease is above the fp32 evaluation noise floor
+    k = min(len(r.sequence), len(ro.sequence))
+    floor = 1e-5
+    cut = next((i for i in range(k) if abs(ro.trace[i, 2] - ro.trace[i, 3]) < floor * max(ro.trace[i, 2], 1e-30)), k)
+    assert cut >= 4 and r.sequence[:cut] == ro.sequence[:cut]
+    st.close()
+
+
+# ---- tst/parallel.cpp:70-94 ------------------------------------------------------------------
+def test_parallel_cost_1m_points(ctx):
+    rng = np.random.default_rng(0)
+    n = 1_000_000
+    src = (rng.uniform(-1, 1, (n, 3)) + np.array([3.0, 1.0, 1.0])) * 5.0
+    tgt = src + np.array([1.0, 2.0, 3.0])
+    st = capi.Store(ctx, capi.MODEL_POINT_DIST, n, capi.F64)
+    st.upload(0, src)
+    st.upload(1, tgt)
+    prob = capi.make_problem(capi.MODEL_POINT_DIST, capi.JAC_FORWARD, capi.F64)
+    s = ctx.compute_cost(st, prob, [])
+    so = orc.compute_cost(orc.Cost(orc.POINT_DIST, 0, 3, n, a=src, b=tgt, cost_threads=8), [], parallel=True)
+    assert s == pytest.approx(so, abs=1e-6) and s == pytest.approx(14.0 * n, rel=1e-12)
+    st.close()
+
+
+# ---- edge cases: ragged sizes, empty store, round trips ----------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 3, 5, 1023, 1025, 4099])
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_ragged_sizes(ctx, n, dtype):
+    src, tgt, _, _ = fachada()
+    src, tgt = src[:n], tgt[:n]
+    st = capi.Store(ctx, capi.MODEL_POINT2POINT, n, dtype)
+    if n:
+        st.upload(0, src)
+        st.upload(1, tgt)
+    x = [0.3, -0.2, 0.1, 0.05, 0.02, -0.03]
+    prob = capi.make_problem(capi.MODEL_POINT2POINT, capi.JAC_ANALYTICAL, capi.F64)
+    H, b, s = ctx.linearize(st, prob, x)
+    if n == 0:
+        assert not H.any() and not b.any() and s == 0.0
+    else:
+        osrc, otgt = oracle_data(src, tgt, dtype)
+        Ho, bo, so = orc.linearize(orc.Cost(orc.P2P, 6, 3, n, a=osrc, b=otgt, jac_mode=orc.JAC_ANALYTICAL), x)
+        assert rel_err(H, Ho) < 1e-10 and rel_err(b, bo) < 1e-10 and abs(s - so) <= 1e-10 * so
+        assert np.array_equal(st.download(0), osrc) and np.array_equal(st.download(1), otgt)
+    st.close()
+
+
+def test_error_paths(ctx):
+    st = capi.Store(ctx, capi.MODEL_PINHOLE, 4, capi.F64)
+    with pytest.raises(capi.MoptError, match="f_df"):  # model.h:66-70
+        ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE, capi.JAC_ANALYTICAL, capi.F64), [0.0] * 6)
+    with pytest.raises(capi.MoptError, match="model"):
+        ctx.linearize(st, capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_FORWARD, capi.F64), [0.0] * 2)
+    with pytest.raises(capi.MoptError, match="No cost function added"):  # optimizer.h:48-54
+        ctx.lm_minimize([], [], [0.0] * 6)
+    bad = capi.make_problem(capi.MODEL_PINHOLE, capi.JAC_FORWARD, capi.F64, covariance=np.array([[1.0, 0.2], [0.1, 1.0]]))
+    with pytest.raises(capi.MoptError, match="symmetric"):
+        ctx.linearize(st, bad, [0.0] * 6)
+    st.close()
+
+
+def test_device_ldlt_matches_oracle(ctx):
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 4, 6, 15, 16):
+        A = rng.normal(size=(n + 2, n))
+        Hm = A.T @ A + 1e-3 * np.eye(n)
+        b = rng.normal(size=n)
+        assert np.allclose(capi.ldlt_solve_device(Hm, b), orc.ldlt_solve(Hm, b), rtol=1e-12, atol=1e-14)
+    Hs = np.array([[4.0, 2.0, 0.0], [2.0, 1.0, 0.0], [0.0, 0.0, 0.0]])
+    assert np.allclose(capi.ldlt_solve_device(Hs, np.array([2.0, 1.0, 0.0])), orc.ldlt_solve(Hs, np.array([2.0, 1.0, 0.0])))
