@@ -78,6 +78,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_cpp_tests(force: bool = False) -> str:
+    """Host-only g++ build of the C++ API mirror tests (tests/cpp) against libmopt_b200.so."""
+    build()
+    tdir = os.path.join(ROOT, "tests", "cpp")
+    exe = os.path.join(tdir, "run_tests")
+    srcs = [os.path.join(tdir, f) for f in ("test_main.cpp", "reference_tests.cpp")]
+    deps = srcs + [os.path.join(tdir, f) for f in ("mini_test.h", "fixtures.h")] + [LIB]
+    for d, _, files in os.walk(os.path.join(ROOT, "include")):
+        deps += [os.path.join(d, f) for f in files]
+    if force or _mtime(exe) < max(_mtime(d) for d in deps):
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+               '-DTEST_DATA_PATH="tests/golden"', *srcs, "-o", exe, "-L", PKG, "-lmopt_b200",
+               "-Wl,-rpath,$ORIGIN/../../moptimizer_0_b200"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for tests/cpp:\n{r.stdout}\n{r.stderr}")
+    return exe
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)

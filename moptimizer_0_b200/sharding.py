@@ -1,0 +1,33 @@
+"""Host-side helpers for sharded (multi-GPU) problems: contiguous residual ranges per rank and the packed
+(H upper, b, sum) vector that one fp64 all-reduce combines.  Pure Python/numpy so the
+world_size>1 logic is testable on CPU with the gloo backend."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous [first, last) of `rank`: [rank*N/W, (rank+1)*N/W) in integer arithmetic."""
+    if not (0 <= rank < world):
+        raise ValueError("rank outside [0, world)")
+    return (n_total * rank) // world, (n_total * (rank + 1)) // world
+
+
+def packed_size(P: int) -> int:
+    return P * (P + 1) // 2 + P + 1
+
+
+def pack(H: np.ndarray, b: np.ndarray, s: float) -> np.ndarray:
+    """Same layout as csrc PassResult: H upper triangle row-major, then b, then sum."""
+    P = b.shape[0]
+    iu = np.triu_indices(P)
+    return np.concatenate([np.asarray(H, dtype=np.float64)[iu], np.asarray(b, dtype=np.float64), [float(s)]])
+
+
+def unpack(v: np.ndarray, P: int):
+    H = np.zeros((P, P), dtype=np.float64)
+    iu = np.triu_indices(P)
+    nh = P * (P + 1) // 2
+    H[iu] = v[:nh]
+    H = H + np.triu(H, 1).T
+    return H, np.array(v[nh:nh + P]), float(v[nh + P])

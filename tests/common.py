@@ -30,7 +30,7 @@ def rot_z(a):
 
 def fachada():
     """src cloud + tgt = T_gt * src, as tst/point2point.cpp:87-103 builds them (fp64)."""
-    src = np.load(os.path.join(GOLDEN, "fachada_xyz.npz"))["xyz"]
+    src = np.fromfile(os.path.join(GOLDEN, "fachada_xyz.f64"), dtype="<f8").reshape(-1, 3)
     ex, ey, ez = FX["fachada"]["gt_euler_xyz"]
     R = rot_x(ex) @ rot_y(ey) @ rot_z(ez)
     t = np.array(FX["fachada"]["gt_translation"])

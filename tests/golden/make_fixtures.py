@@ -78,7 +78,8 @@ def fachada():
     assert md5 == "747d84d2a7f92db4f727414699b69e07", md5
     arr = np.loadtxt(path, dtype=np.float64)
     assert arr.shape == (29310, 6)
-    np.savez_compressed(os.path.join(OUT, "fachada_xyz.npz"), xyz=arr[:, :3].copy())
+    # raw little-endian float64, n x 3 row-major: readable by numpy.fromfile and by fread in tests/cpp
+    np.ascontiguousarray(arr[:, :3], dtype="<f8").tofile(os.path.join(OUT, "fachada_xyz.f64"))
     return {"n": 29310, "md5_txt": md5,
             "gt_euler_xyz": [0.3, 0.4, 0.5], "gt_translation": [10.5, 10.2, 0.1],
             "note": "tgt = T * src with R = Rx(.3) Ry(.4) Rz(.5) (tst/point2point.cpp:93-103)"}
@@ -90,7 +91,21 @@ def main():
           "powell": {"x0": [3, -1, 0, 4], "iters": 25, "tol": 5e-5, "cov_scale": 0.01}}
     with open(os.path.join(OUT, "reference_fixtures.json"), "w") as f:
         json.dump(fx, f, indent=1)
-    print("wrote", os.path.join(OUT, "reference_fixtures.json"), "and fachada_xyz.npz")
+    # the same numbers as "name count v0 v1 ..." lines for the C++ tests (tests/cpp/fixtures.h)
+    flat = {
+        "curve_t": fx["curve"]["t"], "curve_y": fx["curve"]["y"], "curve_expected": fx["curve"]["expected"],
+        "camera_K": fx["camera"]["K"], "camera_points": sum(fx["camera"]["points"], []),
+        "camera_pixels": sum(fx["camera"]["pixels"], []), "camera_ceres": fx["camera"]["ceres_solution"],
+        "camera_bad_x0": fx["camera"]["bad_x0"],
+        "mm_t7": fx["michaelis_menten"]["t7"], "mm_y7": fx["michaelis_menten"]["y7"],
+        "mm_t9": fx["michaelis_menten"]["t9"], "mm_y9": fx["michaelis_menten"]["y9"],
+        "mm_expected": fx["michaelis_menten"]["expected"],
+        "fachada_gt_euler": fx["fachada"]["gt_euler_xyz"], "fachada_gt_t": fx["fachada"]["gt_translation"],
+    }
+    with open(os.path.join(OUT, "reference_fixtures.txt"), "w") as f:
+        for k, v in flat.items():
+            f.write(k + " " + str(len(v)) + " " + " ".join(repr(float(x)) for x in v) + "\n")
+    print("wrote reference_fixtures.json/.txt and fachada_xyz.f64 in", OUT)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,37 @@
+"""The C++ mirror of the reference API (include/moptimizer/*.h over the C ABI): builds the C++ test binary
+that re-states the reference's own tests (tests/cpp/reference_tests.cpp) and, on a GPU, runs it."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "run_tests")
+
+
+def build_cpp_tests():
+    from moptimizer_0_b200 import build
+    return build.build_cpp_tests()
+
+
+def test_cpp_mirror_compiles_and_links():
+    exe = build_cpp_tests()
+    assert os.path.exists(exe)
+
+
+def test_cpp_binary_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe = build_cpp_tests()
+    r = subprocess.run([exe], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 77 and "no usable CUDA device" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_reference_tests_pass_on_gpu():
+    exe = EXE if os.path.exists(EXE) else build_cpp_tests()
+    r = subprocess.run([exe], capture_output=True, text=True, cwd=ROOT, timeout=600)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert " 0 failed" in r.stdout
