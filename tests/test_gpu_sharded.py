@@ -1,43 +1,45 @@
-"""Sharded path on real GPUs: 2 ranks (torchrun) over NCCL must reproduce the single-GPU result.
-Skipped unless the box has >= 2 GPUs (`gpurun --gpus 2`)."""
+"""Sharded path on real GPUs: 2 ranks (torchrun) over NCCL must reproduce the single-GPU result — same sums,
+same LM status / iteration count / accept-reject sequence / parameters.  Skipped unless the box has >= 2 GPUs
+(`gpurun --gpus 2`); the world_size>1 host logic is covered on CPU by tests/test_sharding_gloo.py."""
 import json
 import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
+
+from tests.common import rel_err
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _ngpu():
-    import torch
-    return torch.cuda.device_count()
-
-
-def _bench(args, nproc):
+def _run(nproc):
     cmd = [sys.executable]
     if nproc > 1:
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
                 "--master-port", "29611"]
-    cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(nproc)] + args
+    cmd += [os.path.join(ROOT, "tests", "sharded_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
-    return json.loads(line)
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    return json.loads(line[len("RESULT "):])
 
 
-def test_two_rank_linearization_and_lm_match_single_gpu():
-    if _ngpu() < 2:
+def test_two_ranks_match_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    common = ["--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-e2e", "--lm", "--strong-total", "8000000"]
-    one = _bench(common, 1)
-    two = _bench(common, 2)
-    # same 8 M global correspondences, sharded 2 x 4 M: sums agree to fp64 rounding of a different order
-    for k in ("sum_rtr", "H00", "b0"):
-        assert abs(one["check"][k] - two["check"][k]) <= 1e-9 * abs(one["check"][k]), (k, one["check"], two["check"])
-    assert one["lm"]["status"] == two["lm"]["status"]
-    assert one["lm"]["executed_iterations"] == two["lm"]["executed_iterations"]
-    assert one["lm"]["sequence"] == two["lm"]["sequence"]
-    assert abs(one["lm"]["x_err_inf"] - two["lm"]["x_err_inf"]) < 1e-9
+    one, two = _run(1), _run(2)
+    f1, f2 = one["fachada"], two["fachada"]
+    # fp64: different summation order only
+    assert rel_err(f2["H"], f1["H"]) < 1e-12 and rel_err(f2["b"], f1["b"]) < 1e-12
+    assert abs(f2["sum"] - f1["sum"]) <= 1e-12 * f1["sum"] and abs(f2["cost"] - f1["cost"]) <= 1e-12 * f1["cost"]
+    assert f1["status"] == f2["status"] == "CONVERGED"
+    assert f1["executed"] == f2["executed"] and f1["sequence"] == f2["sequence"]
+    assert np.allclose(f1["x"], f2["x"], atol=1e-9)
+    s1, s2 = one["synthetic"], two["synthetic"]
+    # fp32 partials are grouped differently per shard: agreement to ~1e-9, far inside the 1e-5 parity bar
+    assert rel_err(s2["H"], s1["H"]) < 1e-8 and rel_err(s2["b"], s1["b"]) < 1e-8
+    assert abs(s2["sum"] - s1["sum"]) <= 1e-8 * s1["sum"]
