@@ -203,7 +203,7 @@ PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate
 
 int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int slot, int accumulate, int mode_override) {
   const PassArgs a = make_args(ctx, st, slot, accumulate, mode_override);
-  PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm};
+  PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
   if (p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL)
     return launch_p2p_moment(L, st->dtype, p->compute_dtype, p->loss, p->variant == MOPT_P2P_EXACT, a);
   return launch_dense(L, p->model, p->jacobian != MOPT_JAC_ANALYTICAL, st->dtype, p->compute_dtype, a);

@@ -149,6 +149,11 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
   return r;
 }
 
+// TMA bulk prefetch of `bytes` (multiple of 16, 16-byte aligned source) into L2.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 template <typename ST>
 struct VecOf;
 template <>

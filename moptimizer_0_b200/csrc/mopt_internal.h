@@ -57,6 +57,7 @@ struct PassLaunch {
   cudaStream_t stream;
   int num_sms;
   int ctas_per_sm;  // 0 = occupancy-derived default
+  int threads;      // 0 = default launch shape
 };
 
 // mopt_pass_p2p.cu

@@ -17,28 +17,39 @@ int pick_grid(const void* kernel, int threads, const PassLaunch& L, int64_t work
 
 namespace {
 
-constexpr int kThreads = 256;
+// Launch shapes (profiles/r1_tune_p2p.txt): the fp32 kernel is bound by bytes in flight, not by its ALU
+// work, and does best with the whole SM's 32 warps x 6 outstanding 16-byte loads (64 registers/thread).
+struct ShapeF32 {
+  static constexpr int THREADS = 1024, MINB = 1, UNROLL = 1, FLUSH = 16;
+};
+struct ShapeF32Small {  // 2 CTAs/SM x 256 threads, 2 rounds in flight; selectable with mopt_ctx_set_launch(.., 256)
+  static constexpr int THREADS = 256, MINB = 2, UNROLL = 2, FLUSH = 16;
+};
+struct ShapeF64 {
+  static constexpr int THREADS = 256, MINB = 1, UNROLL = 2, FLUSH = 8;
+};
 
-template <typename ST, typename CT, int LOSS, bool QROT, int MINB>
+template <typename ST, typename CT, int LOSS, bool QROT, class S>
 int launch_one(const PassLaunch& L, const PassArgs& a) {
-  auto kern = p2p_moment_kernel<ST, CT, LOSS, QROT, kThreads, MINB>;
+  auto kern = p2p_moment_kernel<ST, CT, LOSS, QROT, S::THREADS, S::MINB, S::UNROLL, S::FLUSH>;
   const int64_t groups = a.n / VecOf<ST>::N;
-  const int grid = pick_grid(reinterpret_cast<const void*>(kern), kThreads, L, groups);
-  kern<<<grid, kThreads, 0, L.stream>>>(a);
+  // small problems: keep CTAs at 256 threads' worth of work granularity by capping the grid, never below 1
+  const int grid = pick_grid(reinterpret_cast<const void*>(kern), S::THREADS, L, groups);
+  kern<<<grid, S::THREADS, 0, L.stream>>>(a);
   MOPT_CUDA_TRY(cudaGetLastError());
   return MOPT_OK;
 }
 
-template <typename ST, typename CT, int MINB>
+template <typename ST, typename CT, class S>
 int launch_loss(const PassLaunch& L, int loss, bool qrot, const PassArgs& a) {
   switch (loss) {
     case MOPT_LOSS_NONE:
-      return qrot ? launch_one<ST, CT, MOPT_LOSS_NONE, true, MINB>(L, a) : launch_one<ST, CT, MOPT_LOSS_NONE, false, MINB>(L, a);
+      return qrot ? launch_one<ST, CT, MOPT_LOSS_NONE, true, S>(L, a) : launch_one<ST, CT, MOPT_LOSS_NONE, false, S>(L, a);
     case MOPT_LOSS_GEMAN_MCCLURE:
-      return qrot ? launch_one<ST, CT, MOPT_LOSS_GEMAN_MCCLURE, true, MINB>(L, a)
-                  : launch_one<ST, CT, MOPT_LOSS_GEMAN_MCCLURE, false, MINB>(L, a);
+      return qrot ? launch_one<ST, CT, MOPT_LOSS_GEMAN_MCCLURE, true, S>(L, a)
+                  : launch_one<ST, CT, MOPT_LOSS_GEMAN_MCCLURE, false, S>(L, a);
     case MOPT_LOSS_HUBER:
-      return qrot ? launch_one<ST, CT, MOPT_LOSS_HUBER, true, MINB>(L, a) : launch_one<ST, CT, MOPT_LOSS_HUBER, false, MINB>(L, a);
+      return qrot ? launch_one<ST, CT, MOPT_LOSS_HUBER, true, S>(L, a) : launch_one<ST, CT, MOPT_LOSS_HUBER, false, S>(L, a);
     default:
       set_last_error("unknown loss kind");
       return MOPT_ERR_INVALID_ARGUMENT;
@@ -48,9 +59,11 @@ int launch_loss(const PassLaunch& L, int loss, bool qrot, const PassArgs& a) {
 }  // namespace
 
 int launch_p2p_moment(const PassLaunch& L, int store_dtype, int compute_dtype, int loss, bool qrot, const PassArgs& a) {
-  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F32) return launch_loss<float, float, 2>(L, loss, qrot, a);
-  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F64) return launch_loss<float, double, 1>(L, loss, qrot, a);
-  if (store_dtype == MOPT_F64 && compute_dtype == MOPT_F64) return launch_loss<double, double, 1>(L, loss, qrot, a);
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F32)
+    return (L.threads == 256) ? launch_loss<float, float, ShapeF32Small>(L, loss, qrot, a)
+                              : launch_loss<float, float, ShapeF32>(L, loss, qrot, a);
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F64) return launch_loss<float, double, ShapeF64>(L, loss, qrot, a);
+  if (store_dtype == MOPT_F64 && compute_dtype == MOPT_F64) return launch_loss<double, double, ShapeF64>(L, loss, qrot, a);
   set_last_error("point2point: store dtype f64 with compute dtype f32 is not supported");
   return MOPT_ERR_UNSUPPORTED;
 }
