@@ -103,9 +103,9 @@ float time_launch(Env& E, F launch, int reps = 15) {
   return ms[ms.size() / 2];
 }
 
-template <int THREADS, int MINB, int UNROLL, int FLUSH, int PF = 0, bool SWP = false>
-void run_variant(Env& E, int ctas_per_sm) {
-  auto kern = p2p_moment_kernel<float, float, MOPT_LOSS_HUBER, true, THREADS, MINB, UNROLL, FLUSH, PF, SWP>;
+template <int THREADS, int MINB, int UNROLL, int FLUSH, int PF = 0, bool SWP = false, int LOSS = MOPT_LOSS_HUBER>
+void run_variant(Env& E, int ctas_per_sm, int mode = PASS_LINEARIZE) {
+  auto kern = p2p_moment_kernel<float, float, LOSS, true, THREADS, MINB, UNROLL, FLUSH, PF, SWP>;
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
   cudaFuncAttributes fa;
@@ -114,6 +114,8 @@ void run_variant(Env& E, int ctas_per_sm) {
   if (per_sm < ctas_per_sm) return;  // shape not reachable
   const int grid = per_sm * E.num_sms;
   PassArgs a = E.a;
+  a.mode_override = mode;
+  if (mode != PASS_LINEARIZE || LOSS != MOPT_LOSS_HUBER) std::printf("[mode=%d loss=%d] ", mode, LOSS);
   const float ms = time_launch(E, [&] { kern<<<grid, THREADS, 0, E.stream>>>(a); });
   const double gbs = 24.0 * double(a.n) / (ms * 1e-3) / 1e9;
   std::printf("moment%s threads=%3d minb=%d unroll=%d flush=%2d pf=%2d ctas/sm=%d regs=%3d occ=%d  %8.1f us  %7.1f GB/s  %6.1f Gres/s\n",
@@ -174,6 +176,21 @@ int main(int argc, char** argv) {
   CK(cudaStreamSynchronize(E.stream));
   std::printf("%s, %d SMs, n = %lld, data = %s\n", prop.name, E.num_sms, (long long)n, argc > 2 ? argv[2] : "random");
 
+  if (argc > 3) {  // sustained-clock experiment: long pre-warm, then the variants that separate ALU from HBM limits
+    auto kern = p2p_moment_kernel<float, float, MOPT_LOSS_HUBER, true, 1024, 1, 1, 16>;
+    PassArgs a = E.a;
+    for (int i = 0; i < std::atoi(argv[3]); ++i) kern<<<148, 1024, 0, E.stream>>>(a);
+    CK(cudaStreamSynchronize(E.stream));
+    for (int rep = 0; rep < 3; ++rep) {
+      run_ceiling<256, 4>(E, 3);
+      run_variant<1024, 1, 1, 16>(E, 1);
+      run_variant<1024, 1, 1, 16, 0, false, MOPT_LOSS_NONE>(E, 1);
+      run_variant<1024, 1, 1, 16>(E, 1, PASS_COST);
+      run_variant<256, 2, 2, 16>(E, 2);
+      run_variant<256, 2, 2, 16>(E, 2, PASS_COST);
+    }
+    return 0;
+  }
   run_ceiling<256, 1>(E, 8); run_ceiling<256, 2>(E, 8); run_ceiling<256, 4>(E, 8);
   run_ceiling<256, 2>(E, 4); run_ceiling<256, 4>(E, 4); run_ceiling<256, 4>(E, 2);
   run_ceiling<512, 2>(E, 4); run_ceiling<512, 4>(E, 2); run_ceiling<1024, 2>(E, 2);

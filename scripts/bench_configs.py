@@ -1,0 +1,111 @@
+"""Throughput of the other BASELINE.json configurations (parity-test cases, not the bench.py line):
+   configs[1] curve fitting 10 M samples, numerical central differences
+   configs[4] camera calibration 50 M observations, numerical Jacobian
+   + point2point variants (numerical, fp64 store).  Prints one JSON object per case."""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from moptimizer_0_b200 import capi
+from oracle import oracle_py as orc
+from tests.common import camera_consts
+
+ctx = capi.Context(0)
+stream = torch.cuda.ExternalStream(ctx.stream())
+
+
+def time_pass(store, prob, x, steps=30, warm=100):
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    for _ in range(warm):
+        ctx.linearize_async(store, prob, x)
+    ctx.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(steps):
+        ctx.linearize_async(store, prob, x)
+    b.record(stream)
+    ctx.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def report(name, n, bytes_per, ms, extra=None):
+    d = {"case": name, "n": n, "ms_per_pass": ms, "Gres_per_s": n / ms / 1e6, "GB_per_s": n * bytes_per / ms / 1e6}
+    d.update(extra or {})
+    print(json.dumps(d), flush=True)
+
+
+def lm_time(stores, probs, x0, **kw):
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    r = ctx.lm_minimize(stores, probs, x0, **kw)
+    dt = time.perf_counter() - t0
+    return r, dt
+
+
+# ---- curve fitting 10 M --------------------------------------------------------------------------
+n = 10_000_000
+st = capi.Store(ctx, capi.MODEL_EXP_CURVE, n, capi.F32)
+st.generate(seed=1, gt=[0.3, 0.1], lo=(0, 0, 0), hi=(5, 0, 0), n_total=n, noise_sigma=0.2)
+for jac, jn in ((capi.JAC_CENTRAL, "central"), (capi.JAC_FORWARD, "forward"), (capi.JAC_ANALYTICAL, "analytical")):
+    for cd, cn in ((capi.F32, "f32"), (capi.F64, "f64")):
+        prob = capi.make_problem(capi.MODEL_EXP_CURVE, jac, cd)
+        report(f"curve10M_{jn}_{cn}", n, 8, time_pass(st, prob, [0.25, 0.15]))
+prob = capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_CENTRAL, capi.F64)
+r, dt = lm_time([st], [prob], [0.0, 0.0], max_iterations=50)
+print(json.dumps({"case": "curve10M_lm_central_f64", "status": r.status, "iters": r.executed_iterations,
+                  "passes": r.num_passes, "seconds": dt, "lm_iters_per_s": r.executed_iterations / dt,
+                  "x": r.x.tolist()}), flush=True)
+st.close()
+
+# ---- camera 50 M ---------------------------------------------------------------------------------
+n = 50_000_000
+consts = camera_consts()
+x_gt = np.array([-0.01, 0.02, -0.06, 0.018, -0.0013, 0.027])
+M = consts[:12].reshape(3, 4) @ orc.so3_convert6dof(x_gt) @ consts[12:].reshape(4, 4)
+st = capi.Store(ctx, capi.MODEL_PINHOLE, n, capi.F32)
+st.generate(seed=3, gt=M.reshape(-1), lo=(2.0, -1.0, -0.5), hi=(5.0, 1.0, 1.0), noise_sigma=0.5)
+for jac, jn in ((capi.JAC_CENTRAL, "central"), (capi.JAC_FORWARD, "forward")):
+    for cd, cn in ((capi.F32, "f32"), (capi.F64, "f64")):
+        prob = capi.make_problem(capi.MODEL_PINHOLE, jac, cd, consts=consts)
+        report(f"camera50M_{jn}_{cn}", n, 20, time_pass(st, prob, [0.0] * 6, steps=10, warm=10))
+prob = capi.make_problem(capi.MODEL_PINHOLE, capi.JAC_CENTRAL, capi.F64, consts=consts)
+r, dt = lm_time([st], [prob], [0.0] * 6, max_iterations=50)
+print(json.dumps({"case": "camera50M_lm_central_f64", "status": r.status, "iters": r.executed_iterations,
+                  "passes": r.num_passes, "seconds": dt, "lm_iters_per_s": r.executed_iterations / dt,
+                  "x_err": float(np.max(np.abs(r.x - x_gt)))}), flush=True)
+st.close()
+
+# ---- point2point variants ------------------------------------------------------------------------
+n = 100_000_000
+X_GT = [0.5, -0.3, 0.2, 0.10, -0.05, 0.08]
+st = capi.Store(ctx, capi.MODEL_POINT2POINT, n, capi.F32)
+st.generate(seed=2, gt=X_GT, noise_sigma=0.01, outlier_fraction=0.05, outlier_range=1.0)
+for jac, jn in ((capi.JAC_ANALYTICAL, "analytical"), (capi.JAC_FORWARD, "forward"), (capi.JAC_CENTRAL, "central")):
+    for cd, cn in ((capi.F32, "f32"), (capi.F64, "f64")):
+        prob = capi.make_problem(capi.MODEL_POINT2POINT, jac, cd, loss=capi.LOSS_HUBER, loss_param=0.05)
+        report(f"p2p100M_f32store_{jn}_{cn}", n, 24, time_pass(st, prob, [0.0] * 6, steps=10, warm=10))
+st.close()
+n = 50_000_000
+st = capi.Store(ctx, capi.MODEL_POINT2POINT, n, capi.F64)
+st.generate(seed=2, gt=X_GT, noise_sigma=0.01, outlier_fraction=0.05, outlier_range=1.0)
+prob = capi.make_problem(capi.MODEL_POINT2POINT, capi.JAC_ANALYTICAL, capi.F64, loss=capi.LOSS_HUBER, loss_param=0.05)
+report("p2p50M_f64store_analytical_f64", n, 48, time_pass(st, prob, [0.0] * 6, steps=10, warm=10))
+st.close()
+
+# ---- small problem LM rate: fachada (29 310 points), fp64 -----------------------------------------
+from tests.common import fachada
+src, tgt, _, _ = fachada()
+st = capi.Store(ctx, capi.MODEL_POINT2POINT, src.shape[0], capi.F64)
+st.upload(0, src); st.upload(1, tgt)
+for jac, jn in ((capi.JAC_ANALYTICAL, "analytical"), (capi.JAC_FORWARD, "forward")):
+    prob = capi.make_problem(capi.MODEL_POINT2POINT, jac, capi.F64)
+    ctx.lm_minimize([st], [prob], [0.0] * 6, max_iterations=50)
+    best = 1e9
+    for _ in range(20):
+        r, dt = lm_time([st], [prob], [0.0] * 6, max_iterations=50)
+        best = min(best, dt)
+    print(json.dumps({"case": f"fachada_lm_{jn}_f64", "status": r.status, "iters": r.executed_iterations,
+                      "passes": r.num_passes, "best_seconds": best, "lm_iters_per_s": r.executed_iterations / best}), flush=True)
+    report(f"fachada_pass_{jn}_f64", src.shape[0], 48, time_pass(st, prob, [0.0] * 6, steps=200, warm=50))
+st.close()
+ctx.close()

@@ -1,0 +1,115 @@
+"""Full-size (-m gpu) checks through size-independent properties, at BASELINE.json's sizes where the oracle
+would take minutes: additivity over shards, agreement of fp32 and fp64 compute, Jacobian-mode consistency,
+and recovery of the generating parameters by the device-resident LM."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as orc
+from tests.common import camera_consts, rel_err
+
+pytestmark = pytest.mark.gpu
+X_GT = [0.5, -0.3, 0.2, 0.10, -0.05, 0.08]
+
+
+@pytest.fixture(scope="module")
+def env():
+    from moptimizer_0_b200 import capi
+    c = capi.Context(0)
+    yield capi, c
+    c.close()
+
+
+def test_p2p_100m_additivity_precision_and_oracle_sample(env):
+    capi, ctx = env
+    n = 100_000_000
+    st = capi.Store(ctx, capi.MODEL_POINT2POINT, n, capi.F32)
+    st.generate(seed=2, gt=X_GT, noise_sigma=0.01, outlier_fraction=0.05, outlier_range=1.0)
+    x = [0.1, -0.1, 0.05, 0.02, -0.01, 0.03]
+    p32 = capi.make_problem(capi.MODEL_POINT2POINT, capi.JAC_ANALYTICAL, capi.F32, loss=capi.LOSS_HUBER, loss_param=0.05)
+    p64 = capi.make_problem(capi.MODEL_POINT2POINT, capi.JAC_ANALYTICAL, capi.F64, loss=capi.LOSS_HUBER, loss_param=0.05)
+    H32, b32, s32 = ctx.linearize(st, p32, x)
+    H64, b64, s64 = ctx.linearize(st, p64, x)
+    # fp32 residual math + fp64 accumulation vs all-fp64 on the same fp32 inputs: the 1e-5 parity bar
+    assert rel_err(H32, H64) < 1e-5 and rel_err(b32, b64) < 1e-5 and abs(s32 - s64) < 1e-5 * s64
+    # additivity (tst/multiple_objectives.cpp as a property): two half-size stores of the same stream sum to the whole
+    half = n // 2
+    parts = []
+    for first, cnt in ((0, half), (half, n - half)):
+        sp = capi.Store(ctx, capi.MODEL_POINT2POINT, cnt, capi.F32)
+        sp.generate(seed=2, gt=X_GT, first_index=first, noise_sigma=0.01, outlier_fraction=0.05, outlier_range=1.0)
+        parts.append(ctx.linearize(sp, p64, x))
+        sp.close()
+    Hs, bs, ss = (parts[0][i] + parts[1][i] for i in range(3))
+    assert rel_err(Hs, H64) < 1e-12 and rel_err(bs, b64) < 1e-12 and abs(ss - s64) < 1e-12 * s64
+    # determinism: bit-identical run to run
+    H32b, b32b, s32b = ctx.linearize(st, p32, x)
+    assert np.array_equal(H32, H32b) and np.array_equal(b32, b32b) and s32 == s32b
+    # oracle on the first 2 M rows == device on a store holding exactly those rows
+    m = 2_000_000
+    src, tgt = st.download(0, np.float64, 0, m), st.download(1, np.float64, 0, m)
+    sm = capi.Store(ctx, capi.MODEL_POINT2POINT, m, capi.F32)
+    sm.upload(0, src)
+    sm.upload(1, tgt)
+    Hd, bd, sd = ctx.linearize(sm, p32, x)
+    Ho, bo, so = orc.linearize(orc.Cost(orc.P2P, 6, 3, m, a=src, b=tgt, jac_mode=orc.JAC_ANALYTICAL,
+                                        loss=orc.LOSS_HUBER, loss_param=0.05), x, nthreads=8)
+    assert rel_err(Hd, Ho) < 1e-5 and rel_err(bd, bo) < 1e-5 and abs(sd - so) < 1e-5 * so
+    sm.close()
+    # LM from x0 = 0 recovers the generating transform (noise sigma 0.01 over 1e8 points => ~1e-6)
+    r = ctx.lm_minimize([st], [p32], [0.0] * 6, max_iterations=50)
+    assert np.max(np.abs(r.x - np.array(X_GT))) < 2e-5, r.x
+    st.close()
+
+
+def test_curve_10m_central_difference(env):
+    capi, ctx = env
+    n = 10_000_000
+    st = capi.Store(ctx, capi.MODEL_EXP_CURVE, n, capi.F32)
+    st.generate(seed=1, gt=[0.3, 0.1], lo=(0, 0, 0), hi=(5, 0, 0), n_total=n, noise_sigma=0.2)
+    x = [0.25, 0.15]
+    ana = ctx.linearize(st, capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_ANALYTICAL, capi.F64), x)
+    cen = ctx.linearize(st, capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_CENTRAL, capi.F64), x)
+    fwd = ctx.linearize(st, capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_FORWARD, capi.F64), x)
+    assert rel_err(cen[0], ana[0]) < 1e-8 and rel_err(cen[1], ana[1]) < 1e-8   # central: O(h^2)
+    assert rel_err(fwd[0], ana[0]) < 1e-6 and rel_err(fwd[1], ana[1]) < 1e-5   # forward: O(h)
+    assert cen[2] == ana[2] == fwd[2]
+    # oracle on a 1 M sample
+    m = 1_000_000
+    t, y = st.download(0, np.float64, 0, m)[:, 0], st.download(1, np.float64, 0, m)[:, 0]
+    sm = capi.Store(ctx, capi.MODEL_EXP_CURVE, m, capi.F32)
+    sm.upload(0, t)
+    sm.upload(1, y)
+    Hd, bd, sd = ctx.linearize(sm, capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_CENTRAL, capi.F64), x)
+    Ho, bo, so = orc.linearize(orc.Cost(orc.EXP_CURVE, 2, 1, m, a=t, b=y, jac_mode=orc.JAC_CENTRAL), x)
+    assert rel_err(Hd, Ho) < 1e-7 and rel_err(bd, bo) < 1e-7 and abs(sd - so) < 1e-10 * so
+    sm.close()
+    r = ctx.lm_minimize([st], [capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_CENTRAL, capi.F64)], [0.0, 0.0],
+                        max_iterations=50)
+    assert abs(r.x[0] - 0.3) < 1e-3 and abs(r.x[1] - 0.1) < 2e-3, r.x
+    st.close()
+
+
+def test_camera_50m_numerical(env):
+    capi, ctx = env
+    n = 50_000_000
+    consts = camera_consts()
+    x_gt = np.array([-0.01, 0.02, -0.06, 0.018, -0.0013, 0.027])
+    T = orc.so3_convert6dof(x_gt)
+    K, C = consts[:12].reshape(3, 4), consts[12:].reshape(4, 4)
+    M = K @ T @ C
+    st = capi.Store(ctx, capi.MODEL_PINHOLE, n, capi.F32)
+    st.generate(seed=3, gt=M.reshape(-1), lo=(2.0, -1.0, -0.5), hi=(5.0, 1.0, 1.0), noise_sigma=0.5)
+    prob = capi.make_problem(capi.MODEL_PINHOLE, capi.JAC_CENTRAL, capi.F64, consts=consts)
+    m = 500_000
+    pts, pix = st.download(0, np.float64, 0, m), st.download(1, np.float64, 0, m)
+    sm = capi.Store(ctx, capi.MODEL_PINHOLE, m, capi.F32)
+    sm.upload(0, pts)
+    sm.upload(1, pix)
+    x = [0.0] * 6
+    Hd, bd, sd = ctx.linearize(sm, prob, x)
+    Ho, bo, so = orc.linearize(orc.Cost(orc.PINHOLE, 6, 2, m, a=pts, b=pix, consts=consts, jac_mode=orc.JAC_CENTRAL), x)
+    assert rel_err(Hd, Ho) < 1e-6 and rel_err(bd, bo) < 1e-6 and abs(sd - so) < 1e-10 * so
+    sm.close()
+    r = ctx.lm_minimize([st], [prob], x, max_iterations=50)
+    assert np.max(np.abs(r.x - x_gt)) < 1e-4, r.x
+    st.close()
