@@ -78,6 +78,10 @@ typedef enum mopt_model {
   MOPT_MODEL_POWELL = 4,
   /* r = p - q, no parameters; P=0, O=3, cost only.  tst/parallel.cpp:12-32 */
   MOPT_MODEL_POINT_DIST = 5,
+  /* Pinhole with OpenCV-style distortion and free intrinsics (NOT in the reference; BASELINE.json configs[4]):
+   * x = [t(3), omega(3), fx, fy, cx, cy, k1, k2, p1, p2, k3]; P=15, O=2.  A = XYZ, B = uv;
+   * consts = C (4x4 row-major, 16), the fixed frame conversion applied before the extrinsics */
+  MOPT_MODEL_PINHOLE_DISTORT = 6,
   MOPT_MODEL_COUNT_
 } mopt_model;
 
@@ -153,6 +157,7 @@ typedef struct mopt_synth {
   int64_t n_total;     /* curve: t_i = lo + (hi-lo) * i / n_total */
   double noise_sigma;  /* approx. Gaussian (Irwin-Hall 4) noise added to B */
   double outlier_fraction, outlier_range; /* fraction of elements whose B gets U(-range, range) added */
+  double consts[32];   /* model constants (same meaning as mopt_problem.consts), e.g. the pinhole frame conversion */
 } mopt_synth;
 
 /* ---- library ------------------------------------------------------------------------------- */

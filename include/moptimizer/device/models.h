@@ -140,6 +140,29 @@ class PinholeCamera : public DeviceModel<Scalar, PinholeCamera<Scalar>> {
   std::vector<double> consts_;
 };
 
+/// Pinhole with free intrinsics and OpenCV distortion — the "n x n calibration case" (not in the reference):
+/// x = [t, omega, fx, fy, cx, cy, k1, k2, p1, p2, k3], 15 parameters, 2 outputs.  C 4x4 row-major.
+template <typename Scalar>
+class PinholeDistortCamera : public DeviceModel<Scalar, PinholeDistortCamera<Scalar>> {
+ public:
+  using Ptr = std::shared_ptr<PinholeDistortCamera>;
+  template <class HostScalar>
+  PinholeDistortCamera(Context::Ptr ctx, const HostScalar* points, int64_t point_stride, const HostScalar* pixels,
+                       int64_t n, const double* C44, int store_dtype = dtypeOf<Scalar>()) {
+    if (n <= 0) throw std::runtime_error("Empty point list");
+    this->store_ = std::make_shared<Store>(std::move(ctx), MOPT_MODEL_PINHOLE_DISTORT, store_dtype, n);
+    this->store_->upload(0, points, n, point_stride);
+    this->store_->upload(1, pixels, n);
+    consts_.assign(32, 0.0);
+    for (int i = 0; i < 16; ++i) consts_[i] = C44[i];
+  }
+  int kind() const override { return MOPT_MODEL_PINHOLE_DISTORT; }
+  void fillConsts(double* c) const override { std::memcpy(c, consts_.data(), sizeof(double) * 32); }
+
+ private:
+  std::vector<double> consts_;
+};
+
 /// Powell's singular function (no data).
 template <typename Scalar>
 class Powell : public DeviceModel<Scalar, Powell<Scalar>> {

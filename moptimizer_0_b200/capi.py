@@ -19,7 +19,7 @@ MAX_PARAMETERS, MAX_OUTPUTS, MAX_COSTS, MAX_TRACE, NCCL_ID_BYTES = 16, 4, 8, 102
 OK = 0
 F32, F64 = 0, 1
 (MODEL_POINT2POINT, MODEL_EXP_CURVE, MODEL_MICHAELIS_MENTEN, MODEL_PINHOLE, MODEL_POWELL,
- MODEL_POINT_DIST) = range(6)
+ MODEL_POINT_DIST, MODEL_PINHOLE_DISTORT) = range(7)
 JAC_ANALYTICAL, JAC_FORWARD, JAC_CENTRAL = range(3)
 P2P_EXACT, P2P_REFTEST, P2P_REFTEST_COLMAJOR = range(3)
 LOSS_NONE, LOSS_GEMAN_MCCLURE, LOSS_HUBER = range(3)
@@ -27,6 +27,7 @@ STATUS = ["CONVERGED", "MAXIMUM_ITERATIONS_REACHED", "SMALL_DELTA", "NUMERIC_ERR
 MODEL_SHAPE = {  # model -> (P, O, ncomp_a, ncomp_b)
     MODEL_POINT2POINT: (6, 3, 3, 3), MODEL_EXP_CURVE: (2, 1, 1, 1), MODEL_MICHAELIS_MENTEN: (2, 1, 1, 1),
     MODEL_PINHOLE: (6, 2, 3, 2), MODEL_POWELL: (4, 4, 0, 0), MODEL_POINT_DIST: (0, 3, 3, 3),
+    MODEL_PINHOLE_DISTORT: (15, 2, 3, 2),
 }
 
 EXPORTS = [
@@ -65,7 +66,8 @@ class LmReport(C.Structure):
 class Synth(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("first_index", C.c_int64), ("gt", C.c_double * MAX_PARAMETERS),
                 ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("n_total", C.c_int64),
-                ("noise_sigma", C.c_double), ("outlier_fraction", C.c_double), ("outlier_range", C.c_double)]
+                ("noise_sigma", C.c_double), ("outlier_fraction", C.c_double), ("outlier_range", C.c_double),
+                ("consts", C.c_double * 32)]
 
 
 class MoptError(RuntimeError):
@@ -285,7 +287,7 @@ class Store:
 
     def generate(self, seed: int, gt: Sequence[float], lo=(0, 0, 0), hi=(10, 10, 10), first_index: int = 0,
                  n_total: int = 0, noise_sigma: float = 0.0, outlier_fraction: float = 0.0,
-                 outlier_range: float = 0.0):
+                 outlier_range: float = 0.0, consts=None):
         d = Synth()
         d.seed, d.first_index, d.n_total = seed, first_index, n_total
         for i, v in enumerate(gt):
@@ -293,6 +295,9 @@ class Store:
         for k in range(3):
             d.lo[k], d.hi[k] = float(lo[k]), float(hi[k])
         d.noise_sigma, d.outlier_fraction, d.outlier_range = noise_sigma, outlier_fraction, outlier_range
+        if consts is not None:
+            for i, v in enumerate(np.asarray(consts, dtype=np.float64).reshape(-1)):
+                d.consts[i] = float(v)
         check(lib().mopt_store_generate(self._h, C.byref(d)))
 
     def close(self):

@@ -206,6 +206,7 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
   PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
   if (p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL)
     return launch_p2p_moment(L, st->dtype, p->compute_dtype, p->loss, p->variant == MOPT_P2P_EXACT, a);
+  if (p->model == MOPT_MODEL_PINHOLE_DISTORT) return launch_wide(L, p->model, st->dtype, p->compute_dtype, a);
   return launch_dense(L, p->model, p->jacobian != MOPT_JAC_ANALYTICAL, st->dtype, p->compute_dtype, a);
 }
 
@@ -260,7 +261,7 @@ int ctx_alloc(mopt_ctx* ctx) {
   ctx->num_sms = prop.multiProcessorCount;
   MOPT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   MOPT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_partials, sizeof(double) * 32 * kMaxGrid));
+  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_partials, sizeof(double) * kMaxRaw * kMaxGrid));
   MOPT_CUDA_TRY(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
   MOPT_CUDA_TRY(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
   MOPT_CUDA_TRY(cudaMalloc(&ctx->d_trial, sizeof(PassResult)));

@@ -42,7 +42,8 @@ void set_last_error(const std::string& msg);
 constexpr int kMaxP = MOPT_MAX_PARAMETERS;
 constexpr int kMaxO = MOPT_MAX_OUTPUTS;
 constexpr int kMaxStreams = 6;
-constexpr int kSetSize = 16;                 // doubles per model parameter set
+constexpr int kSetSize = 24;                 // doubles per model parameter set
+constexpr int kMaxRaw = 160;                 // raw sums a pass kernel may reduce (multiple of 32, >= kPackedMax)
 constexpr int kMaxSets = 1 + 2 * kMaxP;      // base, P plus, P minus
 constexpr int kPackedMax = kMaxP * (kMaxP + 1) / 2 + kMaxP + 1;  // packed (H upper, b, sum)
 constexpr int kMaxGrid = 148 * 8;

@@ -65,6 +65,9 @@ int launch_p2p_moment(const PassLaunch& L, int store_dtype, int compute_dtype, i
 // mopt_pass_dense.cu
 int launch_dense(const PassLaunch& L, int model, bool numeric, int store_dtype, int compute_dtype, const PassArgs& a);
 
+// mopt_pass_wide.cu
+int launch_wide(const PassLaunch& L, int model, int store_dtype, int compute_dtype, const PassArgs& a);
+
 int pick_grid(const void* kernel, int threads, const PassLaunch& L, int64_t work_items);
 
 }  // namespace mopt

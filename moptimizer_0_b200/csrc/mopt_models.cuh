@@ -88,6 +88,30 @@ struct PinholeModel {
   static __device__ __forceinline__ void residual_jacobian(const CT*, const CT (&)[5], CT (&)[2], CT (&)[12]) {}
 };
 
+// Pinhole + OpenCV distortion with free intrinsics (new; BASELINE.json configs[4]).  streams: X,Y,Z | u,v.
+// set = TC (3x4 row-major, 12), fx, fy, cx, cy, k1, k2, p1, p2, k3.
+struct PinholeDistortModel {
+  static constexpr int P = 15, O = 2, NS = 5, NA = 3, SETN = 21;
+  static constexpr bool HAS_JAC = false;
+  template <typename CT>
+  static __device__ __forceinline__ void residual(const CT* s, const CT (&e)[5], CT (&r)[2]) {
+    CT p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p[k] = fma(s[k * 4 + 0], e[0], fma(s[k * 4 + 1], e[1], fma(s[k * 4 + 2], e[2], s[k * 4 + 3])));
+    const CT iz = CT(1) / p[2];
+    const CT xn = p[0] * iz, yn = p[1] * iz;
+    const CT r2 = fma(xn, xn, yn * yn);
+    const CT radial = fma(r2, fma(r2, fma(r2, s[20], s[17]), s[16]), CT(1));  // 1 + k1 r2 + k2 r2^2 + k3 r2^3
+    const CT xy2 = CT(2) * xn * yn;
+    const CT xd = fma(xn, radial, fma(s[18], xy2, s[19] * fma(CT(2) * xn, xn, r2)));
+    const CT yd = fma(yn, radial, fma(s[18], fma(CT(2) * yn, yn, r2), s[19] * xy2));
+    r[0] = e[3] - fma(s[12], xd, s[14]);
+    r[1] = e[4] - fma(s[13], yd, s[15]);
+  }
+  template <typename CT>
+  static __device__ __forceinline__ void residual_jacobian(const CT*, const CT (&)[5], CT (&)[2], CT (&)[30]) {}
+};
+
 // tst/powell.cpp:22-59.  No data.  set = x.
 struct PowellModel {
   static constexpr int P = 4, O = 4, NS = 0, NA = 0, SETN = 4;
@@ -132,6 +156,7 @@ inline ModelShape model_shape(int model) {
     case MOPT_MODEL_PINHOLE: return {6, 2, 5, 3, 3, 2, false};
     case MOPT_MODEL_POWELL: return {4, 4, 0, 0, 0, 0, true};
     case MOPT_MODEL_POINT_DIST: return {0, 3, 6, 3, 3, 3, false};
+    case MOPT_MODEL_PINHOLE_DISTORT: return {15, 2, 5, 3, 3, 2, false};
     default: return {-1, -1, -1, -1, 0, 0, false};
   }
 }

@@ -525,5 +525,181 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
   }
 }
 
+// =============================================================================================
+// Wide pass kernel: models whose packed size P(P+1)/2 + P + 1 exceeds 32 (the n x n calibration case,
+// e.g. P = 15 -> 136 + 15 + 1 = 152 sums).  152 per-thread accumulators do not fit in registers next to a
+// 2 x 15 Jacobian, so the accumulators are distributed over the LANES of each warp instead:
+//   1. every lane evaluates one residual and its finite-difference Jacobian (same code as the dense kernel)
+//      and writes the row  [ J (O x P) | w C J (O x P) | w C r (O) | r^T r ]  into the warp's shared tile;
+//   2. lane l owns packed entries l, l+32, ... and sweeps the 32 rows of the tile, so a warp finishes 32
+//      residuals with ~30 shared-memory instructions per residual and 5 accumulators per lane.
+// The lane-owned layout is exactly what grid_reduce() expects, so no transposing shuffle is needed.
+// =============================================================================================
+template <class M, typename ST, typename CT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) wide_pass_kernel(const PassArgs a) {
+  const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
+  if (mode == PASS_SKIP) return;
+  constexpr int P = M::P, O = M::O, NS = M::NS;
+  constexpr int NRAW = P * (P + 1) / 2 + P + 1;
+  constexpr int NCH = (NRAW + 31) / 32;
+  constexpr int NW = THREADS / 32;
+  constexpr int ROW = 2 * O * P + O + 1;        // values per residual row
+  constexpr int ROWP = ROW | 1;                 // odd stride: lanes writing their own row hit distinct banks
+  constexpr bool kFp32Acc = (sizeof(CT) == 4);
+  constexpr int FLUSH_GROUPS = 8;               // fp32 lane partials are folded into fp64 every 8*32 residuals
+  constexpr int NSETS = 1 + 2 * P;
+  constexpr int SETN = M::SETN;
+
+  extern __shared__ __align__(16) unsigned char wide_smem[];
+  CT* s_tile = reinterpret_cast<CT*>(wide_smem);                       // [NW][32][ROWP]
+  CT* s_sets = s_tile + size_t(NW) * 32 * ROWP;                        // [NSETS][SETN]
+  CT* s_invh = s_sets + NSETS * SETN;                                  // [P]
+  CT* s_cov = s_invh + P;                                              // [O*O]
+  unsigned char* s_idx = reinterpret_cast<unsigned char*>(s_cov + O * O);  // [NRAW][2] (i, j) of each packed entry
+  __shared__ double s_warp[NW * NCH * 32];
+  __shared__ double s_tot[NCH * 32];
+
+  const int jac = a.cost->jacobian;
+  const bool central = (jac == MOPT_JAC_CENTRAL);
+  const int nsets = central ? 1 + 2 * P : 1 + P;
+  for (int i = threadIdx.x; i < nsets * SETN; i += THREADS) s_sets[i] = CT(a.pb->sets[i / SETN][i % SETN]);
+  for (int i = threadIdx.x; i < P; i += THREADS) s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
+  for (int i = threadIdx.x; i < O * O; i += THREADS) s_cov[i] = CT(a.cost->cov[i]);
+  for (int e = threadIdx.x; e < NRAW; e += THREADS) {
+    int i = 0, j = 0;
+    if (e < P * (P + 1) / 2) {
+      int rem = e;
+      while (rem >= P - i) { rem -= P - i; ++i; }
+      j = i + rem;
+    } else if (e < NRAW - 1) {
+      i = e - P * (P + 1) / 2;
+    }
+    s_idx[2 * e] = (unsigned char)i;
+    s_idx[2 * e + 1] = (unsigned char)j;
+  }
+  const int loss = a.cost->loss;
+  const CT lossp = CT(a.cost->loss_param);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  CT* tile = s_tile + size_t(warp) * 32 * ROWP;
+  CT* my_row = tile + lane * ROWP;
+  const ST* __restrict__ sp[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) sp[s] = static_cast<const ST*>(a.streams.p[s]);
+
+  CT acc[NCH];
+  double dacc[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) { acc[c] = CT(0); dacc[c] = 0.0; }
+
+  // warps stride over groups of 32 consecutive residuals
+  const int64_t ngroups = (a.n + 31) / 32;
+  const int64_t wstride = int64_t(gridDim.x) * NW;
+  int since_flush = 0;
+  for (int64_t g = int64_t(blockIdx.x) * NW + warp; g < ngroups; g += wstride) {
+    const int64_t i = g * 32 + lane;
+    const bool valid = i < a.n;
+    // ---- 1. this lane's residual row -------------------------------------------------------------
+    CT e[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) e[s] = valid ? CT(sp[s][i]) : CT(0);
+    CT r[O];
+    M::template residual<CT>(s_sets, e, r);
+    CT e2 = CT(0);
+#pragma unroll
+    for (int o = 0; o < O; ++o) e2 = fma(r[o], r[o], e2);
+    CT w = valid ? loss_weight<CT>(loss, lossp, e2) : CT(0);
+    if (!valid) e2 = CT(0);
+    if (mode == PASS_COST) {
+      CT s = e2;  // cost-only: the warp's 32 squared norms go to the lane that owns the `sum` entry
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) s += shfl_xor(s, off);
+      if (lane == (NRAW - 1) % 32) acc[(NRAW - 1) / 32] += s;
+    } else {
+      CT J[O * P];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        CT rp[O];
+        M::template residual<CT>(s_sets + (1 + j) * SETN, e, rp);
+        if (central) {
+          CT rm[O];
+          M::template residual<CT>(s_sets + (1 + P + j) * SETN, e, rm);
+#pragma unroll
+          for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - rm[o]) * s_invh[j];
+        } else {
+#pragma unroll
+          for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - r[o]) * s_invh[j];
+        }
+      }
+      // row = [ J | w C J | w C r | e2 ]   (C is the identity unless setCovariance was called; s_cov holds it)
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        CT cr = CT(0);
+#pragma unroll
+        for (int k = 0; k < O; ++k) cr = fma(s_cov[o + k * O], r[k], cr);
+        my_row[2 * O * P + o] = w * cr;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          CT cj = CT(0);
+#pragma unroll
+          for (int k = 0; k < O; ++k) cj = fma(s_cov[o + k * O], J[k * P + p], cj);
+          my_row[o * P + p] = J[o * P + p];
+          my_row[O * P + o * P + p] = w * cj;
+        }
+      }
+      my_row[2 * O * P + O] = e2;
+      __syncwarp();
+      // ---- 2. lane-owned packed entries sweep the 32 rows -------------------------------------------
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int k = c * 32 + lane;
+        if (k < NRAW) {
+          const int ii = s_idx[2 * k], jj = s_idx[2 * k + 1];
+          CT s = acc[c];
+          if (k < P * (P + 1) / 2) {
+            for (int row = 0; row < 32; ++row) {
+              const CT* rw = tile + row * ROWP;
+#pragma unroll
+              for (int o = 0; o < O; ++o) s = fma(rw[o * P + ii], rw[O * P + o * P + jj], s);
+            }
+          } else if (k < NRAW - 1) {
+            for (int row = 0; row < 32; ++row) {
+              const CT* rw = tile + row * ROWP;
+#pragma unroll
+              for (int o = 0; o < O; ++o) s = fma(rw[o * P + ii], rw[2 * O * P + o], s);
+            }
+          } else {
+            for (int row = 0; row < 32; ++row) s += tile[row * ROWP + 2 * O * P + O];
+          }
+          acc[c] = s;
+        }
+      }
+      __syncwarp();
+    }
+    if (kFp32Acc && ++since_flush >= FLUSH_GROUPS) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) { dacc[c] += double(acc[c]); acc[c] = CT(0); }
+      since_flush = 0;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) dacc[c] += double(acc[c]);
+
+  if (!grid_reduce<NRAW, 32, NCH, THREADS>(dacc, a, s_tot, s_warp)) return;
+  if (mode == PASS_COST) {
+    if (threadIdx.x == 0) a.out->v[NRAW - 1] = a.accumulate ? a.out->v[NRAW - 1] + s_tot[NRAW - 1] : s_tot[NRAW - 1];
+  } else {
+    for (int i = threadIdx.x; i < NRAW; i += THREADS) a.out->v[i] = a.accumulate ? a.out->v[i] + s_tot[i] : s_tot[i];
+  }
+}
+
+template <class M, typename CT, int THREADS>
+constexpr size_t wide_smem_bytes() {
+  constexpr int ROWP = (2 * M::O * M::P + M::O + 1) | 1;
+  constexpr int NRAW = M::P * (M::P + 1) / 2 + M::P + 1;
+  return sizeof(CT) * (size_t(THREADS / 32) * 32 * ROWP + (1 + 2 * M::P) * M::SETN + M::P + M::O * M::O) + 2 * NRAW + 16;
+}
+
 #endif  // __CUDACC__
 }  // namespace mopt

@@ -1,0 +1,50 @@
+// Instantiations + dispatch of the wide pass kernel (mopt_pass.cuh): models with more than 32 packed sums.
+#include "mopt_internal.h"
+
+namespace mopt {
+namespace {
+
+constexpr int kThreads = 256;
+
+template <class M, typename ST, typename CT>
+int launch_one(const PassLaunch& L, const PassArgs& a) {
+  auto kern = wide_pass_kernel<M, ST, CT, kThreads>;
+  constexpr size_t smem = wide_smem_bytes<M, CT, kThreads>();
+  static bool configured = false;
+  if (!configured) {
+    MOPT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    configured = true;
+  }
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+  int64_t grid = int64_t(occ) * L.num_sms;
+  const int64_t need = (a.n + kThreads - 1) / kThreads;  // one residual per lane per sweep
+  if (need < grid) grid = need;
+  if (grid < 1) grid = 1;
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  kern<<<int(grid), kThreads, smem, L.stream>>>(a);
+  MOPT_CUDA_TRY(cudaGetLastError());
+  return MOPT_OK;
+}
+
+template <class M>
+int launch_types(const PassLaunch& L, int store_dtype, int compute_dtype, const PassArgs& a) {
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F32) return launch_one<M, float, float>(L, a);
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F64) return launch_one<M, float, double>(L, a);
+  if (store_dtype == MOPT_F64 && compute_dtype == MOPT_F64) return launch_one<M, double, double>(L, a);
+  set_last_error("store dtype f64 with compute dtype f32 is not supported");
+  return MOPT_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+int launch_wide(const PassLaunch& L, int model, int store_dtype, int compute_dtype, const PassArgs& a) {
+  switch (model) {
+    case MOPT_MODEL_PINHOLE_DISTORT: return launch_types<PinholeDistortModel>(L, store_dtype, compute_dtype, a);
+    default:
+      set_last_error("unknown wide model kind");
+      return MOPT_ERR_INVALID_ARGUMENT;
+  }
+}
+
+}  // namespace mopt

@@ -89,6 +89,22 @@ __device__ inline void setup_one_set(const CostDev& c, const double* xs, double*
         }
       break;
     }
+    case MOPT_MODEL_PINHOLE_DISTORT: {
+      // set = (T(x) C)(3x4 row-major, 12), fx, fy, cx, cy, k1, k2, p1, p2, k3
+      double R[9];
+      const double w[3] = {xs[3], xs[4], xs[5]};
+      if (c.compute_dtype == MOPT_F32) so3_exp_dev<float>(w, R); else so3_exp_dev<double>(w, R);
+      const double* C = c.consts;
+      for (int r = 0; r < 3; ++r)
+        for (int col = 0; col < 4; ++col) {
+          double s = 0.0;
+          for (int k = 0; k < 3; ++k) s += R[r * 3 + k] * C[k * 4 + col];
+          s += xs[r] * C[12 + col];
+          set[r * 4 + col] = s;
+        }
+      for (int i = 0; i < 9; ++i) set[12 + i] = xs[6 + i];
+      break;
+    }
     default:  // parameter-only models: the set is x itself
       for (int i = 0; i < c.P; ++i) set[i] = xs[i];
       break;

@@ -58,7 +58,8 @@ __device__ __forceinline__ float approx_normal(uint64_t seed, int64_t index, int
 struct SynthDev {
   uint64_t seed;
   int64_t first_index, n_total;
-  float gt[16];  // p2p: R (9) t (3); curve: m, c; pinhole: M (12)
+  float gt[24];  // p2p: R (9) t (3); curve: m, c; pinhole: M (12); pinhole_distort: TC (12), fx..k3 (9)
+  int distort;
   float lo[3], hi[3];
   float sigma, outlier_fraction, outlier_range;
 };
@@ -102,6 +103,15 @@ __global__ void generate_pinhole_kernel(SynthDev d, int64_t n, ST* X, ST* Y, ST*
     float w[3];
     for (int k = 0; k < 3; ++k) w[k] = d.gt[k * 4 + 0] * p[0] + d.gt[k * 4 + 1] * p[1] + d.gt[k * 4 + 2] * p[2] + d.gt[k * 4 + 3];
     float uu = w[0] / w[2], vv = w[1] / w[2];
+    if (d.distort) {  // same model as PinholeDistortModel::residual
+      const float xn = uu, yn = vv, r2 = xn * xn + yn * yn;
+      const float radial = 1.0f + r2 * (d.gt[16] + r2 * (d.gt[17] + r2 * d.gt[20]));
+      const float xy2 = 2.0f * xn * yn;
+      const float xd = xn * radial + d.gt[18] * xy2 + d.gt[19] * (r2 + 2.0f * xn * xn);
+      const float yd = yn * radial + d.gt[18] * (r2 + 2.0f * yn * yn) + d.gt[19] * xy2;
+      uu = d.gt[12] * xd + d.gt[14];
+      vv = d.gt[13] * yd + d.gt[15];
+    }
     if (d.sigma > 0.0f) {
       uu += d.sigma * approx_normal(d.seed, gi, 3);
       vv += d.sigma * approx_normal(d.seed, gi, 7);
@@ -352,9 +362,24 @@ int mopt_store_generate(mopt_store* st, const mopt_synth* desc) {
                                                                                 (double*)st->streams[1]);
       break;
     }
-    case MOPT_MODEL_PINHOLE: {
-      // gt[0..12) = projection matrix M = K T(x_gt) C, supplied by the caller (3x4 row-major)
-      for (int i = 0; i < 12; ++i) d.gt[i] = float(desc->gt[i]);
+    case MOPT_MODEL_PINHOLE:
+    case MOPT_MODEL_PINHOLE_DISTORT: {
+      if (st->model == MOPT_MODEL_PINHOLE) {
+        // gt[0..12) = projection matrix M = K T(x_gt) C, supplied by the caller (3x4 row-major)
+        for (int i = 0; i < 12; ++i) d.gt[i] = float(desc->gt[i]);
+      } else {
+        // gt = the 15 generating parameters [t, omega, fx, fy, cx, cy, k1, k2, p1, p2, k3]; consts = C (4x4)
+        double R[9];
+        rodrigues_host(desc->gt + 3, R);
+        for (int r = 0; r < 3; ++r)
+          for (int col = 0; col < 4; ++col) {
+            double s = desc->gt[r] * desc->consts[12 + col];
+            for (int k = 0; k < 3; ++k) s += R[r * 3 + k] * desc->consts[k * 4 + col];
+            d.gt[r * 4 + col] = float(s);
+          }
+        for (int i = 0; i < 9; ++i) d.gt[12 + i] = float(desc->gt[6 + i]);
+        d.distort = 1;
+      }
       if (f32)
         generate_pinhole_kernel<float><<<int(blocks), threads, 0, ctx->stream>>>(
             d, st->n, (float*)st->streams[0], (float*)st->streams[1], (float*)st->streams[2], (float*)st->streams[3],

@@ -363,6 +363,51 @@ struct Pinhole : IModel<S> {
   S K_[12], C_[16], M_[12];
 };
 
+// NOT in the reference (its camera test has fixed intrinsics and no distortion): pinhole
+// with free intrinsics and OpenCV-style distortion, x = [t, omega, fx, fy, cx, cy, k1, k2, p1, p2, k3],
+//   Pc = T(x) C P;  (xn, yn) = Pc.xy / Pc.z;  r2 = xn^2 + yn^2;  radial = 1 + k1 r2 + k2 r2^2 + k3 r2^3
+//   xd = xn radial + 2 p1 xn yn + p2 (r2 + 2 xn^2);  yd = yn radial + p1 (r2 + 2 yn^2) + 2 p2 xn yn
+//   r = pixel - (fx xd + cx, fy yd + cy).
+template <class S>
+struct PinholeDistort : IModel<S> {
+  PinholeDistort(const S* pts, const S* pix, const S* C44) : pts_(pts), pix_(pix) {
+    for (int i = 0; i < 16; ++i) C_[i] = C44[i];
+    for (int i = 0; i < 12; ++i) TC_[i] = 0;
+    for (int i = 0; i < 9; ++i) in_[i] = 0;
+  }
+  void setup(const S* x) override {
+    S T[16];
+    so3_convert6dof(x, T);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) {
+        S s = 0;
+        for (int k = 0; k < 4; ++k) s += T[r * 4 + k] * C_[k * 4 + c];
+        TC_[r * 4 + c] = s;
+      }
+    for (int i = 0; i < 9; ++i) in_[i] = x[6 + i];
+  }
+  bool f(const S*, S* r, unsigned i) const override {
+    const S* P = pts_ + 3 * size_t(i);
+    S p[3];
+    for (int k = 0; k < 3; ++k)
+      p[k] = TC_[k * 4 + 0] * P[0] + TC_[k * 4 + 1] * P[1] + TC_[k * 4 + 2] * P[2] + TC_[k * 4 + 3];
+    const S xn = p[0] / p[2], yn = p[1] / p[2];
+    const S r2 = xn * xn + yn * yn;
+    const S radial = S(1) + in_[4] * r2 + in_[5] * r2 * r2 + in_[8] * r2 * r2 * r2;
+    const S xd = xn * radial + S(2) * in_[6] * xn * yn + in_[7] * (r2 + S(2) * xn * xn);
+    const S yd = yn * radial + in_[6] * (r2 + S(2) * yn * yn) + S(2) * in_[7] * xn * yn;
+    r[0] = pix_[2 * size_t(i) + 0] - (in_[0] * xd + in_[2]);
+    r[1] = pix_[2 * size_t(i) + 1] - (in_[1] * yd + in_[3]);
+    return true;
+  }
+  bool f_df(const S*, S*, S*, unsigned) const override { return false; }
+  bool has_jacobian() const override { return false; }
+  std::shared_ptr<IModel<S>> clone() const override { return std::make_shared<PinholeDistort>(*this); }
+  const S* pts_;
+  const S* pix_;
+  S C_[16], TC_[12], in_[9];
+};
+
 // ---------------------------------------------------------- linearization ----
 enum JacobianMode { JAC_ANALYTICAL = 0, JAC_FORWARD = 1, JAC_CENTRAL = 2 };
 

@@ -11,7 +11,7 @@ using namespace oracle;
 extern "C" {
 
 enum { ORC_P2P = 0, ORC_EXP_CURVE = 1, ORC_MICHAELIS_MENTEN = 2, ORC_PINHOLE = 3, ORC_POWELL = 4,
-       ORC_POINT_DIST = 5 };
+       ORC_POINT_DIST = 5, ORC_PINHOLE_DISTORT = 6 };
 enum { ORC_LOSS_NONE = 0, ORC_LOSS_GM = 1, ORC_LOSS_HUBER = 2 };
 
 struct orc_cost {
@@ -66,7 +66,8 @@ std::unique_ptr<Holder<S>> build(const orc_cost& c) {
     case ORC_POINT_DIST: na = nb = size_t(c.n) * 3; break;
     case ORC_EXP_CURVE:
     case ORC_MICHAELIS_MENTEN: na = nb = size_t(c.n); break;
-    case ORC_PINHOLE: na = size_t(c.n) * 3; nb = size_t(c.n) * 2; break;
+    case ORC_PINHOLE:
+    case ORC_PINHOLE_DISTORT: na = size_t(c.n) * 3; nb = size_t(c.n) * 2; break;
     default: break;
   }
   h->a = adopt<S>(c.a, c.data_f32 != 0, na, h->a_store);
@@ -78,6 +79,12 @@ std::unique_ptr<Holder<S>> build(const orc_cost& c) {
     case ORC_EXP_CURVE: k.model = std::make_shared<ExpCurve<S>>(h->a, h->b); break;
     case ORC_MICHAELIS_MENTEN: k.model = std::make_shared<MichaelisMenten<S>>(h->a, h->b); break;
     case ORC_POWELL: k.model = std::make_shared<Powell<S>>(); break;
+    case ORC_PINHOLE_DISTORT: {  // consts = C (16, row-major)
+      S C[16];
+      for (int i = 0; i < 16; ++i) C[i] = S(c.consts[i]);
+      k.model = std::make_shared<PinholeDistort<S>>(h->a, h->b, C);
+      break;
+    }
     case ORC_PINHOLE: {
       S K[12], C[16];
       for (int i = 0; i < 12; ++i) K[i] = S(c.consts[i]);

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 # model kinds / enums (mirror oracle_capi.cpp)
-P2P, EXP_CURVE, MICHAELIS_MENTEN, PINHOLE, POWELL, POINT_DIST = range(6)
+P2P, EXP_CURVE, MICHAELIS_MENTEN, PINHOLE, POWELL, POINT_DIST, PINHOLE_DISTORT = range(7)
 LOSS_NONE, LOSS_GM, LOSS_HUBER = range(3)
 JAC_ANALYTICAL, JAC_FORWARD, JAC_CENTRAL = range(3)
 P2P_EXACT, P2P_REFTEST, P2P_REFTEST_COLMAJOR = range(3)

@@ -1,0 +1,115 @@
+"""The n x n calibration case (north star): pinhole + distortion, P = 15, O = 2, numerical Jacobian, 15 x 15
+device solve.  The reference has no such model; parity is against the oracle's restatement
+of the same formulas with the reference's linearization loop."""
+import numpy as np
+import pytest
+
+from oracle import oracle_py as orc
+from tests.common import camera_consts, rel_err
+
+pytestmark = pytest.mark.gpu
+
+X_GT = np.array([-0.01, 0.02, -0.06, 0.018, -0.0013, 0.027, 586.0, 722.0, 638.0, 323.0, -0.12, 0.05, 0.001, -0.0007, 0.01])
+
+
+@pytest.fixture(scope="module")
+def env():
+    from moptimizer_0_b200 import capi
+    c = capi.Context(0)
+    yield capi, c
+    c.close()
+
+
+def fd_noise(x, n, central=False):
+    """Rounding floor of the reference's finite-difference Jacobian column j (linearization.h:85-87,105):
+    the residual is a difference of ~1e3-pixel quantities, so (r(x+h) - r(x)) / h carries ~eps * 1e3 / h_j of
+    noise per residual, which is large for the small-magnitude distortion parameters (h_j = sqrt(eps) |x_j|)."""
+    h = np.sqrt(np.finfo(np.float64).eps) * np.abs(x)
+    h[h == 0] = np.sqrt(np.finfo(np.float64).eps)
+    return 8.0 * np.finfo(np.float64).eps * 1e3 / h * np.sqrt(n)
+
+
+def assert_close_fd(H, b, s, Ho, bo, so, x, n):
+    d = np.sqrt(np.diag(Ho))
+    nz = fd_noise(x, n)
+    tolH = 1e-6 * np.outer(d, d) + np.outer(nz, d) + np.outer(d, nz)
+    assert np.all(np.abs(H - Ho) <= tolH), np.max(np.abs(H - Ho) / tolH)
+    tolb = 1e-6 * d * np.sqrt(max(so, 1e-300)) + nz * np.sqrt(max(so, 1e-300))
+    assert np.all(np.abs(b - bo) <= tolb), np.max(np.abs(b - bo) / tolb)
+    assert abs(s - so) <= 1e-10 * so
+
+
+def make_store(capi, ctx, n, dtype, sigma=0.3, seed=3):
+    Cm = camera_consts()[12:]
+    st = capi.Store(ctx, capi.MODEL_PINHOLE_DISTORT, n, dtype)
+    st.generate(seed=seed, gt=X_GT, lo=(2.0, -1.0, -0.5), hi=(5.0, 1.0, 1.0), noise_sigma=sigma, consts=Cm)
+    return st, Cm
+
+
+@pytest.mark.parametrize("jac", [1, 2])
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 4097, 50_000])
+def test_wide_linearization_matches_oracle(env, jac, n):
+    capi, ctx = env
+    st, Cm = make_store(capi, ctx, n, capi.F64)
+    pts, pix = st.download(0), st.download(1)
+    x = X_GT * (1.0 + 0.01 * np.cos(np.arange(15)))
+    prob = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, jac, capi.F64, consts=Cm)
+    H, b, s = ctx.linearize(st, prob, x)
+    oc = orc.Cost(orc.PINHOLE_DISTORT, 15, 2, n, a=pts, b=pix, consts=Cm, jac_mode=jac)
+    Ho, bo, so = orc.linearize(oc, x)
+    # entries of H span 12 orders of magnitude (focal lengths vs distortion): per-entry natural scale, plus the
+    # finite-difference rounding floor of each column
+    assert_close_fd(H, b, s, Ho, bo, so, x, n)
+    assert ctx.compute_cost(st, prob, x) == pytest.approx(so, rel=1e-10)
+    st.close()
+
+
+def test_wide_covariance_and_loss(env):
+    capi, ctx = env
+    st, Cm = make_store(capi, ctx, 20_000, capi.F64)
+    pts, pix = st.download(0), st.download(1)
+    cov = np.array([[2.0, 0.3], [0.3, 0.5]])
+    prob = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL, capi.F64, consts=Cm, covariance=cov,
+                             loss=capi.LOSS_HUBER, loss_param=0.4)
+    x = X_GT * (1.0 + 0.005 * np.sin(np.arange(15)))
+    H, b, s = ctx.linearize(st, prob, x)
+    oc = orc.Cost(orc.PINHOLE_DISTORT, 15, 2, 20_000, a=pts, b=pix, consts=Cm, jac_mode=orc.JAC_CENTRAL, cov=cov,
+                  loss=orc.LOSS_HUBER, loss_param=0.4)
+    Ho, bo, so = orc.linearize(oc, x)
+    d = np.sqrt(np.diag(Ho))
+    nz = fd_noise(x, 20_000)
+    tolH = 1e-6 * np.outer(d, d) + 2.0 * (np.outer(nz, d) + np.outer(d, nz))
+    assert np.all(np.abs(H - Ho) <= tolH) and abs(s - so) <= 1e-10 * so
+    st.close()
+
+
+def test_wide_lm_15x15_device_solve(env):
+    capi, ctx = env
+    n = 2_000_000
+    st, Cm = make_store(capi, ctx, n, capi.F32, sigma=0.3)
+    prob = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL, capi.F64, consts=Cm)
+    x0 = X_GT.copy()
+    x0[:6] = 0.0
+    x0[6:10] *= np.array([1.03, 0.97, 1.01, 0.99])
+    x0[10:] = 0.0
+    r = ctx.lm_minimize([st], [prob], x0, max_iterations=50)
+    err = np.abs(r.x - X_GT)
+    assert np.all(err[:6] < 2e-3), r.x
+    assert np.all(err[6:10] < 1.0), r.x          # focal lengths / principal point in pixels
+    assert np.all(err[10:] < 5e-3), r.x
+    # same problem, same start, oracle on a 100 k sample converges to the same neighbourhood
+    m = 100_000
+    pts, pix = st.download(0, np.float64, 0, m), st.download(1, np.float64, 0, m)
+    sm = capi.Store(ctx, capi.MODEL_PINHOLE_DISTORT, m, capi.F64)
+    sm.upload(0, pts)
+    sm.upload(1, pix)
+    rd = ctx.lm_minimize([sm], [prob], x0, max_iterations=50)
+    ro = orc.lm_minimize([orc.Cost(orc.PINHOLE_DISTORT, 15, 2, m, a=pts, b=pix, consts=Cm, jac_mode=orc.JAC_CENTRAL,
+                                   cost_threads=8)], x0, 50)
+    assert rd.status == ro.status
+    # well-determined parameters agree tightly; the higher-order distortion terms (k2, k3) sit in a flat valley
+    # where the stopping point is decided by finite-difference rounding (see fd_noise)
+    assert np.allclose(rd.x[:10], ro.x[:10], rtol=1e-6, atol=1e-6)
+    assert np.allclose(rd.x[10:], ro.x[10:], atol=5e-5)
+    sm.close()
+    st.close()

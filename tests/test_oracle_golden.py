@@ -238,3 +238,22 @@ def test_threaded_linearization_matches_serial():
         H1, b1, s1 = orc.linearize(c, x, nthreads=1)
         H8, b8, s8 = orc.linearize(c, x, nthreads=8)
         assert rel_err(H8, H1) < 1e-12 and rel_err(b8, b1) < 1e-12 and s8 == pytest.approx(s1, rel=1e-12)
+
+
+# ---- pinhole + distortion (new model, BASELINE.json configs[4]): consistency with the reference camera model
+def test_pinhole_distort_reduces_to_reference_camera_model():
+    from tests.common import camera_consts
+    consts = camera_consts()
+    K, Cm = consts[:12].reshape(3, 4), consts[12:]
+    pts = np.array(FX["camera"]["points"], dtype=np.float64)
+    pix = np.array(FX["camera"]["pixels"], dtype=np.float64)
+    x6 = np.array([0.01, -0.02, 0.03, 0.02, -0.01, 0.015])
+    # zero distortion + the reference intrinsics => identical residuals, and the 6x6 extrinsic block of H agrees
+    x15 = np.concatenate([x6, [K[0, 0], K[1, 1], K[0, 2], K[1, 2]], np.zeros(5)])
+    ref = orc.Cost(orc.PINHOLE, 6, 2, 5, a=pts, b=pix, consts=consts, jac_mode=orc.JAC_CENTRAL)
+    dis = orc.Cost(orc.PINHOLE_DISTORT, 15, 2, 5, a=pts, b=pix, consts=Cm, jac_mode=orc.JAC_CENTRAL)
+    H6, b6, s6 = orc.linearize(ref, x6)
+    H15, b15, s15 = orc.linearize(dis, x15)
+    assert s15 == pytest.approx(s6, rel=1e-12)
+    assert rel_err(H15[:6, :6], H6) < 1e-6 and rel_err(b15[:6], b6) < 1e-6
+    assert np.allclose(H15, H15.T)
