@@ -96,8 +96,16 @@ typedef enum mopt_jacobian {
 typedef enum mopt_p2p_variant {
   MOPT_P2P_EXACT = 0,           /* [I | -[R p]x J_l(omega)] — exact for the additive update of levenberg_marquadt_dyn.cpp:83 */
   MOPT_P2P_REFTEST = 1,         /* [I | -[p]x], row-major as linearization.h:17-18 requires (tst/point2point.cpp:72-75) */
-  MOPT_P2P_REFTEST_COLMAJOR = 2 /* same values written column-major, bit-faithful to tst/point2point.cpp:18,71 */
+  MOPT_P2P_REFTEST_COLMAJOR = 2, /* same values written column-major, bit-faithful to tst/point2point.cpp:18,71 */
+  MOPT_P2P_LEFT = 3 /* [I | -[R p]x]: derivative w.r.t. a left SO(3) perturbation, for manifold = MOPT_MANIFOLD_SO3_LEFT */
 } mopt_p2p_variant;
+
+/* Parameter update rule.  The reference adds delta to x (levenberg_marquadt_dyn.cpp:82-83, "TODO Manifold
+ * operation"); MOPT_MANIFOLD_SO3_LEFT finishes that TODO as an opt-in for models whose
+ * x[3..5] is a rotation vector: omega <- Log(Exp(delta_omega) Exp(omega)) with so3::Exp / so3::Log
+ * (src/so3.cpp:43-57,96-105), every other component additive.  Jacobians are then taken with respect to the
+ * tangent perturbation at 0 (finite-difference steps sqrt(eps) on the rotation block). */
+typedef enum mopt_manifold { MOPT_MANIFOLD_ADDITIVE = 0, MOPT_MANIFOLD_SO3_LEFT = 1 } mopt_manifold;
 
 /* loss_function/loss_function.h:20-23, loss_function/geman_mcclure.h:7-19; Huber is new. */
 typedef enum mopt_loss {
@@ -121,6 +129,8 @@ typedef struct mopt_problem {
   double loss_param;
   double covariance[MOPT_MAX_OUTPUTS * MOPT_MAX_OUTPUTS]; /* O x O column-major, symmetric (setCovariance, cost_function.h:38-40) */
   double consts[32];                                       /* model constants, see mopt_model */
+  int32_t manifold; /* mopt_manifold: how x + delta is formed and what the Jacobian differentiates */
+  int32_t reserved;
 } mopt_problem;
 
 /* Optimizer knobs: optimizer.h:19,33-37, levenberg_marquadt_dyn.cpp:9,16, levenberg_marquadt_dyn.h:22-24. */
@@ -225,6 +235,19 @@ MOPT_API void mopt_lm_default_options(mopt_lm_options* options);
 /* ---- small host-side math kept for API parity (src/so3.cpp:7-19,43-57; delta.h:11-16) -------- */
 MOPT_API int mopt_so3_convert6dof(const double* x, double* T16_rowmajor);
 MOPT_API int mopt_ldlt_solve(int n, const double* A_colmajor, const double* rhs, double* out);
+
+/* ---- point-cloud ingest (input side of the path) ---------------------------------------------------- */
+/* tst/point2point.cpp:125-138 `txt_cloud_loader`: whitespace-separated records of `columns` numbers (the
+ * fixture tst/data/fachada.txt has 6: x y z r g b); the first `keep` of each record are stored, AoS, in
+ * `host_dtype`.  Parsing stops at the first malformed record, as the reference's stream extraction does.
+ * `pinned` != 0 allocates page-locked memory (needs a CUDA device) so mopt_store_upload runs at full speed.
+ * Free with mopt_cloud_free(ptr, pinned). */
+MOPT_API int mopt_cloud_read_text(const char* path, int columns, int keep, int host_dtype, int pinned, void** out,
+                                  int64_t* n);
+/* Raw binary cache of a parsed cloud: 24-byte header {"MOPTCLD1", int64 n, int32 dtype, int32 keep} + AoS data. */
+MOPT_API int mopt_cloud_write_binary(const char* path, const void* data, int host_dtype, int keep, int64_t n);
+MOPT_API int mopt_cloud_read_binary(const char* path, int pinned, int* host_dtype, int* keep, void** out, int64_t* n);
+MOPT_API int mopt_cloud_free(void* ptr, int pinned);
 
 /* Pinned host memory for callers that want full-speed uploads. */
 MOPT_API int mopt_host_alloc(void** ptr, uint64_t bytes);

@@ -35,6 +35,10 @@ class CostFunctionBase {
 
   inline void setLossFunction(LossFunctionPtr loss_function) { loss_function_ = loss_function; }
   inline void setCovariance(const covariance::MatrixPtr<Scalar> covariance) { covariance_ = covariance; }
+  /// New (opt-in): MOPT_MANIFOLD_SO3_LEFT makes the optimizer update the rotation block of x
+  /// with so3::Exp/Log instead of adding delta (the reference's "TODO Manifold operation"); Jacobians are then
+  /// taken in the tangent space (use the MOPT_P2P_LEFT variant for analytical point2point).
+  inline void setManifold(int manifold) { manifold_ = manifold; }
 
   virtual void update(const Scalar* x) { model_->update(x); }
   virtual Scalar computeCost(const Scalar* x) = 0;
@@ -58,6 +62,7 @@ class CostFunctionBase {
     p->num_outputs = num_outputs;
     p->jacobian = jacobian;
     p->compute_dtype = device::dtypeOf<Scalar>();
+    p->manifold = manifold_;
     if (dynamic_cast<const loss::NoLoss<Scalar>*>(loss_function_.get())) {
       p->loss = MOPT_LOSS_NONE;
     } else if (auto* gm = dynamic_cast<const loss::GemmanMCClure<Scalar>*>(loss_function_.get())) {
@@ -87,6 +92,7 @@ class CostFunctionBase {
   }
 
   int num_residuals_;
+  int manifold_ = MOPT_MANIFOLD_ADDITIVE;
   ModelPtr model_;
   LossFunctionPtr loss_function_;
   covariance::MatrixPtr<Scalar> covariance_;

@@ -21,7 +21,8 @@ F32, F64 = 0, 1
 (MODEL_POINT2POINT, MODEL_EXP_CURVE, MODEL_MICHAELIS_MENTEN, MODEL_PINHOLE, MODEL_POWELL,
  MODEL_POINT_DIST, MODEL_PINHOLE_DISTORT) = range(7)
 JAC_ANALYTICAL, JAC_FORWARD, JAC_CENTRAL = range(3)
-P2P_EXACT, P2P_REFTEST, P2P_REFTEST_COLMAJOR = range(3)
+P2P_EXACT, P2P_REFTEST, P2P_REFTEST_COLMAJOR, P2P_LEFT = range(4)
+MANIFOLD_ADDITIVE, MANIFOLD_SO3_LEFT = 0, 1
 LOSS_NONE, LOSS_GEMAN_MCCLURE, LOSS_HUBER = range(3)
 STATUS = ["CONVERGED", "MAXIMUM_ITERATIONS_REACHED", "SMALL_DELTA", "NUMERIC_ERROR", "FATAL_ERROR"]
 MODEL_SHAPE = {  # model -> (P, O, ncomp_a, ncomp_b)
@@ -37,6 +38,7 @@ EXPORTS = [
     "mopt_store_generate", "mopt_linearize", "mopt_compute_cost", "mopt_linearize_async", "mopt_ctx_result",
     "mopt_upload_and_linearize", "mopt_lm_minimize", "mopt_lm_default_options", "mopt_so3_convert6dof",
     "mopt_ldlt_solve", "mopt_host_alloc", "mopt_host_free",
+    "mopt_cloud_read_text", "mopt_cloud_write_binary", "mopt_cloud_read_binary", "mopt_cloud_free",
 ]
 
 
@@ -44,7 +46,8 @@ class Problem(C.Structure):
     _fields_ = [("model", C.c_int32), ("variant", C.c_int32), ("num_parameters", C.c_int32),
                 ("num_outputs", C.c_int32), ("jacobian", C.c_int32), ("compute_dtype", C.c_int32),
                 ("loss", C.c_int32), ("has_covariance", C.c_int32), ("loss_param", C.c_double),
-                ("covariance", C.c_double * (MAX_OUTPUTS * MAX_OUTPUTS)), ("consts", C.c_double * 32)]
+                ("covariance", C.c_double * (MAX_OUTPUTS * MAX_OUTPUTS)), ("consts", C.c_double * 32),
+                ("manifold", C.c_int32), ("reserved", C.c_int32)]
 
 
 class LmOptions(C.Structure):
@@ -116,6 +119,12 @@ def lib():
         L.mopt_ldlt_solve.argtypes = [C.c_int, dp, dp, dp]
         L.mopt_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
         L.mopt_host_free.argtypes = [vp]
+        L.mopt_cloud_read_text.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp),
+                                           C.POINTER(i64)]
+        L.mopt_cloud_write_binary.argtypes = [C.c_char_p, vp, C.c_int, C.c_int, i64]
+        L.mopt_cloud_read_binary.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                             C.POINTER(vp), C.POINTER(i64)]
+        L.mopt_cloud_free.argtypes = [vp, C.c_int]
         _lib = L
     return _lib
 
@@ -131,9 +140,10 @@ def _dp(a: np.ndarray):
 
 def make_problem(model: int, jacobian: int = JAC_ANALYTICAL, compute_dtype: int = F64, loss: int = LOSS_NONE,
                  loss_param: float = 0.0, variant: int = P2P_EXACT, covariance: Optional[np.ndarray] = None,
-                 consts: Optional[Sequence[float]] = None) -> Problem:
+                 consts: Optional[Sequence[float]] = None, manifold: int = 0) -> Problem:
     P, O, _, _ = MODEL_SHAPE[model]
     p = Problem()
+    p.manifold = manifold
     p.model, p.variant, p.num_parameters, p.num_outputs = model, variant, P, O
     p.jacobian, p.compute_dtype, p.loss, p.loss_param = jacobian, compute_dtype, loss, float(loss_param)
     p.has_covariance = 0
@@ -304,6 +314,37 @@ class Store:
         if self._h:
             lib().mopt_store_destroy(self._h)
             self._h = C.c_void_p()
+
+
+def cloud_read_text(path: str, columns: int = 6, keep: int = 3, dtype=np.float64, pinned: bool = False) -> np.ndarray:
+    """tst/point2point.cpp:125-138 loader: text records -> (n, keep) array (copied out of the library buffer)."""
+    ptr, n = C.c_void_p(), C.c_int64(0)
+    dt = F32 if np.dtype(dtype) == np.float32 else F64
+    check(lib().mopt_cloud_read_text(path.encode(), columns, keep, dt, 1 if pinned else 0, C.byref(ptr), C.byref(n)))
+    try:
+        ctype = C.c_float if dt == F32 else C.c_double
+        arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(max(n.value, 0) * keep,)).copy()
+    finally:
+        lib().mopt_cloud_free(ptr, 1 if pinned else 0)
+    return arr.reshape(n.value, keep)
+
+
+def cloud_write_binary(path: str, data: np.ndarray):
+    data = np.ascontiguousarray(data)
+    assert data.dtype in (np.float32, np.float64) and data.ndim == 2
+    dt = F32 if data.dtype == np.float32 else F64
+    check(lib().mopt_cloud_write_binary(path.encode(), data.ctypes.data, dt, data.shape[1], data.shape[0]))
+
+
+def cloud_read_binary(path: str) -> np.ndarray:
+    ptr, n, dt, keep = C.c_void_p(), C.c_int64(0), C.c_int(0), C.c_int(0)
+    check(lib().mopt_cloud_read_binary(path.encode(), 0, C.byref(dt), C.byref(keep), C.byref(ptr), C.byref(n)))
+    try:
+        ctype = C.c_float if dt.value == F32 else C.c_double
+        arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(max(n.value, 0) * keep.value,)).copy()
+    finally:
+        lib().mopt_cloud_free(ptr, 0)
+    return arr.reshape(n.value, keep.value)
 
 
 def ldlt_solve_device(A: np.ndarray, rhs: np.ndarray) -> np.ndarray:

@@ -112,7 +112,7 @@ __global__ void lm_init_kernel(LmState* st, CostSlot* slots, LmInit in) {
 // One optimizer transition between passes; also publishes the done flag of this slot to the host.
 __global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* slots, int* flag) {
   __shared__ int s_act;
-  if (threadIdx.x == 0) s_act = st->scalar_f32 ? lm_step_thread<float>(st, trial) : lm_step_thread<double>(st, trial);
+  if (threadIdx.x == 0) s_act = st->scalar_f32 ? lm_step_thread<float>(st, trial, slots[0].cost) : lm_step_thread<double>(st, trial, slots[0].cost);
   __syncthreads();
   if (s_act) {
     const int nc = st->n_costs;
@@ -147,7 +147,12 @@ int validate_problem(const mopt_store* st, const mopt_problem* p, bool need_line
     }
   }
   if (p->model == MOPT_MODEL_POINT2POINT)
-    MOPT_REQUIRE(p->variant >= MOPT_P2P_EXACT && p->variant <= MOPT_P2P_REFTEST_COLMAJOR, "unknown point2point variant");
+    MOPT_REQUIRE(p->variant >= MOPT_P2P_EXACT && p->variant <= MOPT_P2P_LEFT, "unknown point2point variant");
+  MOPT_REQUIRE(p->manifold == MOPT_MANIFOLD_ADDITIVE || p->manifold == MOPT_MANIFOLD_SO3_LEFT, "unknown manifold");
+  if (p->manifold == MOPT_MANIFOLD_SO3_LEFT)
+    MOPT_REQUIRE(p->model == MOPT_MODEL_POINT2POINT || p->model == MOPT_MODEL_PINHOLE ||
+                     p->model == MOPT_MODEL_PINHOLE_DISTORT,
+                 "MOPT_MANIFOLD_SO3_LEFT needs a model whose x[3..5] is a rotation vector");
   if (p->has_covariance) {
     const int O = sh.O;
     for (int r = 0; r < O; ++r)
@@ -165,6 +170,9 @@ void fill_cost(const mopt_problem* p, CostDev* c) {
   c->model = p->model; c->variant = p->variant; c->P = p->num_parameters; c->O = p->num_outputs;
   c->jacobian = p->jacobian; c->loss = p->loss; c->has_cov = p->has_covariance ? 1 : 0;
   c->compute_dtype = p->compute_dtype; c->loss_param = p->loss_param;
+  c->manifold = p->manifold;
+  c->rot_offset = (p->model == MOPT_MODEL_POINT2POINT || p->model == MOPT_MODEL_PINHOLE ||
+                   p->model == MOPT_MODEL_PINHOLE_DISTORT) ? 3 : -1;
   const int O = p->num_outputs;
   for (int i = 0; i < O * O; ++i) c->cov[i] = p->has_covariance ? p->covariance[i] : ((i % (O + 1) == 0) ? 1.0 : 0.0);
   std::memcpy(c->consts, p->consts, sizeof(c->consts));
@@ -205,7 +213,8 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
   const PassArgs a = make_args(ctx, st, slot, accumulate, mode_override);
   PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
   if (p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL)
-    return launch_p2p_moment(L, st->dtype, p->compute_dtype, p->loss, p->variant == MOPT_P2P_EXACT, a);
+    return launch_p2p_moment(L, st->dtype, p->compute_dtype, p->loss,
+                             p->variant == MOPT_P2P_EXACT || p->variant == MOPT_P2P_LEFT, a);
   if (p->model == MOPT_MODEL_PINHOLE_DISTORT) return launch_wide(L, p->model, st->dtype, p->compute_dtype, a);
   return launch_dense(L, p->model, p->jacobian != MOPT_JAC_ANALYTICAL, st->dtype, p->compute_dtype, a);
 }
@@ -465,6 +474,7 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
     MOPT_REQUIRE(stores[c] && stores[c]->ctx == ctx, "store does not belong to this context");
     MOPT_TRY(validate_problem(stores[c], &problems[c], true));
     MOPT_REQUIRE(problems[c].num_parameters == P, "all cost terms must share the parameter vector");
+    MOPT_REQUIRE(problems[c].manifold == problems[0].manifold, "all cost terms must use the same manifold");
   }
   MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
   std::memset(report, 0, sizeof(*report));

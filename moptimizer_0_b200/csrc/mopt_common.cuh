@@ -68,6 +68,8 @@ struct CostDev {
   double loss_param;
   double cov[kMaxO * kMaxO];  // column-major O x O
   double consts[32];
+  int manifold;    // mopt_manifold
+  int rot_offset;  // index of the rotation-vector block of x, or -1
 };
 
 // Packed result of one pass: H upper triangle (row-major, P(P+1)/2), then b (P), then sum.

@@ -107,7 +107,7 @@ __device__ inline void lm_finish(LmState* st, int status) {
 
 // Solve (H + lambda diag(H)) delta = -b (levenberg_marquadt_dyn.cpp:65,78-80), xi = x + delta (:83).
 template <typename S>
-__device__ inline void lm_solve_propose(LmState* st) {
+__device__ inline void lm_solve_propose(LmState* st, const CostDev& cost0) {
   const int P = st->P;
   S A[kMaxP * kMaxP], nb[kMaxP], d[kMaxP];
   for (int r = 0; r < P; ++r)
@@ -120,12 +120,13 @@ __device__ inline void lm_solve_propose(LmState* st) {
   for (int i = 0; i < P; ++i) A[i + i * P] = A[i + i * P] + lam * A[i + i * P];
   for (int i = 0; i < P; ++i) nb[i] = -S(st->cur.v[P * (P + 1) / 2 + i]);
   ldlt_solve_dev<S>(P, A, nb, d);
-  for (int i = 0; i < P; ++i) {
-    st->delta[i] = double(d[i]);
-    const S xi = S(st->x[i]) + d[i];
-    st->xi[i] = double(xi);
-    st->x_eval[i] = double(xi);
+  for (int i = 0; i < P; ++i) st->delta[i] = double(d[i]);
+  if (cost0.manifold == MOPT_MANIFOLD_SO3_LEFT) {
+    retract_dev(cost0, st->x, st->delta, st->xi, sizeof(S) == 4);  // opt-in manifold update
+  } else {
+    for (int i = 0; i < P; ++i) st->xi[i] = double(S(st->x[i]) + d[i]);  // levenberg_marquadt_dyn.cpp:83
   }
+  for (int i = 0; i < P; ++i) st->x_eval[i] = st->xi[i];
   st->phase = LM_PHASE_TRIAL;
   st->pass_mode = st->speculative ? PASS_LINEARIZE : PASS_COST;
 }
@@ -133,7 +134,7 @@ __device__ inline void lm_solve_propose(LmState* st) {
 // One transition of the optimizer.  Returns 1 if a new evaluation point x_eval was set (the caller then
 // runs model setup for every cost), 0 if the optimization ended.
 template <typename S>
-__device__ inline int lm_step_thread(LmState* st, const PassResult* trial) {
+__device__ inline int lm_step_thread(LmState* st, const PassResult* trial, const CostDev& cost0) {
   if (st->done) return 0;
   const int P = st->P;
   const int npk = packed_size(P);
@@ -171,7 +172,7 @@ __device__ inline int lm_step_thread(LmState* st, const PassResult* trial) {
       st->nu = double(S(2) * S(st->nu));
       st->k += 1;
       if (st->k < st->lm_max_it) {
-        lm_solve_propose<S>(st);
+        lm_solve_propose<S>(st, cost0);
         return 1;
       }
       // inner tries exhausted: the outer loop re-linearizes at the unchanged x (identical H, b, y0)
@@ -219,7 +220,7 @@ __device__ inline int lm_step_thread(LmState* st, const PassResult* trial) {
     st->nu = 2.0;
     st->k = 0;
     if (st->lm_max_it > 0) {
-      lm_solve_propose<S>(st);
+      lm_solve_propose<S>(st, cost0);
       return 1;
     }
     st->it += 1;

@@ -50,6 +50,36 @@ __device__ inline void so3_left_jacobian_dev(const double w[3], double J[9]) {
     }
 }
 
+// src/so3.cpp:96-105 — so3::Log as the reference defines it (first-order branch below theta = 1e-3).
+__device__ inline void so3_log_dev(const double R[9], double w[3]) {
+  const double tr = R[0] + R[4] + R[8];
+  const double theta = (tr > 3.0 - 1e-6) ? 0.0 : acos(0.5 * (tr - 1.0));
+  const double K[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  const double f = (fabs(theta) < 0.001) ? 0.5 : 0.5 * theta / sin(theta);
+  for (int i = 0; i < 3; ++i) w[i] = f * K[i];
+}
+
+// x (+) delta.  Additive everywhere (levenberg_marquadt_dyn.cpp:83) except, with MOPT_MANIFOLD_SO3_LEFT, on
+// the rotation-vector block: omega <- Log(Exp(delta_omega) Exp(omega)).  `f32` rounds like the float Scalar.
+__device__ inline void retract_dev(const CostDev& c, const double* x, const double* delta, double* out, bool f32) {
+  for (int i = 0; i < c.P; ++i) out[i] = f32 ? double(float(x[i]) + float(delta[i])) : x[i] + delta[i];
+  if (c.manifold == MOPT_MANIFOLD_SO3_LEFT && c.rot_offset >= 0) {
+    const int o = c.rot_offset;
+    double Rx[9], Rd[9], Rn[9];
+    if (f32) { so3_exp_dev<float>(x + o, Rx); so3_exp_dev<float>(delta + o, Rd); }
+    else { so3_exp_dev<double>(x + o, Rx); so3_exp_dev<double>(delta + o, Rd); }
+    for (int r = 0; r < 3; ++r)
+      for (int col = 0; col < 3; ++col) {
+        double s = 0.0;
+        for (int k = 0; k < 3; ++k) s += Rd[r * 3 + k] * Rx[k * 3 + col];
+        Rn[r * 3 + col] = s;
+      }
+    double w[3];
+    so3_log_dev(Rn, w);
+    for (int i = 0; i < 3; ++i) out[o + i] = f32 ? double(float(w[i])) : w[i];
+  }
+}
+
 // One parameter set for model `c.model` at parameters xs[0..P).
 __device__ inline void setup_one_set(const CostDev& c, const double* xs, double* set) {
   for (int i = 0; i < kSetSize; ++i) set[i] = 0.0;
@@ -170,6 +200,16 @@ __device__ inline void setup_cost(const CostDev& c, const double* x, ParamBlock*
         h = ms * fabs(x[j]);
         if (h == 0.0) h = ms;
         xs[j] = minus ? x[j] - h : x[j] + h;
+      }
+      if (c.manifold == MOPT_MANIFOLD_SO3_LEFT && c.rot_offset >= 0 && j >= c.rot_offset && j < c.rot_offset + 3) {
+        // tangent coordinate of the rotation block is 0 at x, so the reference's rule (:85-87) gives h = sqrt(eps)
+        h = f32 ? double(sqrtf(1.1920928955078125e-07f)) : sqrt(2.220446049250313e-16);
+        double d[kMaxP];
+        for (int i = 0; i < P; ++i) d[i] = 0.0;
+        d[j] = minus ? -h : h;
+        double base[kMaxP];
+        for (int i = 0; i < P; ++i) base[i] = f32 ? double(float(x[i])) : x[i];
+        retract_dev(c, base, d, xs, f32);
       }
       if (!minus) pb->h[j] = h;
     }

@@ -84,6 +84,41 @@ inline void so3_convert6dof(const S* x, S T[16]) {
   T[15] = 1;
 }
 
+// src/so3.cpp:96-105 — so3::Log exactly as the reference defines it.  R row-major.
+template <class S>
+inline void so3_log(const S R[9], S w[3]) {
+  const S tr = R[0] + R[4] + R[8];
+  const S theta = (tr > S(3.0) - S(1e-6)) ? S(0.0) : std::acos(S(0.5) * (tr - S(1)));
+  const S K[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  if (std::fabs(theta) < S(0.001)) {
+    for (int i = 0; i < 3; ++i) w[i] = S(0.5) * K[i];
+  } else {
+    for (int i = 0; i < 3; ++i) w[i] = S(0.5) * theta / std::sin(theta) * K[i];
+  }
+}
+
+// x (+) delta: additive (levenberg_marquadt_dyn.cpp:82-83) or, as the opt-in that finishes the reference's
+// "TODO Manifold operation" (SURVEY.md §8f-3), a left SO(3) perturbation of the rotation-vector block x[3..5]:
+// omega <- Log(Exp(delta_omega) Exp(omega)).
+enum Manifold { MANIFOLD_ADDITIVE = 0, MANIFOLD_SO3_LEFT = 1 };
+template <class S>
+inline void retract(int manifold, int P, const S* x, const S* delta, S* out) {
+  for (int i = 0; i < P; ++i) out[i] = x[i] + delta[i];
+  if (manifold == MANIFOLD_SO3_LEFT && P >= 6) {
+    S Rx[9], Rd[9], Rn[9], w[3];
+    so3_exp(x + 3, Rx);
+    so3_exp(delta + 3, Rd);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        S s = 0;
+        for (int k = 0; k < 3; ++k) s += Rd[r * 3 + k] * Rx[k * 3 + c];
+        Rn[r * 3 + c] = s;
+      }
+    so3_log(Rn, w);
+    for (int i = 0; i < 3; ++i) out[3 + i] = w[i];
+  }
+}
+
 // Full closed-form left Jacobian of SO(3):  I + (1-cos)/th^2 [w]x + (th-sin)/th^3 [w]x^2.
 // (The reference's so3::leftJacobian, src/so3.cpp:141-155, omits the [w]x^2 term; the
 //  exact form is needed for an analytical Jacobian that agrees with finite differences.)
@@ -157,6 +192,7 @@ enum P2PJacobian {
   P2P_REFTEST = 1,           // [I | -[p]x] stored row-major (tst/point2point.cpp:72-75, layout fixed)
   P2P_REFTEST_COLMAJOR = 2,  // same values written column-major into the row-major buffer,
                              // bit-faithful to tst/point2point.cpp:18,71 (scrambled H)
+  P2P_LEFT = 3,              // [I | -[R p]x]: derivative w.r.t. a left SO(3) perturbation (MANIFOLD_SO3_LEFT)
 };
 
 // tst/point2point.cpp:24-84 — r = T p - q;  data as AoS xyz.
@@ -190,7 +226,7 @@ struct Point2Point : IModel<S> {
     S wp[3];
     residual(i, r, wp);
     const S* p = src_ + 3 * size_t(i);
-    const S* v = (jac_ == P2P_EXACT) ? wp : p;
+    const S* v = (jac_ == P2P_EXACT || jac_ == P2P_LEFT) ? wp : p;
     // -[v]x
     const S nsk[9] = {0, v[2], -v[1], -v[2], 0, v[0], v[1], -v[0], 0};
     S right[9];
@@ -483,14 +519,12 @@ struct CostComputation {
       xm.assign(P_, std::vector<S>(x, x + P_));
       mm.resize(P_);
     }
+    (void)min_step;
     for (int j = 0; j < P_; ++j) {
-      h[j] = min_step * std::fabs(x[j]);  // see SURVEY.md §3.3 hazard: must be fabs
-      if (h[j] == S(0)) h[j] = min_step;
-      xp[j][j] += h[j];
+      perturbed(x, j, h[j], xp[j], mode == JAC_CENTRAL ? &xm[j] : nullptr);
       mp[j] = m.clone();
       mp[j]->setup(xp[j].data());
       if (mode == JAC_CENTRAL) {
-        xm[j][j] -= h[j];
         mm[j] = m.clone();
         mm[j]->setup(xm[j].data());
       }
@@ -528,10 +562,8 @@ struct CostComputation {
     std::vector<std::shared_ptr<IModel<S>>> mp(P_), mm(P_);
     if (mode != JAC_ANALYTICAL)
       for (int j = 0; j < P_; ++j) {
-        h[j] = min_step * std::fabs(x[j]);
-        if (h[j] == S(0)) h[j] = min_step;
-        xp[j][j] += h[j];
-        xm[j][j] -= h[j];
+        (void)min_step;
+        perturbed(x, j, h[j], xp[j], &xm[j]);
         mp[j] = m.clone();
         mp[j]->setup(xp[j].data());
         mm[j] = m.clone();
@@ -606,7 +638,30 @@ struct CostComputation {
     sum += e2;
   }
 
+  // Step and perturbed copies of x along parameter j: h_j = sqrt(eps) |x_j| (sqrt(eps) if that is 0),
+  // linearization.h:78,85-89.  With MANIFOLD_SO3_LEFT the rotation block is perturbed on the manifold and
+  // its tangent coordinate is 0, hence h_j = sqrt(eps).
+  void perturbed(const S* x, int j, S& h, std::vector<S>& plus, std::vector<S>* minus) const {
+    const S min_step = std::sqrt(std::numeric_limits<S>::epsilon());
+    h = min_step * std::fabs(x[j]);  // see SURVEY.md §3.3 hazard: must be fabs
+    if (h == S(0)) h = min_step;
+    if (manifold_ == MANIFOLD_SO3_LEFT && P_ >= 6 && j >= 3 && j < 6) {
+      h = min_step;
+      std::vector<S> d(P_, S(0));
+      d[j] = h;
+      retract(manifold_, P_, x, d.data(), plus.data());
+      if (minus) {
+        d[j] = -h;
+        retract(manifold_, P_, x, d.data(), minus->data());
+      }
+    } else {
+      plus[j] += h;
+      if (minus) (*minus)[j] -= h;
+    }
+  }
+
   static constexpr int kMaxP = 16, kMaxO = 4;
+  int manifold_ = MANIFOLD_ADDITIVE;
   int P_, O_;
   std::vector<S> r_, rp_, J_;
 
@@ -700,8 +755,10 @@ struct Cost {  // include/moptimizer/cost_function.h:15-59 + the *_dyn wrappers
   int jac_mode;      // JAC_ANALYTICAL => computeHessian, else computeHessianNumerical
   int cost_threads = 1;
   bool float_carry = false;
+  int manifold = MANIFOLD_ADDITIVE;
   S linearize(const S* x, S* H, S* b) {
     CostComputation<S> cc(P, O);
+    cc.manifold_ = manifold;
     if (jac_mode == JAC_ANALYTICAL) return cc.computeHessian(x, C.data(), *loss, H, b, *model, n);
     return cc.computeHessianNumerical(x, C.data(), *loss, H, b, *model, n, jac_mode);
   }
@@ -764,7 +821,8 @@ inline Status lm_minimize(std::vector<Cost<S>*>& costs, int P, int max_iteration
       for (int d = 0; d < P; ++d) A[d + size_t(d) * P] += lambda * H[d + size_t(d) * P];
       for (int d = 0; d < P; ++d) nb[d] = -b[d];
       ldlt_solve(P, A.data(), nb.data(), delta.data());
-      for (int d = 0; d < P; ++d) xi[d] = x0[d] + delta[d];  // additive, no manifold (:82-83)
+      // additive, no manifold (:82-83) unless the opt-in MANIFOLD_SO3_LEFT is set on the costs
+      retract(costs[0]->manifold, P, x0, delta.data(), xi.data());
       S yi = 0;
       for (auto* c : costs) yi += c->computeCost(xi.data());
       if (std::isnan(yi)) return NUMERIC_ERROR;

@@ -28,6 +28,7 @@ struct orc_cost {
   const double* consts;  // pinhole: K (12, row-major) then C (16, row-major)
   int cost_threads;      // threads for computeCost's parallel reduce (>=1)
   int float_carry;       // emulate the oneTBB float-identity quirk in computeCost
+  int manifold;          // Manifold: 0 additive (reference), 1 left SO(3) perturbation of x[3..5]
 };
 
 }  // extern "C"
@@ -106,6 +107,7 @@ std::unique_ptr<Holder<S>> build(const orc_cost& c) {
   k.jac_mode = c.jac_mode;
   k.cost_threads = c.cost_threads < 1 ? 1 : c.cost_threads;
   k.float_carry = c.float_carry != 0;
+  k.manifold = c.manifold;
   k.C.assign(size_t(c.O) * c.O, S(0));
   for (int i = 0; i < c.O; ++i) k.C[i + size_t(i) * c.O] = S(1);
   if (c.cov)
@@ -125,6 +127,7 @@ int linearize_t(const orc_cost* c, const double* x, double* H, double* b, double
   S s;
   if (nthreads > 1) {
     CostComputation<S> cc(P, c->O);
+    cc.manifold_ = c->manifold;
     s = cc.parallelLinearize(xs.data(), h->cost.C.data(), *h->cost.loss, Hs.data(), bs.data(),
                              *h->cost.model, c->n, c->jac_mode, nthreads);
   } else {
@@ -232,6 +235,7 @@ double orc_time_linearize(const orc_cost* c, int scalar, const double* x, int nt
   for (int r = 0; r < reps; ++r) {
     if (nthreads > 1) {
       CostComputation<double> cc(P, c->O);
+      cc.manifold_ = c->manifold;
       s = cc.parallelLinearize(x, h->cost.C.data(), *h->cost.loss, Hs.data(), bs.data(),
                                *h->cost.model, c->n, c->jac_mode, nthreads);
     } else {

@@ -21,7 +21,8 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 P2P, EXP_CURVE, MICHAELIS_MENTEN, PINHOLE, POWELL, POINT_DIST, PINHOLE_DISTORT = range(7)
 LOSS_NONE, LOSS_GM, LOSS_HUBER = range(3)
 JAC_ANALYTICAL, JAC_FORWARD, JAC_CENTRAL = range(3)
-P2P_EXACT, P2P_REFTEST, P2P_REFTEST_COLMAJOR = range(3)
+P2P_EXACT, P2P_REFTEST, P2P_REFTEST_COLMAJOR, P2P_LEFT = range(4)
+MANIFOLD_ADDITIVE, MANIFOLD_SO3_LEFT = 0, 1
 F32, F64 = 0, 1
 STATUS = ["CONVERGED", "MAXIMUM_ITERATIONS_REACHED", "SMALL_DELTA", "NUMERIC_ERROR", "FATAL_ERROR"]
 
@@ -34,7 +35,7 @@ class _OrcCost(C.Structure):
         ("cov", C.POINTER(C.c_double)),
         ("a", C.c_void_p), ("b", C.c_void_p), ("data_f32", C.c_int),
         ("consts", C.POINTER(C.c_double)),
-        ("cost_threads", C.c_int), ("float_carry", C.c_int),
+        ("cost_threads", C.c_int), ("float_carry", C.c_int), ("manifold", C.c_int),
     ]
 
 
@@ -96,6 +97,7 @@ class Cost:
     consts: Optional[np.ndarray] = None   # pinhole: K(3x4 row-major) ++ C(4x4 row-major)
     cost_threads: int = 1
     float_carry: bool = False
+    manifold: int = 0
     _keep: list = field(default_factory=list, repr=False)
 
     def c_struct(self) -> _OrcCost:
@@ -135,6 +137,7 @@ class Cost:
             s.consts = None
         s.cost_threads = int(self.cost_threads)
         s.float_carry = 1 if self.float_carry else 0
+        s.manifold = int(self.manifold)
         return s
 
 

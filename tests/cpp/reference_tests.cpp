@@ -370,6 +370,46 @@ TEST(ParallelCostTest, ComputeCost) {
   EXPECT_NEAR(mt_diff, 14.0 * n_elements, 1e-5);
 }
 
+// ------------------------------------------------- opt-in additions: manifold update, cloud ingest ----
+TEST(Manifold, Point2PointLeftPerturbation) {
+  P2PFixture f;
+  using M = device::Point2Point<double>;
+  M::Ptr model = std::make_shared<M>(g_ctx, f.src.data(), f.tgt.data(), f.n, MOPT_P2P_LEFT);
+  CostFunctionAnalyticalDynamic<double> cost(model, 6, 3, f.n);
+  cost.setManifold(MOPT_MANIFOLD_SO3_LEFT);  // finishes levenberg_marquadt_dyn.cpp:82 "TODO Manifold operation"
+  LevenbergMarquadtDynamic<double> lm(6);
+  lm.setMaximumIterations(50);
+  lm.addCost(&cost);
+  double x0[6] = {0};
+  EXPECT_EQ(lm.minimize(x0), OptimizationStatus::CONVERGED);
+  const double expect[6] = {10.5, 10.2, 0.1, 0.3899450238, 0.3154200672, 0.5496221593};
+  for (int i = 0; i < 6; ++i) EXPECT_NEAR(x0[i], expect[i], 1e-7);
+}
+
+TEST(Ingest, TextCloudFeedsTheDeviceStore) {
+  P2PFixture f;
+  const char* path = "/tmp/mopt_cpp_cloud.txt";
+  FILE* out = std::fopen(path, "w");
+  for (int i = 0; i < f.n; ++i)
+    std::fprintf(out, "%.8f %.8f %.8f %d %d %d\n", f.src[i * 3], f.src[i * 3 + 1], f.src[i * 3 + 2], i % 256, 7, 0);
+  std::fclose(out);
+  void* xyz = nullptr;
+  int64_t n = 0;
+  device::check(mopt_cloud_read_text(path, 6, 3, MOPT_F64, /*pinned=*/1, &xyz, &n), "mopt_cloud_read_text");
+  EXPECT_EQ(n, int64_t(f.n));
+  const double* p = static_cast<const double*>(xyz);
+  bool same = true;
+  for (int64_t i = 0; i < n * 3; ++i) same = same && (p[i] == f.src[size_t(i)]);
+  EXPECT_TRUE(same);
+  using M = device::Point2Point<double>;
+  M::Ptr model = std::make_shared<M>(g_ctx, p, f.tgt.data(), n);
+  CostFunctionAnalyticalDynamic<double> cost(model, 6, 3, int(n));
+  double x0[6] = {0}, H[36], b[6];
+  EXPECT_NEAR(cost.linearize(x0, H, b), 11726562.69752771, 1e-3);
+  device::check(mopt_cloud_free(xyz, 1), "mopt_cloud_free");
+  std::remove(path);
+}
+
 // ---------------------------------------------------------------------------- API misuse paths ----
 namespace {
 struct HostOnlyModel : BaseModel<double, HostOnlyModel> {
