@@ -236,6 +236,22 @@ MOPT_API void mopt_lm_default_options(mopt_lm_options* options);
 MOPT_API int mopt_so3_convert6dof(const double* x, double* T16_rowmajor);
 MOPT_API int mopt_ldlt_solve(int n, const double* A_colmajor, const double* rhs, double* out);
 
+/* ---- correspondence re-association: model->update(x) ------------------------------ */
+/* The reference calls cost->update(x0) -> model->update(x) before every linearization
+ * (src/levenberg_marquadt_dyn.cpp:54; include/moptimizer/model.h:24-26 "i.e registration correspondences") but
+ * ships no implementation.  A mopt_nn_index holds a fixed TARGET cloud in a device uniform grid; attached to a
+ * point2point store it makes update(x) mean: tgt_i <- nearest target point of T(x) src_i within `max_distance`,
+ * source points without one being skipped by later passes (model f returning false, linearization.h:102,144). */
+typedef struct mopt_nn_index mopt_nn_index;
+MOPT_API int mopt_nn_index_create(mopt_ctx* ctx, const void* host_xyz, int host_dtype, int index_dtype, int64_t m,
+                                  double max_distance, mopt_nn_index** out);
+MOPT_API int mopt_nn_index_destroy(mopt_nn_index* index);
+/* Attach (or detach with NULL) the target cloud.  With one attached, mopt_lm_minimize re-associates at the start
+ * of every outer iteration, exactly where the reference calls cost->update(x0), and uses the reference pass order. */
+MOPT_API int mopt_store_set_target(mopt_store* store, mopt_nn_index* index);
+/* CostFunctionBase::update(x) (cost_function.h:44): re-associate now; *matched = correspondences found. */
+MOPT_API int mopt_store_reassociate(mopt_store* store, const double* x, int64_t* matched);
+
 /* ---- point-cloud ingest (input side of the path) ---------------------------------------------------- */
 /* tst/point2point.cpp:125-138 `txt_cloud_loader`: whitespace-separated records of `columns` numbers (the
  * fixture tst/data/fachada.txt has 6: x y z r g b); the first `keep` of each record are stored, AoS, in

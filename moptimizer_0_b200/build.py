@@ -19,7 +19,7 @@ OBJ = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libmopt_b200.so")
 
 CU_SOURCES = ["mopt_capi.cu", "mopt_store.cu", "mopt_pass_p2p.cu", "mopt_pass_dense.cu", "mopt_pass_wide.cu",
-              "mopt_ingest.cu"]
+              "mopt_ingest.cu", "mopt_icp.cu"]
 HEADERS = ["mopt_common.cuh", "mopt_setup.cuh", "mopt_models.cuh", "mopt_pass.cuh", "mopt_lm.cuh",
            "mopt_internal.h"]
 

@@ -39,6 +39,7 @@ EXPORTS = [
     "mopt_upload_and_linearize", "mopt_lm_minimize", "mopt_lm_default_options", "mopt_so3_convert6dof",
     "mopt_ldlt_solve", "mopt_host_alloc", "mopt_host_free",
     "mopt_cloud_read_text", "mopt_cloud_write_binary", "mopt_cloud_read_binary", "mopt_cloud_free",
+    "mopt_nn_index_create", "mopt_nn_index_destroy", "mopt_store_set_target", "mopt_store_reassociate",
 ]
 
 
@@ -125,6 +126,10 @@ def lib():
         L.mopt_cloud_read_binary.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                              C.POINTER(vp), C.POINTER(i64)]
         L.mopt_cloud_free.argtypes = [vp, C.c_int]
+        L.mopt_nn_index_create.argtypes = [vp, vp, C.c_int, C.c_int, i64, C.c_double, C.POINTER(vp)]
+        L.mopt_nn_index_destroy.argtypes = [vp]
+        L.mopt_store_set_target.argtypes = [vp, vp]
+        L.mopt_store_reassociate.argtypes = [vp, dp, C.POINTER(i64)]
         _lib = L
     return _lib
 
@@ -314,6 +319,39 @@ class Store:
         if self._h:
             lib().mopt_store_destroy(self._h)
             self._h = C.c_void_p()
+
+
+class NNIndex:
+    """Fixed target cloud in a device uniform grid (mopt_nn_index): the data behind model->update(x)."""
+
+    def __init__(self, ctx: Context, target_xyz: np.ndarray, max_distance: float, dtype: int = F64):
+        t = np.ascontiguousarray(target_xyz)
+        if t.dtype not in (np.float32, np.float64):
+            t = t.astype(np.float64)
+        self._h = C.c_void_p()
+        self._keep = ctx
+        check(lib().mopt_nn_index_create(ctx.handle, t.ctypes.data, F32 if t.dtype == np.float32 else F64, dtype,
+                                         t.shape[0], float(max_distance), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib().mopt_nn_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def store_set_target(store: "Store", index: Optional[NNIndex]):
+    check(lib().mopt_store_set_target(store.handle, index.handle if index is not None else None))
+
+
+def store_reassociate(store: "Store", x) -> int:
+    xs = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    m = C.c_int64(0)
+    check(lib().mopt_store_reassociate(store.handle, _dp(xs), C.byref(m)))
+    return m.value
 
 
 def cloud_read_text(path: str, columns: int = 6, keep: int = 3, dtype=np.float64, pinned: bool = False) -> np.ndarray:

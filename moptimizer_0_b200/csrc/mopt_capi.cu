@@ -206,6 +206,7 @@ PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate
   a.accumulate = accumulate;
   a.mode_ptr = &ctx->d_lm->pass_mode;
   a.mode_override = mode_override;
+  a.masked = st->may_have_invalid ? 1 : 0;
   return a;
 }
 
@@ -255,6 +256,22 @@ int enqueue_pass(mopt_ctx* ctx, mopt_store* st, const mopt_problem* p, const dou
   MOPT_TRY(allreduce_trial(ctx, P));
   return MOPT_OK;
 }
+
+}  // namespace
+
+namespace mopt {
+int setup_slot(mopt_ctx* ctx, int slot, const mopt_problem* problem, const double* x) {
+  MOPT_TRY(stage_cost(ctx, slot, problem));
+  XArg xa;
+  std::memset(&xa, 0, sizeof(xa));
+  for (int i = 0; i < problem->num_parameters; ++i) xa.v[i] = x[i];
+  setup_kernel<<<1, 32, 0, ctx->stream>>>(&ctx->d_slots[slot], xa);
+  MOPT_CUDA_TRY(cudaGetLastError());
+  return MOPT_OK;
+}
+}  // namespace mopt
+
+namespace {
 
 int fetch_result(mopt_ctx* ctx, int P, double* H, double* b, double* sum) {
   MOPT_CUDA_TRY(cudaMemcpyAsync(ctx->h_result, ctx->d_trial, sizeof(double) * packed_size(P), cudaMemcpyDeviceToHost, ctx->stream));
@@ -488,6 +505,11 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
   std::memset(&in, 0, sizeof(in));
   in.P = P; in.n_costs = n_costs; in.max_it = opt.max_iterations; in.lm_max_it = opt.lm_max_iterations;
   in.speculative = opt.speculative ? 1 : 0; in.scalar_f32 = (opt.scalar_dtype == MOPT_F32) ? 1 : 0;
+  // model->update(x) (levenberg_marquadt_dyn.cpp:54) changes the residual set at every outer iteration, so the
+  // H, b evaluated speculatively at a trial point are not those of the next linearization: reference pass order.
+  bool has_update = false;
+  for (int c = 0; c < n_costs; ++c) has_update = has_update || (stores[c]->index != nullptr);
+  if (has_update) in.speculative = 0;
   in.lambda_factor = opt.lambda_factor;
   for (int i = 0; i < P; ++i) in.x0[i] = x[i];
   lm_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_slots, in);
@@ -504,6 +526,8 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
     *last_slot = -1;
     for (int s = 0; s < kBatch && enq < max_slots; ++s, ++enq) {
       ctx->h_flags[enq] = 0;
+      // cost->update(x0): re-associate correspondences; the kernel gates itself on "start of an outer iteration"
+      for (int c = 0; c < n_costs; ++c) MOPT_TRY(enqueue_reassociate(stores[c], &ctx->d_slots[c].pb, ctx->d_lm));
       for (int c = 0; c < n_costs; ++c) MOPT_TRY(launch_pass(ctx, stores[c], &problems[c], c, c > 0 ? 1 : 0, -1));
       MOPT_TRY(allreduce_trial(ctx, P));
       lm_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_trial, ctx->d_slots, ctx->d_flags + enq);

@@ -49,6 +49,8 @@ struct mopt_store {
   int64_t n = 0;
   int nstreams = 0;
   void* streams[mopt::kMaxStreams] = {nullptr};
+  struct mopt_nn_index* index = nullptr;  // target cloud for model->update(x) (mopt_icp.cu), not owned
+  bool may_have_invalid = false;          // target streams may hold the NaN "no correspondence" marker
 };
 
 namespace mopt {
@@ -64,6 +66,11 @@ struct PassLaunch {
 int launch_p2p_moment(const PassLaunch& L, int store_dtype, int compute_dtype, int loss, bool qrot, const PassArgs& a);
 // mopt_pass_dense.cu
 int launch_dense(const PassLaunch& L, int model, bool numeric, int store_dtype, int compute_dtype, const PassArgs& a);
+
+// mopt_capi.cu: copy the cost constants of `problem` into slot `slot` and run model setup at x on the device
+int setup_slot(mopt_ctx* ctx, int slot, const mopt_problem* problem, const double* x);
+// mopt_icp.cu: enqueue model->update(x) for a store with a target index (no-op without one)
+int enqueue_reassociate(mopt_store* st, const ParamBlock* pb, const LmState* gate);
 
 // mopt_pass_wide.cu
 int launch_wide(const PassLaunch& L, int model, int store_dtype, int compute_dtype, const PassArgs& a);

@@ -21,6 +21,8 @@ struct PassArgs {
   int accumulate;            // 1: out += this pass (second and later cost terms)
   const int* mode_ptr;       // device control word (PassMode), used when mode_override < 0
   int mode_override;
+  int masked;                // 1: a NaN in the first B-group stream marks "no correspondence" (model f returned
+                             // false, linearization.h:102,144): the residual is skipped entirely
 };
 
 #ifdef __CUDACC__
@@ -88,17 +90,19 @@ __device__ __forceinline__ bool grid_reduce(const double (&lane_val)[NCH], const
 constexpr int kP2PRaw = 23;
 
 template <typename CT, int LOSS, bool QROT>
-__device__ __forceinline__ void p2p_moments(const CT (&R)[9], const CT (&t)[3], CT lossp, CT px, CT py, CT pz,
-                                            CT yx, CT yy, CT yz, CT (&acc)[32]) {
+__device__ __forceinline__ void p2p_moments(bool masked, const CT (&R)[9], const CT (&t)[3], CT lossp, CT px, CT py,
+                                            CT pz, CT yx, CT yy, CT yz, CT (&acc)[32]) {
   // q = R p ; r = (q + t) - y          (tst/point2point.cpp:41-44)
   const CT q0 = fma(R[0], px, fma(R[1], py, R[2] * pz));
   const CT q1 = fma(R[3], px, fma(R[4], py, R[5] * pz));
   const CT q2 = fma(R[6], px, fma(R[7], py, R[8] * pz));
-  const CT r0 = (q0 + t[0]) - yx;
-  const CT r1 = (q1 + t[1]) - yy;
-  const CT r2 = (q2 + t[2]) - yz;
+  CT r0 = (q0 + t[0]) - yx;
+  CT r1 = (q1 + t[1]) - yy;
+  CT r2 = (q2 + t[2]) - yz;
+  const bool skip = masked && (yx != yx);  // NaN target = no correspondence: f returned false, skip the residual
+  if (skip) { r0 = CT(0); r1 = CT(0); r2 = CT(0); }
   const CT e2 = fma(r0, r0, fma(r1, r1, r2 * r2));
-  const CT w = loss_weight<CT>(LOSS, lossp, e2);
+  const CT w = skip ? CT(0) : loss_weight<CT>(LOSS, lossp, e2);
   const CT a0 = QROT ? q0 : px, a1 = QROT ? q1 : py, a2 = QROT ? q2 : pz;
   const CT w0 = w * a0, w1 = w * a1, w2 = w * a2;
   acc[0] += w;
@@ -113,12 +117,13 @@ __device__ __forceinline__ void p2p_moments(const CT (&R)[9], const CT (&t)[3], 
 }
 
 template <typename CT>
-__device__ __forceinline__ void p2p_cost_only(const CT (&R)[9], const CT (&t)[3], CT px, CT py, CT pz, CT yx,
-                                              CT yy, CT yz, CT (&acc)[32]) {
+__device__ __forceinline__ void p2p_cost_only(bool masked, const CT (&R)[9], const CT (&t)[3], CT px, CT py, CT pz,
+                                              CT yx, CT yy, CT yz, CT (&acc)[32]) {
   const CT r0 = (fma(R[0], px, fma(R[1], py, R[2] * pz)) + t[0]) - yx;
   const CT r1 = (fma(R[3], px, fma(R[4], py, R[5] * pz)) + t[1]) - yy;
   const CT r2 = (fma(R[6], px, fma(R[7], py, R[8] * pz)) + t[2]) - yz;
-  acc[22] += fma(r0, r0, fma(r1, r1, r2 * r2));
+  const CT e2 = fma(r0, r0, fma(r1, r1, r2 * r2));
+  acc[22] += (masked && (yx != yx)) ? CT(0) : e2;
 }
 
 // Assemble packed (H upper, b, sum) of the 6-parameter problem from the 23 moment totals.
@@ -180,6 +185,7 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
 #pragma unroll
   for (int i = 0; i < 3; ++i) t[i] = CT(a.pb->sets[0][9 + i]);
   const CT lossp = CT(a.cost->loss_param);
+  const bool masked = a.masked != 0;
 
   const ST* __restrict__ sx = static_cast<const ST*>(a.streams.p[0]);
   const ST* __restrict__ sy = static_cast<const ST*>(a.streams.p[1]);
@@ -211,11 +217,11 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
     load_vec<ST, CT>(tx, g, qx); load_vec<ST, CT>(ty, g, qy); load_vec<ST, CT>(tz, g, qz);
     if (mode == PASS_COST) {
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) p2p_cost_only<CT>(R, t, px[e], py[e], pz[e], qx[e], qy[e], qz[e], acc);
+      for (int e = 0; e < VEC; ++e) p2p_cost_only<CT>(masked, R, t, px[e], py[e], pz[e], qx[e], qy[e], qz[e], acc);
     } else {
 #pragma unroll
       for (int e = 0; e < VEC; ++e)
-        p2p_moments<CT, LOSS, QROT>(R, t, lossp, px[e], py[e], pz[e], qx[e], qy[e], qz[e], acc);
+        p2p_moments<CT, LOSS, QROT>(masked, R, t, lossp, px[e], py[e], pz[e], qx[e], qy[e], qz[e], acc);
     }
   };
 
@@ -246,11 +252,11 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
     auto consume = [&](const CT (&buf)[6][VEC]) {
       if (mode == PASS_COST) {
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) p2p_cost_only<CT>(R, t, buf[0][e], buf[1][e], buf[2][e], buf[3][e], buf[4][e], buf[5][e], acc);
+        for (int e = 0; e < VEC; ++e) p2p_cost_only<CT>(masked, R, t, buf[0][e], buf[1][e], buf[2][e], buf[3][e], buf[4][e], buf[5][e], acc);
       } else {
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
-          p2p_moments<CT, LOSS, QROT>(R, t, lossp, buf[0][e], buf[1][e], buf[2][e], buf[3][e], buf[4][e], buf[5][e], acc);
+          p2p_moments<CT, LOSS, QROT>(masked, R, t, lossp, buf[0][e], buf[1][e], buf[2][e], buf[3][e], buf[4][e], buf[5][e], acc);
       }
     };
     if (full_rounds > 0) {
@@ -292,11 +298,11 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
       if (mode == PASS_COST) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
-          p2p_cost_only<CT>(R, t, px[u][e], py[u][e], pz[u][e], qx[u][e], qy[u][e], qz[u][e], acc);
+          p2p_cost_only<CT>(masked, R, t, px[u][e], py[u][e], pz[u][e], qx[u][e], qy[u][e], qz[u][e], acc);
       } else {
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
-          p2p_moments<CT, LOSS, QROT>(R, t, lossp, px[u][e], py[u][e], pz[u][e], qx[u][e], qy[u][e], qz[u][e], acc);
+          p2p_moments<CT, LOSS, QROT>(masked, R, t, lossp, px[u][e], py[u][e], pz[u][e], qx[u][e], qy[u][e], qz[u][e], acc);
       }
     }
     if (kFp32Acc) {
@@ -314,9 +320,9 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       for (int64_t i = ngroups * VEC; i < a.n; ++i) {
         if (mode == PASS_COST)
-          p2p_cost_only<CT>(R, t, CT(sx[i]), CT(sy[i]), CT(sz[i]), CT(tx[i]), CT(ty[i]), CT(tz[i]), acc);
+          p2p_cost_only<CT>(masked, R, t, CT(sx[i]), CT(sy[i]), CT(sz[i]), CT(tx[i]), CT(ty[i]), CT(tz[i]), acc);
         else
-          p2p_moments<CT, LOSS, QROT>(R, t, lossp, CT(sx[i]), CT(sy[i]), CT(sz[i]), CT(tx[i]), CT(ty[i]), CT(tz[i]), acc);
+          p2p_moments<CT, LOSS, QROT>(masked, R, t, lossp, CT(sx[i]), CT(sy[i]), CT(sz[i]), CT(tx[i]), CT(ty[i]), CT(tz[i]), acc);
       }
     }
   }
@@ -387,8 +393,13 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
   };
 
   // one residual: e[] = its NS stream values
+  const bool masked = a.masked != 0;
   auto do_elem = [&](const CT (&e)[NS > 0 ? NS : 1]) {
     CT r[O];
+    if (NS > 0 && masked) {  // NaN in the first B-group stream: no correspondence, the residual is skipped
+      const CT probe = e[(M::NA < NS) ? M::NA : 0];
+      if (probe != probe) return;
+    }
     if (mode == PASS_COST) {
       M::template residual<CT>(s_sets[0], e, r);
       CT e2 = CT(0);

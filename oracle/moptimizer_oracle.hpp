@@ -264,6 +264,64 @@ struct Point2Point : IModel<S> {
   S Jl_[9];
 };
 
+// Point-to-point with correspondence re-association in update(x) — the hook the reference declares
+// (model.h:24-26 "i.e registration correspondences", called at levenberg_marquadt_dyn.cpp:54) and never
+// implements.  Brute-force exact nearest neighbour in the fixed target cloud (ties -> lowest index), within
+// max_dist; a source point without a match makes f / f_df return false, so it is skipped (linearization.h:102,144).
+template <class S>
+struct Point2PointICP : IModel<S> {
+  Point2PointICP(const S* src, int n, const S* target, int m, S max_dist, int jac)
+      : src_(src), n_(n), target_(target), m_(m), max_dist_(max_dist), jac_(jac), tgt_(size_t(n) * 3, S(0)),
+        valid_(size_t(n), 0), inner_(src, tgt_.data(), jac) {}
+  Point2PointICP(const Point2PointICP& o)
+      : src_(o.src_), n_(o.n_), target_(o.target_), m_(o.m_), max_dist_(o.max_dist_), jac_(o.jac_), tgt_(o.tgt_),
+        valid_(o.valid_), inner_(o.inner_) {
+    inner_.tgt_ = tgt_.data();
+  }
+  void setup(const S* x) override { inner_.setup(x); }
+  void update(const S* x) override {
+    S T[16];
+    so3_convert6dof(x, T);
+    const S r2max = max_dist_ * max_dist_;
+    for (int i = 0; i < n_; ++i) {
+      const S* p = src_ + 3 * size_t(i);
+      S q[3];
+      for (int k = 0; k < 3; ++k) q[k] = T[k * 4] * p[0] + T[k * 4 + 1] * p[1] + T[k * 4 + 2] * p[2] + T[k * 4 + 3];
+      S best = r2max;
+      int arg = -1;
+      for (int j = 0; j < m_; ++j) {
+        const S* t = target_ + 3 * size_t(j);
+        const S d0 = t[0] - q[0], d1 = t[1] - q[1], d2 = t[2] - q[2];
+        const S dd = d0 * d0 + d1 * d1 + d2 * d2;
+        if (dd < best || (arg < 0 && dd <= r2max)) {
+          best = dd;
+          arg = j;
+        }
+      }
+      valid_[i] = arg >= 0;
+      if (arg >= 0)
+        for (int k = 0; k < 3; ++k) tgt_[3 * size_t(i) + k] = target_[3 * size_t(arg) + k];
+    }
+  }
+  bool f(const S* x, S* r, unsigned i) const override { return valid_[i] ? inner_.f(x, r, i) : false; }
+  bool f_df(const S* x, S* r, S* J, unsigned i) const override { return valid_[i] ? inner_.f_df(x, r, J, i) : false; }
+  std::shared_ptr<IModel<S>> clone() const override { return std::make_shared<Point2PointICP>(*this); }
+  int matched() const {
+    int c = 0;
+    for (char v : valid_) c += v;
+    return c;
+  }
+  const S* src_;
+  int n_;
+  const S* target_;
+  int m_;
+  S max_dist_;
+  int jac_;
+  std::vector<S> tgt_;
+  std::vector<char> valid_;
+  Point2Point<S> inner_;
+};
+
 // tst/parallel.cpp:12-32 — r = src - tgt, no parameters.
 template <class S>
 struct PointDist : IModel<S> {

@@ -11,7 +11,7 @@ using namespace oracle;
 extern "C" {
 
 enum { ORC_P2P = 0, ORC_EXP_CURVE = 1, ORC_MICHAELIS_MENTEN = 2, ORC_PINHOLE = 3, ORC_POWELL = 4,
-       ORC_POINT_DIST = 5, ORC_PINHOLE_DISTORT = 6 };
+       ORC_POINT_DIST = 5, ORC_PINHOLE_DISTORT = 6, ORC_P2P_ICP = 7 };
 enum { ORC_LOSS_NONE = 0, ORC_LOSS_GM = 1, ORC_LOSS_HUBER = 2 };
 
 struct orc_cost {
@@ -29,6 +29,11 @@ struct orc_cost {
   int cost_threads;      // threads for computeCost's parallel reduce (>=1)
   int float_carry;       // emulate the oneTBB float-identity quirk in computeCost
   int manifold;          // Manifold: 0 additive (reference), 1 left SO(3) perturbation of x[3..5]
+  const void* target;    // ORC_P2P_ICP: fixed target cloud (xyz AoS, same dtype as a/b)
+  int target_m;
+  double max_dist;       // ORC_P2P_ICP: maximum correspondence distance
+  const double* update_x;  // ORC_P2P_ICP: parameters at which cost->update(x) ran before linearize / computeCost
+                           // (NULL: at the evaluation point)
 };
 
 }  // extern "C"
@@ -37,9 +42,10 @@ namespace {
 
 template <class S>
 struct Holder {
-  std::vector<S> a_store, b_store;
+  std::vector<S> a_store, b_store, t_store;
   const S* a = nullptr;
   const S* b = nullptr;
+  const S* target = nullptr;
   Cost<S> cost;
 };
 
@@ -65,6 +71,7 @@ std::unique_ptr<Holder<S>> build(const orc_cost& c) {
   switch (c.model) {
     case ORC_P2P:
     case ORC_POINT_DIST: na = nb = size_t(c.n) * 3; break;
+    case ORC_P2P_ICP: na = size_t(c.n) * 3; nb = 0; break;
     case ORC_EXP_CURVE:
     case ORC_MICHAELIS_MENTEN: na = nb = size_t(c.n); break;
     case ORC_PINHOLE:
@@ -76,6 +83,10 @@ std::unique_ptr<Holder<S>> build(const orc_cost& c) {
   Cost<S>& k = h->cost;
   switch (c.model) {
     case ORC_P2P: k.model = std::make_shared<Point2Point<S>>(h->a, h->b, c.variant); break;
+    case ORC_P2P_ICP:
+      h->target = adopt<S>(c.target, c.data_f32 != 0, size_t(c.target_m) * 3, h->t_store);
+      k.model = std::make_shared<Point2PointICP<S>>(h->a, c.n, h->target, c.target_m, S(c.max_dist), c.variant);
+      break;
     case ORC_POINT_DIST: k.model = std::make_shared<PointDist<S>>(h->a, h->b); break;
     case ORC_EXP_CURVE: k.model = std::make_shared<ExpCurve<S>>(h->a, h->b); break;
     case ORC_MICHAELIS_MENTEN: k.model = std::make_shared<MichaelisMenten<S>>(h->a, h->b); break;
@@ -116,6 +127,16 @@ std::unique_ptr<Holder<S>> build(const orc_cost& c) {
   return h;
 }
 
+// cost->update(x) (cost_function.h:44) for models that implement it, before a stand-alone evaluation
+template <class S>
+void run_update(const orc_cost* c, Cost<S>& cost, const std::vector<S>& x_eval) {
+  if (c->model != ORC_P2P_ICP) return;
+  std::vector<S> xu(x_eval);
+  if (c->update_x)
+    for (int i = 0; i < c->P; ++i) xu[i] = S(c->update_x[i]);
+  cost.model->update(xu.data());
+}
+
 template <class S>
 int linearize_t(const orc_cost* c, const double* x, double* H, double* b, double* sum,
                 int nthreads) {
@@ -125,6 +146,7 @@ int linearize_t(const orc_cost* c, const double* x, double* H, double* b, double
   std::vector<S> xs(P), Hs(size_t(P) * P), bs(P);
   for (int i = 0; i < P; ++i) xs[i] = S(x[i]);
   S s;
+  run_update<S>(c, h->cost, xs);
   if (nthreads > 1) {
     CostComputation<S> cc(P, c->O);
     cc.manifold_ = c->manifold;
@@ -145,6 +167,7 @@ int cost_t(const orc_cost* c, const double* x, double* sum, int parallel) {
   if (!h) return 1;
   std::vector<S> xs(c->P > 0 ? c->P : 1);
   for (int i = 0; i < c->P; ++i) xs[i] = S(x[i]);
+  run_update<S>(c, h->cost, xs);
   CostComputation<S> cc(c->P, c->O);
   S s = parallel ? cc.parallelComputeCost(xs.data(), *h->cost.model, c->n, h->cost.cost_threads,
                                           h->cost.float_carry)

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 # model kinds / enums (mirror oracle_capi.cpp)
-P2P, EXP_CURVE, MICHAELIS_MENTEN, PINHOLE, POWELL, POINT_DIST, PINHOLE_DISTORT = range(7)
+P2P, EXP_CURVE, MICHAELIS_MENTEN, PINHOLE, POWELL, POINT_DIST, PINHOLE_DISTORT, P2P_ICP = range(8)
 LOSS_NONE, LOSS_GM, LOSS_HUBER = range(3)
 JAC_ANALYTICAL, JAC_FORWARD, JAC_CENTRAL = range(3)
 P2P_EXACT, P2P_REFTEST, P2P_REFTEST_COLMAJOR, P2P_LEFT = range(4)
@@ -36,6 +36,8 @@ class _OrcCost(C.Structure):
         ("a", C.c_void_p), ("b", C.c_void_p), ("data_f32", C.c_int),
         ("consts", C.POINTER(C.c_double)),
         ("cost_threads", C.c_int), ("float_carry", C.c_int), ("manifold", C.c_int),
+        ("target", C.c_void_p), ("target_m", C.c_int), ("max_dist", C.c_double),
+        ("update_x", C.POINTER(C.c_double)),
     ]
 
 
@@ -98,6 +100,9 @@ class Cost:
     cost_threads: int = 1
     float_carry: bool = False
     manifold: int = 0
+    target: Optional[np.ndarray] = None   # P2P_ICP: fixed target cloud (m, 3)
+    max_dist: float = 0.0                 # P2P_ICP: maximum correspondence distance
+    update_x: Optional[Sequence[float]] = None  # P2P_ICP: where cost->update(x) ran (default: evaluation point)
     _keep: list = field(default_factory=list, repr=False)
 
     def c_struct(self) -> _OrcCost:
@@ -138,6 +143,15 @@ class Cost:
         s.cost_threads = int(self.cost_threads)
         s.float_carry = 1 if self.float_carry else 0
         s.manifold = int(self.manifold)
+        s.target, s.target_m, s.max_dist, s.update_x = None, 0, float(self.max_dist), None
+        if self.target is not None:
+            t = np.ascontiguousarray(np.asarray(self.target, dtype=np.float32 if f32 else np.float64))
+            self._keep.append(t)
+            s.target, s.target_m = t.ctypes.data, t.shape[0]
+        if self.update_x is not None:
+            u = np.ascontiguousarray(np.asarray(self.update_x, dtype=np.float64))
+            self._keep.append(u)
+            s.update_x = _dp(u)
         return s
 
 
