@@ -71,4 +71,24 @@ class Store {
   int64_t n_ = 0;
 };
 
+/// Fixed target cloud in a device uniform grid: the data behind `model->update(x)` (model.h:24-26).
+class NNIndex {
+ public:
+  using Ptr = std::shared_ptr<NNIndex>;
+  template <class HostScalar>
+  NNIndex(Context::Ptr ctx, const HostScalar* target_xyz, int64_t m, double max_distance, int index_dtype = MOPT_F64)
+      : ctx_(std::move(ctx)) {
+    check(mopt_nn_index_create(ctx_->get(), target_xyz, dtypeOf<HostScalar>(), index_dtype, m, max_distance, &index_),
+          "mopt_nn_index_create");
+  }
+  ~NNIndex() { mopt_nn_index_destroy(index_); }
+  NNIndex(const NNIndex&) = delete;
+  NNIndex& operator=(const NNIndex&) = delete;
+  mopt_nn_index* get() const { return index_; }
+
+ private:
+  Context::Ptr ctx_;
+  mopt_nn_index* index_ = nullptr;
+};
+
 }  // namespace moptimizer::device

@@ -64,11 +64,39 @@ class Point2Point : public DeviceModel<Scalar, Point2Point<Scalar>> {
   explicit Point2Point(Store::Ptr store, int jacobian_variant = MOPT_P2P_EXACT) : variant_(jacobian_variant) {
     this->store_ = std::move(store);
   }
+  /// Source cloud only: correspondences come from setTarget() + update(x) (registration with unknown matches).
+  template <class HostScalar>
+  Point2Point(Context::Ptr ctx, const HostScalar* src, int64_t n, int jacobian_variant = MOPT_P2P_EXACT,
+              int store_dtype = dtypeOf<Scalar>())
+      : variant_(jacobian_variant) {
+    this->store_ = std::make_shared<Store>(std::move(ctx), MOPT_MODEL_POINT2POINT, store_dtype, n);
+    this->store_->upload(0, src, n);
+  }
   int kind() const override { return MOPT_MODEL_POINT2POINT; }
   int variant() const override { return variant_; }
 
+  /// The fixed cloud update(x) searches: tgt_i <- nearest target point of T(x) src_i within max_distance;
+  /// source points without one are skipped (`f` returning false in the reference, linearization.h:102,144).
+  template <class HostScalar>
+  void setTarget(const HostScalar* target_xyz, int64_t m, double max_distance) {
+    index_ = std::make_shared<NNIndex>(this->store_->context(), target_xyz, m, max_distance);
+    check(mopt_store_set_target(this->store_->get(), index_->get()), "mopt_store_set_target");
+  }
+  /// model->update(x) (model.h:24-26): re-associate correspondences on the device.  The optimizer calls it at
+  /// the start of every outer iteration (levenberg_marquadt_dyn.cpp:54); on the device path that happens
+  /// inside mopt_lm_minimize without a host round trip.
+  void update(const Scalar* x) override {
+    if (!index_) return;
+    double xd[6];
+    for (int i = 0; i < 6; ++i) xd[i] = double(x[i]);
+    check(mopt_store_reassociate(this->store_->get(), xd, &matched_), "mopt_store_reassociate");
+  }
+  int64_t matched() const { return matched_; }
+
  private:
   int variant_;
+  NNIndex::Ptr index_;
+  int64_t matched_ = 0;
 };
 
 /// r = src - tgt (no parameters); cost only.

@@ -386,6 +386,35 @@ TEST(Manifold, Point2PointLeftPerturbation) {
   for (int i = 0; i < 6; ++i) EXPECT_NEAR(x0[i], expect[i], 1e-7);
 }
 
+TEST(Registration, UpdateHookReassociatesCorrespondences) {
+  // model->update(x) (model.h:24-26, called at levenberg_marquadt_dyn.cpp:54): unknown correspondences
+  P2PFixture f;
+  const int m = 6000, n = 3000;
+  std::vector<double> target(f.src.begin(), f.src.begin() + size_t(m) * 3), src(size_t(n) * 3);
+  const double x_true[6] = {0.12, -0.08, 0.05, 0.03, -0.02, 0.04};
+  double T[16];
+  so3::convert6DOFParameterToMatrix(x_true, T);
+  for (int i = 0; i < n; ++i) {  // src = R^T (target_{2i} - t)
+    const double* q = &target[size_t(2 * i) * 3];
+    const double d[3] = {q[0] - T[3], q[1] - T[7], q[2] - T[11]};
+    for (int k = 0; k < 3; ++k) src[size_t(i) * 3 + k] = T[k] * d[0] + T[4 + k] * d[1] + T[8 + k] * d[2];
+  }
+  using M = device::Point2Point<double>;
+  M::Ptr model = std::make_shared<M>(g_ctx, src.data(), int64_t(n));
+  model->setTarget(target.data(), m, 0.6);
+  CostFunctionAnalyticalDynamic<double> cost(model, 6, 3, n);
+  double x0[6] = {0};
+  cost.update(x0);
+  EXPECT_TRUE(model->matched() > n / 2);
+  LevenbergMarquadtDynamic<double> lm(6);
+  lm.setMaximumIterations(30);
+  lm.addCost(&cost);
+  lm.minimize(x0);
+  for (int i = 0; i < 6; ++i) EXPECT_NEAR(x0[i], x_true[i], 2e-3);
+  cost.update(x0);
+  EXPECT_EQ(model->matched(), int64_t(n));
+}
+
 TEST(Ingest, TextCloudFeedsTheDeviceStore) {
   P2PFixture f;
   const char* path = "/tmp/mopt_cpp_cloud.txt";

@@ -120,7 +120,9 @@ def test_device_icp_lm_matches_oracle(env, jac, variant):
     decisive = [i for i in range(k) if abs(ro.trace[i, 2] - ro.trace[i, 3]) > 1e-9 * ro.trace[i, 2]]
     cut = (decisive[-1] + 1) if decisive else 0
     assert cut >= 3 and r.sequence[:cut] == ro.sequence[:cut]
-    assert np.allclose(r.trace[:cut, 2], ro.trace[:cut, 2], rtol=1e-9)   # y0 after each re-association
+    # y0 after each re-association: the analytical path reproduces the oracle's iterates to rounding; with
+    # forward differences the iterates differ by the finite-difference noise (1/h ~ 7e7 times eps)
+    assert np.allclose(r.trace[:cut, 2], ro.trace[:cut, 2], rtol=1e-9 if jac == 0 else 1e-4)
     ix.close()
     st.close()
 
