@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--lm", action="store_true", help="also time a device-resident LM solve (LM iters/s)")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: how the 28 packed doubles are combined per step")
     ap.add_argument("--strong-total", type=int, default=0,
                     help="strong scaling: this many correspondences in total, sharded contiguously over the ranks "
                          "(BASELINE configs[3] uses 1e9); default is weak scaling with --n per GPU")
@@ -201,17 +203,16 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the CUDA path is the only implementation (no CPU fallback)")
     torch.cuda.set_device(local)
-    sharded = None
+    from moptimizer_0_b200 import sharding
+    collective, collective_note = "none", ""
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        uid = [capi.Context.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        sharded = (rank, world, uid[0])
-    ctx = capi.Context(local, sharded=sharded)
+        ctx, collective, collective_note = sharding.make_sharded_context(local, rank, world, args.collective)
+    else:
+        ctx = capi.Context(local)
     if args.ctas_per_sm or args.threads:
         ctx.set_launch(args.ctas_per_sm, args.threads)
-    from moptimizer_0_b200 import sharding
     if args.strong_total:
         first, last = sharding.shard_range(args.strong_total, rank, world)
         n, n_total = last - first, args.strong_total
@@ -325,7 +326,10 @@ def run_ours(args):
                        "accumulate": "fp32 partials folded into fp64 every 64 residuals/thread",
                        "prewarm_steps": args.prewarm_steps,
                        "l2": f"inputs {BYTES_PER_RES * n / 1e6:.0f} MB per GPU >> 126 MB L2, no flush needed",
-                       "collective": "ncclAllReduce(28 x f64) per step" if world > 1 else "none"},
+                       "collective": {"none": "none",
+                                      "p2p": "NVLink peer exchange of 28 x f64, pushed by the pass kernel's last CTA",
+                                      "nccl": "ncclAllReduce(28 x f64) per step"}[collective]
+                                     + (f" (p2p unavailable: {collective_note})" if collective_note else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                          "kernel": "p2p_moment_kernel<float,float,HUBER,QROT>",

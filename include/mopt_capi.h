@@ -183,6 +183,14 @@ MOPT_API int mopt_ctx_create(int device, mopt_ctx** out);
  * P(P+1)/2 + P + 1 values per pass), identical on every rank. */
 MOPT_API int mopt_ctx_create_sharded(int device, int rank, int world_size, const void* nccl_unique_id, mopt_ctx** out);
 MOPT_API int mopt_comm_unique_id(void* out_id);
+/* NVLink peer exchange instead of NCCL: the last CTA of every pass stores the packed result straight into every
+ * rank's exchange buffer (P2P stores through NVSwitch) and a one-warp consumer sums the slots in rank order.
+ * Each rank publishes mopt_ctx_peer_handle (MOPT_PEER_HANDLE_BYTES bytes, a CUDA IPC handle), the host gathers
+ * them in rank order and every rank calls mopt_ctx_open_peers.  With this open, `nccl_unique_id` of
+ * mopt_ctx_create_sharded may be NULL. */
+#define MOPT_PEER_HANDLE_BYTES 64
+MOPT_API int mopt_ctx_peer_handle(mopt_ctx* ctx, void* out_handle);
+MOPT_API int mopt_ctx_open_peers(mopt_ctx* ctx, const void* handles_in_rank_order);
 MOPT_API int mopt_ctx_destroy(mopt_ctx* ctx);
 MOPT_API int mopt_ctx_synchronize(mopt_ctx* ctx);
 /* cudaStream_t of the context as an integer (for CUDA-event timing by the caller). */

@@ -40,7 +40,9 @@ EXPORTS = [
     "mopt_ldlt_solve", "mopt_host_alloc", "mopt_host_free",
     "mopt_cloud_read_text", "mopt_cloud_write_binary", "mopt_cloud_read_binary", "mopt_cloud_free",
     "mopt_nn_index_create", "mopt_nn_index_destroy", "mopt_store_set_target", "mopt_store_reassociate",
+    "mopt_ctx_peer_handle", "mopt_ctx_open_peers",
 ]
+PEER_HANDLE_BYTES = 64
 
 
 class Problem(C.Structure):
@@ -130,6 +132,8 @@ def lib():
         L.mopt_nn_index_destroy.argtypes = [vp]
         L.mopt_store_set_target.argtypes = [vp, vp]
         L.mopt_store_reassociate.argtypes = [vp, dp, C.POINTER(i64)]
+        L.mopt_ctx_peer_handle.argtypes = [vp, vp]
+        L.mopt_ctx_open_peers.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -172,9 +176,10 @@ class Context:
         if sharded is None:
             check(lib().mopt_ctx_create(device, C.byref(self._h)))
         else:
-            rank, world, uid = sharded
-            buf = C.create_string_buffer(bytes(uid), NCCL_ID_BYTES)
-            check(lib().mopt_ctx_create_sharded(device, rank, world, C.cast(buf, C.c_void_p), C.byref(self._h)))
+            rank, world, uid = sharded  # uid None: no NCCL communicator, open_peers() must follow
+            buf = C.create_string_buffer(bytes(uid), NCCL_ID_BYTES) if uid is not None else None
+            check(lib().mopt_ctx_create_sharded(device, rank, world, C.cast(buf, C.c_void_p) if buf else None,
+                                                C.byref(self._h)))
 
     @staticmethod
     def unique_id() -> bytes:
@@ -185,6 +190,17 @@ class Context:
     @property
     def handle(self):
         return self._h
+
+    def peer_handle(self) -> bytes:
+        """CUDA IPC handle of this rank's exchange buffer (NVLink peer exchange, see mopt_ctx_open_peers)."""
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        check(lib().mopt_ctx_peer_handle(self._h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def open_peers(self, handles_in_rank_order: Sequence[bytes]):
+        blob = b"".join(bytes(h) for h in handles_in_rank_order)
+        buf = C.create_string_buffer(blob, len(blob))
+        check(lib().mopt_ctx_open_peers(self._h, C.cast(buf, C.c_void_p)))
 
     def synchronize(self):
         check(lib().mopt_ctx_synchronize(self._h))

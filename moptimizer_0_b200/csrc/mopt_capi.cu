@@ -121,6 +121,43 @@ __global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* s
   if (threadIdx.x == 0) *flag = st->done;
 }
 
+// Consumer side of the NVLink peer exchange (mopt_pass.cuh peer_push): acquire every rank's sequence flag for
+// this exchange, then sum the slots in rank order into `out` — identical bits on every rank.
+__global__ void peer_reduce_kernel(XSlot* local, int world, unsigned long long seq, PassResult* out, int npk,
+                                   const int* mode_ptr, int mode_override, int* err) {
+  const int mode = mode_override >= 0 ? mode_override : *mode_ptr;
+  if (mode == PASS_SKIP) return;  // the optimizer finished: no rank pushed, nothing to wait for
+  const int base = int(seq & 1ull) * kMaxWorld;
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) {
+    bool ok = true;
+    const long long t0 = clock64();
+    for (int r = 0; r < world && ok; ++r) {
+      const unsigned long long* flag = &local[base + r].seq;
+      for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v == seq) break;
+        if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; fail loudly instead of hanging the GPU
+          ok = false;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+    if (!ok) *err = 1;
+    s_ok = ok ? 1 : 0;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  for (int k = threadIdx.x; k < npk; k += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += *reinterpret_cast<volatile double*>(&local[base + r].v[k]);
+    out->v[k] = s;
+  }
+}
+
 __global__ void ldlt_test_kernel(int n, double* A, const double* rhs, double* out) { ldlt_solve_dev<double>(n, A, rhs, out); }
 
 }  // namespace
@@ -210,8 +247,18 @@ PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate
   return a;
 }
 
-int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int slot, int accumulate, int mode_override) {
-  const PassArgs a = make_args(ctx, st, slot, accumulate, mode_override);
+// `push`: this pass completes the rank-local result (last cost term), so its last CTA also pushes the packed
+// result to every peer when the NVLink exchange is open.
+int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int slot, int accumulate, int mode_override,
+                bool push) {
+  PassArgs a = make_args(ctx, st, slot, accumulate, mode_override);
+  if (push && ctx->world > 1 && ctx->peers_open) {
+    for (int r = 0; r < ctx->world; ++r) a.peer.base[r] = ctx->peer_base[r];
+    a.peer.world = ctx->world;
+    a.peer.rank = ctx->rank;
+    a.peer.push = 1;
+    a.peer.seq = ++ctx->xseq;
+  }
   PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
   if (p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL)
     return launch_p2p_moment(L, st->dtype, p->compute_dtype, p->loss,
@@ -220,8 +267,18 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
   return launch_dense(L, p->model, p->jacobian != MOPT_JAC_ANALYTICAL, st->dtype, p->compute_dtype, a);
 }
 
-int allreduce_trial(mopt_ctx* ctx, int P) {
+int allreduce_trial(mopt_ctx* ctx, int P, int mode_override) {
   if (ctx->world <= 1) return MOPT_OK;
+  if (ctx->peers_open) {
+    peer_reduce_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_xbuf, ctx->world, ctx->xseq, ctx->d_trial, packed_size(P),
+                                                  &ctx->d_lm->pass_mode, mode_override, ctx->d_xerr);
+    MOPT_CUDA_TRY(cudaGetLastError());
+    return MOPT_OK;
+  }
+  if (!ctx->nccl_comm) {
+    set_last_error("sharded context has neither a NCCL communicator nor an open peer exchange");
+    return MOPT_ERR_COMM;
+  }
   MOPT_NCCL_TRY(nccl().AllReduce(ctx->d_trial, ctx->d_trial, size_t(packed_size(P)), kNcclFloat64, kNcclSum,
                                  static_cast<NcclApi::comm_t>(ctx->nccl_comm), ctx->stream));
   return MOPT_OK;
@@ -252,8 +309,8 @@ int enqueue_pass(mopt_ctx* ctx, mopt_store* st, const mopt_problem* p, const dou
   }
   setup_kernel<<<1, 32, 0, ctx->stream>>>(&ctx->d_slots[0], xa);
   MOPT_CUDA_TRY(cudaGetLastError());
-  MOPT_TRY(launch_pass(ctx, st, p, 0, 0, mode));
-  MOPT_TRY(allreduce_trial(ctx, P));
+  MOPT_TRY(launch_pass(ctx, st, p, 0, 0, mode, true));
+  MOPT_TRY(allreduce_trial(ctx, P, mode));
   return MOPT_OK;
 }
 
@@ -276,6 +333,10 @@ namespace {
 int fetch_result(mopt_ctx* ctx, int P, double* H, double* b, double* sum) {
   MOPT_CUDA_TRY(cudaMemcpyAsync(ctx->h_result, ctx->d_trial, sizeof(double) * packed_size(P), cudaMemcpyDeviceToHost, ctx->stream));
   MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_xerr && *reinterpret_cast<volatile int*>(ctx->h_xerr)) {
+    set_last_error("peer exchange timed out waiting for another rank");
+    return MOPT_ERR_COMM;
+  }
   unpack_result(*ctx->h_result, P, H, b, sum);
   return MOPT_OK;
 }
@@ -299,6 +360,11 @@ int ctx_alloc(mopt_ctx* ctx) {
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_result, sizeof(PassResult), cudaHostAllocDefault));
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_lm, sizeof(LmState), cudaHostAllocDefault));
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_slot, sizeof(CostSlot), cudaHostAllocDefault));
+  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_xbuf, sizeof(XSlot) * 2 * kMaxWorld));
+  MOPT_CUDA_TRY(cudaMemset(ctx->d_xbuf, 0, sizeof(XSlot) * 2 * kMaxWorld));
+  MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_xerr, sizeof(int), cudaHostAllocMapped));
+  *ctx->h_xerr = 0;
+  MOPT_CUDA_TRY(cudaHostGetDevicePointer(&ctx->d_xerr, ctx->h_xerr, 0));
   ctx->flags_capacity = 4096;
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_flags, sizeof(int) * ctx->flags_capacity, cudaHostAllocMapped));
   MOPT_CUDA_TRY(cudaHostGetDevicePointer(&ctx->d_flags, ctx->h_flags, 0));
@@ -350,13 +416,14 @@ int mopt_comm_unique_id(void* out_id) {
 }
 
 int mopt_ctx_create_sharded(int device, int rank, int world_size, const void* nccl_unique_id, mopt_ctx** out) {
-  MOPT_REQUIRE(out && nccl_unique_id, "null out/unique id");
+  MOPT_REQUIRE(out, "null out");
   MOPT_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad rank/world_size");
   MOPT_TRY(mopt_ctx_create(device, out));
   mopt_ctx* ctx = *out;
   ctx->rank = rank;
   ctx->world = world_size;
-  if (world_size > 1) {
+  MOPT_REQUIRE(world_size <= kMaxWorld, "at most 8 ranks (one box) are supported");
+  if (world_size > 1 && nccl_unique_id) {  // without an id the caller must open the NVLink peer exchange instead
     if (!nccl().ok) {
       set_last_error(nccl().why);
       mopt_ctx_destroy(ctx);
@@ -383,6 +450,11 @@ int mopt_ctx_destroy(mopt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->nccl_comm) nccl().CommDestroy(static_cast<NcclApi::comm_t>(ctx->nccl_comm));
+  if (ctx->peers_open)
+    for (int r = 0; r < ctx->world; ++r)
+      if (r != ctx->rank && ctx->peer_base[r]) cudaIpcCloseMemHandle(ctx->peer_base[r]);
+  cudaFree(ctx->d_xbuf);
+  if (ctx->h_xerr) cudaFreeHost(ctx->h_xerr);
   cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trial);
   cudaFree(ctx->d_slots); cudaFree(ctx->d_lm);
   for (int i = 0; i < 2; ++i) {
@@ -398,6 +470,36 @@ int mopt_ctx_destroy(mopt_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
+  return MOPT_OK;
+}
+
+int mopt_ctx_peer_handle(mopt_ctx* ctx, void* out_handle) {
+  MOPT_REQUIRE(ctx && out_handle, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == MOPT_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  MOPT_CUDA_TRY(cudaIpcGetMemHandle(&h, ctx->d_xbuf));
+  std::memcpy(out_handle, &h, sizeof(h));
+  return MOPT_OK;
+}
+
+int mopt_ctx_open_peers(mopt_ctx* ctx, const void* handles) {
+  MOPT_REQUIRE(ctx && handles, "null argument");
+  MOPT_REQUIRE(ctx->world > 1, "not a sharded context");
+  MOPT_REQUIRE(!ctx->peers_open, "peers already open");
+  MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
+  for (int r = 0; r < ctx->world; ++r) {
+    if (r == ctx->rank) {
+      ctx->peer_base[r] = ctx->d_xbuf;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char*>(handles) + size_t(r) * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    MOPT_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_base[r] = static_cast<XSlot*>(p);
+  }
+  ctx->peers_open = true;
   return MOPT_OK;
 }
 
@@ -528,8 +630,9 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
       ctx->h_flags[enq] = 0;
       // cost->update(x0): re-associate correspondences; the kernel gates itself on "start of an outer iteration"
       for (int c = 0; c < n_costs; ++c) MOPT_TRY(enqueue_reassociate(stores[c], &ctx->d_slots[c].pb, ctx->d_lm));
-      for (int c = 0; c < n_costs; ++c) MOPT_TRY(launch_pass(ctx, stores[c], &problems[c], c, c > 0 ? 1 : 0, -1));
-      MOPT_TRY(allreduce_trial(ctx, P));
+      for (int c = 0; c < n_costs; ++c)
+        MOPT_TRY(launch_pass(ctx, stores[c], &problems[c], c, c > 0 ? 1 : 0, -1, c == n_costs - 1));
+      MOPT_TRY(allreduce_trial(ctx, P, -1));
       lm_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_trial, ctx->d_slots, ctx->d_flags + enq);
       MOPT_CUDA_TRY(cudaGetLastError());
       *last_slot = enq;
@@ -552,6 +655,10 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
   LmState* hs = ctx->h_lm;
   MOPT_CUDA_TRY(cudaMemcpyAsync(hs, ctx->d_lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
   MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_xerr && *reinterpret_cast<volatile int*>(ctx->h_xerr)) {
+    set_last_error("peer exchange timed out waiting for another rank");
+    return MOPT_ERR_COMM;
+  }
   if (!hs->done) {
     set_last_error("internal error: the LM state machine did not terminate within its slot budget");
     return MOPT_ERR_CUDA;

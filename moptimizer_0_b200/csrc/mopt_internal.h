@@ -40,6 +40,13 @@ struct mopt_ctx {
   // sharding
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  // NVLink peer exchange (mopt_ctx_open_peers): replaces the NCCL all-reduce of the packed result
+  mopt::XSlot* d_xbuf = nullptr;                 // this rank's slots[2][kMaxWorld]
+  mopt::XSlot* peer_base[mopt::kMaxWorld] = {nullptr};
+  bool peers_open = false;
+  unsigned long long xseq = 0;
+  int* h_xerr = nullptr;                         // mapped: set by the consumer kernel on a wait timeout
+  int* d_xerr = nullptr;
 };
 
 struct mopt_store {

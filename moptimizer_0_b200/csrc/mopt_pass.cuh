@@ -10,7 +10,26 @@
 
 namespace mopt {
 
+// Cross-GPU exchange of the packed result over NVLink peer memory (fused into the pass kernel's last CTA
+// instead of a separate NCCL all-reduce): every rank owns slots[parity][source rank]; the last CTA of a pass
+// stores its packed (H, b, sum) into its slot on EVERY rank (P2P stores through NVSwitch), fences, then
+// releases a sequence flag; a one-warp consumer on each rank acquires the flags and sums the slots in rank
+// order, so all ranks obtain bit-identical totals.  Two parities suffice: a rank can only be two passes ahead
+// of a peer after that peer has consumed the older slot.
+constexpr int kMaxWorld = 8;
+struct XSlot {
+  double v[kPackedMax];
+  unsigned long long seq;
+  unsigned long long pad;
+};
+struct PeerArgs {
+  XSlot* base[kMaxWorld];  // exchange buffer of rank r as mapped in this process (base[rank] is local)
+  int world, rank, push;
+  unsigned long long seq;  // sequence number of this exchange (>= 1)
+};
+
 struct PassArgs {
+  PeerArgs peer;
   StreamPtrs streams;
   int64_t n;                 // residuals in this store (this rank's shard)
   const ParamBlock* pb;      // setup(x) result (device)
@@ -73,6 +92,23 @@ __device__ __forceinline__ bool grid_reduce(const double (&lane_val)[NCH], const
   if (threadIdx.x == 0) *a.ticket = 0u;  // ready for the next launch (stream-ordered)
   __syncthreads();
   return true;
+}
+
+// Last CTA of a pass, after `out` is complete: push the packed result into this rank's slot on every rank.
+__device__ __forceinline__ void peer_push(const PassArgs& a, int npk) {
+  if (!a.peer.push) return;
+  __syncthreads();  // a.out fully written by this CTA
+  const int slot = int(a.peer.seq & 1ull) * kMaxWorld + a.peer.rank;
+  for (int i = threadIdx.x; i < npk * a.peer.world; i += blockDim.x) {
+    const int r = i / npk, k = i - r * npk;
+    a.peer.base[r][slot].v[k] = a.out->v[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (int(threadIdx.x) < a.peer.world) {
+    unsigned long long* flag = &a.peer.base[threadIdx.x][slot].seq;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(a.peer.seq) : "memory");
+  }
 }
 
 // =============================================================================================
@@ -337,6 +373,7 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
   } else {
     p2p_assemble(s_tot, a.pb, a.cost, a.out, a.accumulate, threadIdx.x, THREADS);
   }
+  peer_push(a, packed_size(6));
 }
 
 // =============================================================================================
@@ -534,6 +571,7 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
   } else {
     for (int i = threadIdx.x; i < NRAW; i += THREADS) a.out->v[i] = a.accumulate ? a.out->v[i] + s_tot[i] : s_tot[i];
   }
+  peer_push(a, NRAW);
 }
 
 // =============================================================================================
@@ -703,6 +741,7 @@ __global__ void __launch_bounds__(THREADS, 1) wide_pass_kernel(const PassArgs a)
   } else {
     for (int i = threadIdx.x; i < NRAW; i += THREADS) a.out->v[i] = a.accumulate ? a.out->v[i] + s_tot[i] : s_tot[i];
   }
+  peer_push(a, NRAW);
 }
 
 template <class M, typename CT, int THREADS>

@@ -6,6 +6,34 @@ from __future__ import annotations
 import numpy as np
 
 
+def make_sharded_context(local_device: int, rank: int, world: int, collective: str = "p2p"):
+    """One mopt context per rank of a torch.distributed job (already initialised).
+    collective = "p2p": NVLink peer exchange fused into the pass kernels (CUDA IPC handles gathered over
+    torch.distributed); "nccl": one ncclAllReduce per pass.  Returns (ctx, collective actually used, note)."""
+    import torch.distributed as dist
+    from . import capi
+    note = ""
+    if collective == "p2p":
+        ctx = capi.Context(local_device, sharded=(rank, world, None))
+        try:
+            mine = ctx.peer_handle()
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)
+            ctx.open_peers(handles)
+            ok = True
+        except capi.MoptError as e:  # e.g. IPC not permitted in this container
+            ok, note = False, str(e)
+        flags = [None] * world
+        dist.all_gather_object(flags, ok)
+        if all(flags):
+            return ctx, "p2p", ""
+        ctx.close()
+        note = note or "a peer could not open the exchange"
+    uid = [capi.Context.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    return capi.Context(local_device, sharded=(rank, world, uid[0])), "nccl", note
+
+
 def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous [first, last) of `rank`: [rank*N/W, (rank+1)*N/W) in integer arithmetic."""
     if not (0 <= rank < world):

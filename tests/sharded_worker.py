@@ -20,14 +20,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    shard = None
+    want = sys.argv[1] if len(sys.argv) > 1 else "p2p"
+    used = "none"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        uid = [capi.Context.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        shard = (rank, world, uid[0])
-    ctx = capi.Context(local, sharded=shard)
-    out = {}
+        ctx, used, note = sharding.make_sharded_context(local, rank, world, want)
+        assert used == want, f"collective {want} unavailable: {note}"
+    else:
+        ctx = capi.Context(local)
+    out = {"collective": used}
 
     # (1) fachada, fp64 store + fp64 compute, numerical Jacobian: exact LM parity across shardings
     src, tgt, _, _ = fachada()

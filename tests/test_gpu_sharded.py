@@ -15,23 +15,25 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(nproc):
+def _run(nproc, collective="p2p"):
     cmd = [sys.executable]
     if nproc > 1:
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
                 "--master-port", "29611"]
-    cmd += [os.path.join(ROOT, "tests", "sharded_worker.py")]
+    cmd += [os.path.join(ROOT, "tests", "sharded_worker.py"), collective]
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
     return json.loads(line[len("RESULT "):])
 
 
-def test_two_ranks_match_single_gpu():
+@pytest.mark.parametrize("collective", ["p2p", "nccl"])
+def test_two_ranks_match_single_gpu(collective):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    one, two = _run(1), _run(2)
+    one, two = _run(1), _run(2, collective)
+    assert two["collective"] == collective
     f1, f2 = one["fachada"], two["fachada"]
     # fp64: different summation order only
     assert rel_err(f2["H"], f1["H"]) < 1e-12 and rel_err(f2["b"], f1["b"]) < 1e-12
