@@ -98,16 +98,20 @@ __device__ __forceinline__ bool grid_reduce(const double (&lane_val)[NCH], const
 __device__ __forceinline__ void peer_push(const PassArgs& a, int npk) {
   if (!a.peer.push) return;
   __syncthreads();  // a.out fully written by this CTA
+  if (threadIdx.x >= 32) return;  // one warp pushes: a system-scope fence per thread of a 1024-thread CTA costs ~80 us
+  const int lane = threadIdx.x;
   const int slot = int(a.peer.seq & 1ull) * kMaxWorld + a.peer.rank;
-  for (int i = threadIdx.x; i < npk * a.peer.world; i += blockDim.x) {
+  for (int i = lane; i < npk * a.peer.world; i += 32) {
     const int r = i / npk, k = i - r * npk;
     a.peer.base[r][slot].v[k] = a.out->v[k];
   }
-  __threadfence_system();
-  __syncthreads();
-  if (int(threadIdx.x) < a.peer.world) {
-    unsigned long long* flag = &a.peer.base[threadIdx.x][slot].seq;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(a.peer.seq) : "memory");
+  __syncwarp();  // orders the lanes' stores before lane 0's fence
+  if (lane == 0) {
+    __threadfence_system();
+    for (int r = 0; r < a.peer.world; ++r) {
+      unsigned long long* flag = &a.peer.base[r][slot].seq;
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(a.peer.seq) : "memory");
+    }
   }
 }
 
