@@ -255,6 +255,23 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     H, b, s = ctx.result(6)
+    # diagnostics for N > 1: every rank's own pass time with the exchange switched off (no lock-step coupling);
+    # the gap between max(local) and the coupled step is what the collective + straggling cost
+    local_ms = None
+    if world > 1:
+        ctx.set_exchange_enabled(False)
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        for _ in range(args.steps):
+            ctx.linearize_async(store, prob, x0)
+        l1.record(stream)
+        barrier()
+        ctx.set_exchange_enabled(True)
+        mine = torch.tensor([l0.elapsed_time(l1) / args.steps], dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        local_ms = [float(v.item()) for v in allv]
     value = n_total / (ms_step * 1e-3) / 1e9
     peak, peak_kind = peaks()
     achieved = BYTES_PER_RES * n / (ms_total / args.steps * 1e-3) / 1e9  # this rank's kernel, GB/s
@@ -338,6 +355,8 @@ def run_ours(args):
             "gpu_launches": 2 * args.steps,
             "check": {"sum_rtr": s, "H00": float(H[0, 0]), "b0": float(b[0])},
         }
+        if local_ms is not None:
+            line["per_rank_uncoupled_ms_per_step"] = local_ms
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:

@@ -191,6 +191,9 @@ MOPT_API int mopt_comm_unique_id(void* out_id);
 #define MOPT_PEER_HANDLE_BYTES 64
 MOPT_API int mopt_ctx_peer_handle(mopt_ctx* ctx, void* out_handle);
 MOPT_API int mopt_ctx_open_peers(mopt_ctx* ctx, const void* handles_in_rank_order);
+/* Diagnostics: 0 makes every call return this rank's local sums only (no collective), e.g. to time each shard's
+ * pass without the lock-step coupling of the exchange.  Must be switched identically on every rank. */
+MOPT_API int mopt_ctx_set_exchange_enabled(mopt_ctx* ctx, int enabled);
 MOPT_API int mopt_ctx_destroy(mopt_ctx* ctx);
 MOPT_API int mopt_ctx_synchronize(mopt_ctx* ctx);
 /* cudaStream_t of the context as an integer (for CUDA-event timing by the caller). */

@@ -40,7 +40,7 @@ EXPORTS = [
     "mopt_ldlt_solve", "mopt_host_alloc", "mopt_host_free",
     "mopt_cloud_read_text", "mopt_cloud_write_binary", "mopt_cloud_read_binary", "mopt_cloud_free",
     "mopt_nn_index_create", "mopt_nn_index_destroy", "mopt_store_set_target", "mopt_store_reassociate",
-    "mopt_ctx_peer_handle", "mopt_ctx_open_peers",
+    "mopt_ctx_peer_handle", "mopt_ctx_open_peers", "mopt_ctx_set_exchange_enabled",
 ]
 PEER_HANDLE_BYTES = 64
 
@@ -134,6 +134,7 @@ def lib():
         L.mopt_store_reassociate.argtypes = [vp, dp, C.POINTER(i64)]
         L.mopt_ctx_peer_handle.argtypes = [vp, vp]
         L.mopt_ctx_open_peers.argtypes = [vp, vp]
+        L.mopt_ctx_set_exchange_enabled.argtypes = [vp, C.c_int]
         _lib = L
     return _lib
 
@@ -201,6 +202,9 @@ class Context:
         blob = b"".join(bytes(h) for h in handles_in_rank_order)
         buf = C.create_string_buffer(blob, len(blob))
         check(lib().mopt_ctx_open_peers(self._h, C.cast(buf, C.c_void_p)))
+
+    def set_exchange_enabled(self, enabled: bool):
+        check(lib().mopt_ctx_set_exchange_enabled(self._h, 1 if enabled else 0))
 
     def synchronize(self):
         check(lib().mopt_ctx_synchronize(self._h))

@@ -252,7 +252,7 @@ PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate
 int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int slot, int accumulate, int mode_override,
                 bool push) {
   PassArgs a = make_args(ctx, st, slot, accumulate, mode_override);
-  if (push && ctx->world > 1 && ctx->peers_open) {
+  if (push && ctx->world > 1 && ctx->peers_open && ctx->exchange_enabled) {
     for (int r = 0; r < ctx->world; ++r) a.peer.base[r] = ctx->peer_base[r];
     a.peer.world = ctx->world;
     a.peer.rank = ctx->rank;
@@ -268,7 +268,7 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
 }
 
 int allreduce_trial(mopt_ctx* ctx, int P, int mode_override) {
-  if (ctx->world <= 1) return MOPT_OK;
+  if (ctx->world <= 1 || !ctx->exchange_enabled) return MOPT_OK;
   if (ctx->peers_open) {
     peer_reduce_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_xbuf, ctx->world, ctx->xseq, ctx->d_trial, packed_size(P),
                                                   &ctx->d_lm->pass_mode, mode_override, ctx->d_xerr);
@@ -500,6 +500,12 @@ int mopt_ctx_open_peers(mopt_ctx* ctx, const void* handles) {
     ctx->peer_base[r] = static_cast<XSlot*>(p);
   }
   ctx->peers_open = true;
+  return MOPT_OK;
+}
+
+int mopt_ctx_set_exchange_enabled(mopt_ctx* ctx, int enabled) {
+  MOPT_REQUIRE(ctx, "null ctx");
+  ctx->exchange_enabled = enabled != 0;
   return MOPT_OK;
 }
 

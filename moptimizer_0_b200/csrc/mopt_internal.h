@@ -44,6 +44,7 @@ struct mopt_ctx {
   mopt::XSlot* d_xbuf = nullptr;                 // this rank's slots[2][kMaxWorld]
   mopt::XSlot* peer_base[mopt::kMaxWorld] = {nullptr};
   bool peers_open = false;
+  bool exchange_enabled = true;                  // diagnostics: false = rank-local results, no collective
   unsigned long long xseq = 0;
   int* h_xerr = nullptr;                         // mapped: set by the consumer kernel on a wait timeout
   int* d_xerr = nullptr;
