@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=100_000_000, help="correspondences per GPU")
+    ap.add_argument("--n", "--per-gpu", dest="n", type=int, default=100_000_000, help="correspondences per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=20_000_000, help="correspondences in the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -107,10 +107,12 @@ __device__ __forceinline__ void peer_push(const PassArgs& a, int npk) {
   }
   __syncwarp();  // orders the lanes' stores before lane 0's fence
   if (lane == 0) {
+    // ONE system-scope fence orders every slot store above before every flag store below; the flags themselves
+    // are relaxed stores (a release store per peer repeats the fence: measured +100 us per step at 8 ranks)
     __threadfence_system();
     for (int r = 0; r < a.peer.world; ++r) {
       unsigned long long* flag = &a.peer.base[r][slot].seq;
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(a.peer.seq) : "memory");
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(a.peer.seq) : "memory");
     }
   }
 }
