@@ -21,7 +21,9 @@
 #ifndef MOPT_CAPI_H
 #define MOPT_CAPI_H
 
+#ifndef __CUDACC_RTC__ /* NVRTC (user-defined device models) has no host headers; the kernel prologue typedefs these */
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -84,6 +86,8 @@ typedef enum mopt_model {
   MOPT_MODEL_PINHOLE_DISTORT = 6,
   MOPT_MODEL_COUNT_
 } mopt_model;
+/* Ids >= MOPT_MODEL_USER_BASE name run-time compiled user models (mopt_user_model_compile below). */
+#define MOPT_MODEL_USER_BASE 1000
 
 /* Which Jacobian the linearization uses. */
 typedef enum mopt_jacobian {
@@ -275,6 +279,41 @@ MOPT_API int mopt_cloud_read_text(const char* path, int columns, int keep, int h
 MOPT_API int mopt_cloud_write_binary(const char* path, const void* data, int host_dtype, int keep, int64_t n);
 MOPT_API int mopt_cloud_read_binary(const char* path, int pinned, int* host_dtype, int* keep, void** out, int64_t* n);
 MOPT_API int mopt_cloud_free(void* ptr, int pinned);
+
+/* ---- user-defined device models --------------------------------------------------- */
+/* IBaseModel's virtual f / f_df / setup (include/moptimizer/model.h:19-42) are host functions and cannot run in a
+ * kernel.  A user model is therefore given as CUDA C++ SOURCE and compiled at run time (NVRTC, sm_100a) INTO the
+ * same pass kernels the builtin models use: residual + analytical or finite-difference Jacobian + loss weighting +
+ * packed H / b accumulation + the three-level reduction, with the user's functions inlined.  The source defines
+ *
+ *   template <typename T>   // T = float or double: mopt_problem.compute_dtype, the reference's Scalar
+ *   __device__ void mopt_f(const T* s, const T* a, const T* b, T* r);             // model.h:33  f(x, r, index)
+ *   template <typename T>
+ *   __device__ void mopt_f_df(const T* s, const T* a, const T* b, T* r, T* J);    // model.h:42  f_df, J row-major O x P
+ *   __device__ void mopt_setup(const double* x, const double* consts, double* s); // model.h:19  setup(x), optional
+ *
+ * `a` / `b` are the ncomp_a / ncomp_b data components of ONE residual (what the reference models fetch from their
+ * caller-owned vectors with `index`), `s` is x itself or, when set_size > 0, the set_size values mopt_setup derived
+ * from x (and from mopt_problem.consts) — evaluated once per pass on the device, also for every finite-difference
+ * perturbation of x, exactly where linearization.h:84-93 calls setup on the cloned models.  mopt_f_df is only
+ * required with has_jacobian.  Helpers of csrc/mopt_setup.cuh (mopt::so3_exp_dev, ...) are visible to the source. */
+typedef struct mopt_user_model_desc {
+  int32_t num_parameters; /* P in [1, MOPT_MAX_PARAMETERS] */
+  int32_t num_outputs;    /* O in [1, MOPT_MAX_OUTPUTS] */
+  int32_t ncomp_a;        /* components of data group A (>= 1) */
+  int32_t ncomp_b;        /* components of data group B; ncomp_a + ncomp_b <= 6 planar streams */
+  int32_t has_jacobian;   /* the source defines mopt_f_df (MOPT_JAC_ANALYTICAL allowed) */
+  int32_t set_size;       /* 0: s = x;  1..24: the source defines mopt_setup writing this many values */
+  int32_t rot_offset;     /* index of a rotation-vector block in x for MOPT_MANIFOLD_SO3_LEFT, or -1 */
+  int32_t reserved;
+} mopt_user_model_desc;
+/* Compiles the model (the fp64 finite-difference variant immediately, so source errors surface here with the
+ * compiler log in mopt_last_error(); other dtype / Jacobian variants on first use) and returns its model id
+ * (>= MOPT_MODEL_USER_BASE) for mopt_store_create and mopt_problem.model.  Needs no GPU; launching does. */
+MOPT_API int mopt_user_model_compile(const char* cuda_source, const mopt_user_model_desc* desc, int* model_id);
+MOPT_API int mopt_user_model_release(int model_id);
+/* Compiler log of the most recent NVRTC compilation of this model (warnings included), "" if none. */
+MOPT_API const char* mopt_user_model_log(int model_id);
 
 /* Pinned host memory for callers that want full-speed uploads. */
 MOPT_API int mopt_host_alloc(void** ptr, uint64_t bytes);

@@ -202,4 +202,54 @@ class Powell : public DeviceModel<Scalar, Powell<Scalar>> {
   int kind() const override { return MOPT_MODEL_POWELL; }
 };
 
+/// A model defined by the user as CUDA C++ source (mopt_capi.h, "user-defined device models"): the device
+/// counterpart of deriving from BaseModel / BaseModelJacobian (model.h:50-104).  The source defines
+///   template <typename T> __device__ void mopt_f(const T* s, const T* a, const T* b, T* r);
+///   template <typename T> __device__ void mopt_f_df(const T* s, const T* a, const T* b, T* r, T* J);   // optional
+///   __device__ void mopt_setup(const double* x, const double* consts, double* s);                      // optional
+/// and is compiled at run time into the library's pass kernels.  `a` / `b` are AoS arrays with ncomp_a / ncomp_b
+/// scalars per residual.
+class UserModelSource {
+ public:
+  using Ptr = std::shared_ptr<UserModelSource>;
+  UserModelSource(const std::string& cuda_source, const mopt_user_model_desc& desc) : desc_(desc) {
+    check(mopt_user_model_compile(cuda_source.c_str(), &desc, &id_), "mopt_user_model_compile");
+  }
+  ~UserModelSource() { mopt_user_model_release(id_); }
+  UserModelSource(const UserModelSource&) = delete;
+  UserModelSource& operator=(const UserModelSource&) = delete;
+  int id() const { return id_; }
+  const mopt_user_model_desc& desc() const { return desc_; }
+  std::string log() const { return mopt_user_model_log(id_); }
+
+ private:
+  mopt_user_model_desc desc_;
+  int id_ = 0;
+};
+
+template <typename Scalar>
+class UserModel : public DeviceModel<Scalar, UserModel<Scalar>> {
+ public:
+  using Ptr = std::shared_ptr<UserModel>;
+  template <class HostScalar>
+  UserModel(Context::Ptr ctx, UserModelSource::Ptr source, const HostScalar* a, const HostScalar* b, int64_t n,
+            int store_dtype = dtypeOf<Scalar>())
+      : source_(std::move(source)) {
+    this->store_ = std::make_shared<Store>(std::move(ctx), source_->id(), store_dtype, n);
+    this->store_->upload(0, a, n);
+    if (source_->desc().ncomp_b > 0) this->store_->upload(1, b, n);
+    consts_.assign(32, 0.0);
+  }
+  int kind() const override { return source_->id(); }
+  /// Constants handed to the source's mopt_setup (mopt_problem.consts, up to 32 doubles).
+  void setConsts(const std::vector<double>& c) {
+    for (size_t i = 0; i < c.size() && i < 32; ++i) consts_[i] = c[i];
+  }
+  void fillConsts(double* c) const override { std::memcpy(c, consts_.data(), sizeof(double) * 32); }
+
+ private:
+  UserModelSource::Ptr source_;
+  std::vector<double> consts_;
+};
+
 }  // namespace moptimizer::device

@@ -41,7 +41,9 @@ EXPORTS = [
     "mopt_cloud_read_text", "mopt_cloud_write_binary", "mopt_cloud_read_binary", "mopt_cloud_free",
     "mopt_nn_index_create", "mopt_nn_index_destroy", "mopt_store_set_target", "mopt_store_reassociate",
     "mopt_ctx_peer_handle", "mopt_ctx_open_peers", "mopt_ctx_set_exchange_enabled",
+    "mopt_user_model_compile", "mopt_user_model_release", "mopt_user_model_log",
 ]
+MODEL_USER_BASE = 1000
 PEER_HANDLE_BYTES = 64
 
 
@@ -74,6 +76,12 @@ class Synth(C.Structure):
                 ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("n_total", C.c_int64),
                 ("noise_sigma", C.c_double), ("outlier_fraction", C.c_double), ("outlier_range", C.c_double),
                 ("consts", C.c_double * 32)]
+
+
+class UserModelDesc(C.Structure):
+    _fields_ = [("num_parameters", C.c_int32), ("num_outputs", C.c_int32), ("ncomp_a", C.c_int32),
+                ("ncomp_b", C.c_int32), ("has_jacobian", C.c_int32), ("set_size", C.c_int32),
+                ("rot_offset", C.c_int32), ("reserved", C.c_int32)]
 
 
 class MoptError(RuntimeError):
@@ -135,6 +143,10 @@ def lib():
         L.mopt_ctx_peer_handle.argtypes = [vp, vp]
         L.mopt_ctx_open_peers.argtypes = [vp, vp]
         L.mopt_ctx_set_exchange_enabled.argtypes = [vp, C.c_int]
+        L.mopt_user_model_compile.argtypes = [C.c_char_p, C.POINTER(UserModelDesc), C.POINTER(C.c_int)]
+        L.mopt_user_model_release.argtypes = [C.c_int]
+        L.mopt_user_model_log.argtypes = [C.c_int]
+        L.mopt_user_model_log.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -167,6 +179,30 @@ def make_problem(model: int, jacobian: int = JAC_ANALYTICAL, compute_dtype: int 
         for i, v in enumerate(np.asarray(consts, dtype=np.float64).reshape(-1)):
             p.consts[i] = v
     return p
+
+
+class UserModel:
+    """A run-time compiled device model (mopt_user_model_compile): CUDA C++ source defining mopt_f
+    (+ mopt_f_df, mopt_setup).  `.model` is the id to pass to Store(...) and make_problem(...)."""
+
+    def __init__(self, source: str, num_parameters: int, num_outputs: int, ncomp_a: int, ncomp_b: int,
+                 has_jacobian: bool = False, set_size: int = 0, rot_offset: int = -1):
+        d = UserModelDesc(num_parameters, num_outputs, ncomp_a, ncomp_b, 1 if has_jacobian else 0, set_size,
+                          rot_offset, 0)
+        mid = C.c_int(0)
+        check(lib().mopt_user_model_compile(source.encode(), C.byref(d), C.byref(mid)))
+        self.model = mid.value
+        MODEL_SHAPE[self.model] = (num_parameters, num_outputs, ncomp_a, ncomp_b)
+
+    @property
+    def log(self) -> str:
+        return lib().mopt_user_model_log(self.model).decode()
+
+    def release(self):
+        if self.model:
+            MODEL_SHAPE.pop(self.model, None)
+            check(lib().mopt_user_model_release(self.model))
+            self.model = 0
 
 
 class Context:

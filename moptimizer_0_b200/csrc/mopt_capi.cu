@@ -79,9 +79,6 @@ namespace {
 
 // model->setup(x) for one cost slot (and its finite-difference perturbations).  x travels as a
 // kernel argument, so back-to-back asynchronous calls need no staging buffer.
-struct XArg {
-  double v[kMaxP];
-};
 __global__ void setup_kernel(CostSlot* slot, XArg x) { setup_cost(slot->cost, x.v, &slot->pb, threadIdx.x, blockDim.x); }
 
 struct LmInit {
@@ -188,7 +185,8 @@ int validate_problem(const mopt_store* st, const mopt_problem* p, bool need_line
   MOPT_REQUIRE(p->manifold == MOPT_MANIFOLD_ADDITIVE || p->manifold == MOPT_MANIFOLD_SO3_LEFT, "unknown manifold");
   if (p->manifold == MOPT_MANIFOLD_SO3_LEFT)
     MOPT_REQUIRE(p->model == MOPT_MODEL_POINT2POINT || p->model == MOPT_MODEL_PINHOLE ||
-                     p->model == MOPT_MODEL_PINHOLE_DISTORT,
+                     p->model == MOPT_MODEL_PINHOLE_DISTORT ||
+                     (p->model >= MOPT_MODEL_USER_BASE && user_model_rot_offset(p->model) >= 0),
                  "MOPT_MANIFOLD_SO3_LEFT needs a model whose x[3..5] is a rotation vector");
   if (p->has_covariance) {
     const int O = sh.O;
@@ -210,6 +208,7 @@ void fill_cost(const mopt_problem* p, CostDev* c) {
   c->manifold = p->manifold;
   c->rot_offset = (p->model == MOPT_MODEL_POINT2POINT || p->model == MOPT_MODEL_PINHOLE ||
                    p->model == MOPT_MODEL_PINHOLE_DISTORT) ? 3 : -1;
+  if (p->model >= MOPT_MODEL_USER_BASE) c->rot_offset = user_model_rot_offset(p->model);
   const int O = p->num_outputs;
   for (int i = 0; i < O * O; ++i) c->cov[i] = p->has_covariance ? p->covariance[i] : ((i % (O + 1) == 0) ? 1.0 : 0.0);
   std::memcpy(c->consts, p->consts, sizeof(c->consts));
@@ -260,6 +259,8 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
     a.peer.seq = ++ctx->xseq;
   }
   PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
+  if (p->model >= MOPT_MODEL_USER_BASE)
+    return launch_user(L, ctx->device, p->model, p->jacobian != MOPT_JAC_ANALYTICAL, st->dtype, p->compute_dtype, a);
   if (p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL)
     return launch_p2p_moment(L, st->dtype, p->compute_dtype, p->loss,
                              p->variant == MOPT_P2P_EXACT || p->variant == MOPT_P2P_LEFT, a);
@@ -309,6 +310,8 @@ int enqueue_pass(mopt_ctx* ctx, mopt_store* st, const mopt_problem* p, const dou
   }
   setup_kernel<<<1, 32, 0, ctx->stream>>>(&ctx->d_slots[0], xa);
   MOPT_CUDA_TRY(cudaGetLastError());
+  if (user_model_has_setup(p->model))
+    MOPT_TRY(launch_user_setup(ctx->stream, ctx->device, p->model, &ctx->d_slots[0], nullptr, xa.v, P));
   MOPT_TRY(launch_pass(ctx, st, p, 0, 0, mode, true));
   MOPT_TRY(allreduce_trial(ctx, P, mode));
   return MOPT_OK;
@@ -324,6 +327,9 @@ int setup_slot(mopt_ctx* ctx, int slot, const mopt_problem* problem, const doubl
   for (int i = 0; i < problem->num_parameters; ++i) xa.v[i] = x[i];
   setup_kernel<<<1, 32, 0, ctx->stream>>>(&ctx->d_slots[slot], xa);
   MOPT_CUDA_TRY(cudaGetLastError());
+  if (user_model_has_setup(problem->model))
+    MOPT_TRY(launch_user_setup(ctx->stream, ctx->device, problem->model, &ctx->d_slots[slot], nullptr, xa.v,
+                               problem->num_parameters));
   return MOPT_OK;
 }
 }  // namespace mopt
@@ -622,6 +628,19 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
   for (int i = 0; i < P; ++i) in.x0[i] = x[i];
   lm_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_slots, in);
   MOPT_CUDA_TRY(cudaGetLastError());
+  // user models with their own setup(x): the run-time compiled setup kernel re-derives their parameter sets from
+  // the state's evaluation point after every optimizer transition (idempotent when x_eval did not move)
+  bool any_user_setup = false;
+  for (int c = 0; c < n_costs; ++c) any_user_setup = any_user_setup || user_model_has_setup(problems[c].model);
+  auto user_setups = [&]() -> int {
+    if (!any_user_setup) return MOPT_OK;
+    for (int c = 0; c < n_costs; ++c)
+      if (user_model_has_setup(problems[c].model))
+        MOPT_TRY(launch_user_setup(ctx->stream, ctx->device, problems[c].model, &ctx->d_slots[c], ctx->d_lm->x_eval,
+                                   nullptr, P));
+    return MOPT_OK;
+  };
+  MOPT_TRY(user_setups());
 
   // Passes are enqueued in batches, always one batch ahead of the one whose done flag is being
   // awaited, so the device never idles on the host; every rank reads the flag of the same slot,
@@ -641,6 +660,7 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
       MOPT_TRY(allreduce_trial(ctx, P, -1));
       lm_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_trial, ctx->d_slots, ctx->d_flags + enq);
       MOPT_CUDA_TRY(cudaGetLastError());
+      MOPT_TRY(user_setups());
       *last_slot = enq;
     }
     if (*last_slot >= 0) MOPT_CUDA_TRY(cudaEventRecord(ctx->ev_batch[par], ctx->stream));

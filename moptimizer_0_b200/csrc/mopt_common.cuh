@@ -1,16 +1,26 @@
 // Shared device/host helpers for the sm_100a linearization kernels.
 #pragma once
 
+// This header is also compiled at run time by NVRTC (mopt_rtc.cu: user-defined device models), where no
+// host headers exist: everything host-only sits behind !__CUDACC_RTC__.
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <cstdio>
 #include <string>
+#else
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#endif
 
 #include "mopt_capi.h"
 
 namespace mopt {
 
+#ifndef __CUDACC_RTC__
 // ------------------------------------------------------------------ errors ----
 void set_last_error(const std::string& msg);
 
@@ -37,6 +47,7 @@ void set_last_error(const std::string& msg);
     int _s = (expr);                \
     if (_s != MOPT_OK) return _s;   \
   } while (0)
+#endif  // !__CUDACC_RTC__
 
 // --------------------------------------------------------------- constants ----
 constexpr int kMaxP = MOPT_MAX_PARAMETERS;
@@ -70,6 +81,17 @@ struct CostDev {
   double consts[32];
   int manifold;    // mopt_manifold
   int rot_offset;  // index of the rotation-vector block of x, or -1
+};
+
+// One cost term on the device: its constants and the result of setup(x).
+struct CostSlot {
+  CostDev cost;
+  ParamBlock pb;
+};
+
+// A parameter vector passed by value as a kernel argument (no staging buffer for asynchronous calls).
+struct XArg {
+  double v[kMaxP];
 };
 
 // Packed result of one pass: H upper triangle (row-major, P(P+1)/2), then b (P), then sum.

@@ -83,6 +83,14 @@ int enqueue_reassociate(mopt_store* st, const ParamBlock* pb, const LmState* gat
 // mopt_pass_wide.cu
 int launch_wide(const PassLaunch& L, int model, int store_dtype, int compute_dtype, const PassArgs& a);
 
+// mopt_rtc.cu: run-time compiled user models (ids >= MOPT_MODEL_USER_BASE)
+int launch_user(const PassLaunch& L, int device, int model, bool numeric, int store_dtype, int compute_dtype,
+                const PassArgs& a);
+int launch_user_setup(cudaStream_t stream, int device, int model, CostSlot* slot, const double* x_dev,
+                      const double* x_host, int P);
+int user_model_rot_offset(int model);
+bool user_model_has_setup(int model);
+
 int pick_grid(const void* kernel, int threads, const PassLaunch& L, int64_t work_items);
 
 }  // namespace mopt

@@ -13,11 +13,6 @@ namespace mopt {
 
 enum LmPhase : int { LM_PHASE_LIN = 0, LM_PHASE_TRIAL = 1 };
 
-struct CostSlot {
-  CostDev cost;
-  ParamBlock pb;
-};
-
 struct LmState {
   // configuration (written by lm_init_kernel)
   int P, n_costs, max_it, lm_max_it, speculative, scalar_f32;

@@ -148,7 +148,9 @@ struct ModelShape {
   int ncomp_a, ncomp_b;  // components of the host AoS groups A and B
   bool has_analytical;
 };
+ModelShape user_model_shape(int model);  // mopt_rtc.cu: run-time compiled user models (ids >= MOPT_MODEL_USER_BASE)
 inline ModelShape model_shape(int model) {
+  if (model >= MOPT_MODEL_USER_BASE) return user_model_shape(model);
   switch (model) {
     case MOPT_MODEL_POINT2POINT: return {6, 3, 6, 3, 3, 3, true};
     case MOPT_MODEL_EXP_CURVE: return {2, 1, 2, 1, 1, 1, true};

@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
 //      residuals with ~30 shared-memory instructions per residual and 5 accumulators per lane.
 // The lane-owned layout is exactly what grid_reduce() expects, so no transposing shuffle is needed.
 // =============================================================================================
-template <class M, typename ST, typename CT, int THREADS>
+template <class M, typename ST, typename CT, int THREADS, bool NUMERIC = true>
 __global__ void __launch_bounds__(THREADS, 1) wide_pass_kernel(const PassArgs a) {
   const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
   if (mode == PASS_SKIP) return;
@@ -616,9 +616,10 @@ __global__ void __launch_bounds__(THREADS, 1) wide_pass_kernel(const PassArgs a)
 
   const int jac = a.cost->jacobian;
   const bool central = (jac == MOPT_JAC_CENTRAL);
-  const int nsets = central ? 1 + 2 * P : 1 + P;
+  const int nsets = !NUMERIC ? 1 : (central ? 1 + 2 * P : 1 + P);
   for (int i = threadIdx.x; i < nsets * SETN; i += THREADS) s_sets[i] = CT(a.pb->sets[i / SETN][i % SETN]);
-  for (int i = threadIdx.x; i < P; i += THREADS) s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
+  if (NUMERIC)
+    for (int i = threadIdx.x; i < P; i += THREADS) s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
   for (int i = threadIdx.x; i < O * O; i += THREADS) s_cov[i] = CT(a.cost->cov[i]);
   for (int e = threadIdx.x; e < NRAW; e += THREADS) {
     int i = 0, j = 0;
@@ -673,19 +674,24 @@ __global__ void __launch_bounds__(THREADS, 1) wide_pass_kernel(const PassArgs a)
       if (lane == (NRAW - 1) % 32) acc[(NRAW - 1) / 32] += s;
     } else {
       CT J[O * P];
+      if constexpr (NUMERIC) {
 #pragma unroll
-      for (int j = 0; j < P; ++j) {
-        CT rp[O];
-        M::template residual<CT>(s_sets + (1 + j) * SETN, e, rp);
-        if (central) {
-          CT rm[O];
-          M::template residual<CT>(s_sets + (1 + P + j) * SETN, e, rm);
+        for (int j = 0; j < P; ++j) {
+          CT rp[O];
+          M::template residual<CT>(s_sets + (1 + j) * SETN, e, rp);
+          if (central) {
+            CT rm[O];
+            M::template residual<CT>(s_sets + (1 + P + j) * SETN, e, rm);
 #pragma unroll
-          for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - rm[o]) * s_invh[j];
-        } else {
+            for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - rm[o]) * s_invh[j];
+          } else {
 #pragma unroll
-          for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - r[o]) * s_invh[j];
+            for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - r[o]) * s_invh[j];
+          }
         }
+      } else {
+        CT ra[O];  // the model's f_df (computeHessian, linearization.h:144); r above is the same f value
+        M::template residual_jacobian<CT>(s_sets, e, ra, J);
       }
       // row = [ J | w C J | w C r | e2 ]   (C is the identity unless setCovariance was called; s_cov holds it)
 #pragma unroll

@@ -6,14 +6,34 @@ namespace {
 
 constexpr int kThreads = 256;
 
-template <class M, typename ST, typename CT, bool NUMERIC>
-int launch_one(const PassLaunch& L, const PassArgs& a) {
-  auto kern = dense_pass_kernel<M, ST, CT, NUMERIC, kThreads, 1>;
+template <class M, typename ST, typename CT, bool NUMERIC, int THREADS, int MINB>
+int launch_shape(const PassLaunch& L, const PassArgs& a) {
+  auto kern = dense_pass_kernel<M, ST, CT, NUMERIC, THREADS, MINB>;
   const int64_t groups = (M::NS == 0) ? 1 : a.n / VecOf<ST>::N;
-  const int grid = pick_grid(reinterpret_cast<const void*>(kern), kThreads, L, groups);
-  kern<<<grid, kThreads, 0, L.stream>>>(a);
+  PassLaunch L2 = L;
+  L2.ctas_per_sm = 0;
+  const int grid = pick_grid(reinterpret_cast<const void*>(kern), THREADS, L2, groups);
+  kern<<<grid, THREADS, 0, L.stream>>>(a);
   MOPT_CUDA_TRY(cudaGetLastError());
   return MOPT_OK;
+}
+
+template <class M, typename ST, typename CT, bool NUMERIC>
+int launch_one(const PassLaunch& L, const PassArgs& a) {
+#ifdef MOPT_TUNE_DENSE
+  // tuning build: register-cap / CTA-shape variants of the fp32 finite-difference kernels, selected with
+  // mopt_ctx_set_launch(ctas_per_sm, threads)
+  if constexpr (NUMERIC && sizeof(CT) == 4 && sizeof(ST) == 4 && M::P > 0) {
+    if (L.threads == 128) {
+      if (L.ctas_per_sm == 6) return launch_shape<M, ST, CT, NUMERIC, 128, 6>(L, a);
+      return launch_shape<M, ST, CT, NUMERIC, 128, 4>(L, a);
+    }
+    if (L.ctas_per_sm == 2) return launch_shape<M, ST, CT, NUMERIC, 256, 2>(L, a);
+    if (L.ctas_per_sm == 3) return launch_shape<M, ST, CT, NUMERIC, 256, 3>(L, a);
+    if (L.ctas_per_sm == 4) return launch_shape<M, ST, CT, NUMERIC, 256, 4>(L, a);
+  }
+#endif
+  return launch_shape<M, ST, CT, NUMERIC, kThreads, 1>(L, a);
 }
 
 template <class M, bool NUMERIC>

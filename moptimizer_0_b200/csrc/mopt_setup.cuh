@@ -136,6 +136,13 @@ __device__ inline void setup_one_set(const CostDev& c, const double* xs, double*
       break;
     }
     default:  // parameter-only models: the set is x itself
+#ifdef MOPT_USER_SETUP
+      // run-time compiled user model with its own setup(x) (mopt_rtc.cu; model.h:19-22)
+      if (c.model >= MOPT_MODEL_USER_BASE) {
+        ::mopt_setup(xs, c.consts, set);
+        break;
+      }
+#endif
       for (int i = 0; i < c.P; ++i) set[i] = xs[i];
       break;
   }

@@ -439,6 +439,39 @@ TEST(Ingest, TextCloudFeedsTheDeviceStore) {
   std::remove(path);
 }
 
+// ------------------------------------------------ user-defined model on tst/curve_fitting ----
+// The reference lets a user derive from BaseModel/BaseModelJacobian (model.h:50-104); on the device path the same
+// model is CUDA source compiled at run time.  Same data, start and known answer as tst/curve_fitting.cpp:101-117.
+TEST(UserModel, CurveFittingFromSource) {
+  const char* src = R"(
+    template <typename T> __device__ void mopt_f(const T* x, const T* a, const T* b, T* r) {
+      r[0] = b[0] - exp(x[0] * a[0] + x[1]);                       // tst/curve_fitting.cpp:90
+    }
+    template <typename T> __device__ void mopt_f_df(const T* x, const T* a, const T* b, T* r, T* J) {
+      const T e = exp(x[0] * a[0] + x[1]);
+      r[0] = b[0] - e;  J[0] = -a[0] * e;  J[1] = -e;
+    })";
+  mopt_user_model_desc d{};
+  d.num_parameters = 2; d.num_outputs = 1; d.ncomp_a = 1; d.ncomp_b = 1; d.has_jacobian = 1; d.rot_offset = -1;
+  auto source = std::make_shared<device::UserModelSource>(src, d);
+  using UM = device::UserModel<double>;
+  UM::Ptr model(new UM(g_ctx, source, fx("curve_t").data(), fx("curve_y").data(), 67));
+  for (int analytical = 0; analytical < 2; ++analytical) {
+    LevenbergMarquadtDynamic<double> optimizer(2);
+    CostFunctionBase<double>* cost = analytical ? static_cast<CostFunctionBase<double>*>(new CostFunctionAnalyticalDynamic<double>(model, 2, 1, 67))
+                                                : new CostFunctionNumericalDynamic<double>(model, 2, 1, 67);
+    optimizer.addCost(cost);
+    double x0[] = {0.0, 0.0};
+    optimizer.minimize(x0);
+    EXPECT_NEAR(x0[0], 0.291861, 5e-5);
+    EXPECT_NEAR(x0[1], 0.131439, 5e-5);
+    delete cost;
+  }
+  // a source that does not compile fails loudly with the compiler's message
+  EXPECT_THROW(device::UserModelSource("template <typename T> __device__ void mopt_f(const T*, const T*, const T*, T* r) { r[0] = oops; }", d),
+               moptimizer::Exception);
+}
+
 // ---------------------------------------------------------------------------- API misuse paths ----
 namespace {
 struct HostOnlyModel : BaseModel<double, HostOnlyModel> {
