@@ -49,7 +49,9 @@ def parse():
     ap.add_argument("--threads", type=int, default=0, help="launch-shape override (0 = default, 256 = small CTAs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--lm", action="store_true", help="also time a device-resident LM solve (LM iters/s)")
+    ap.add_argument("--lm", dest="lm", action="store_true", default=True,
+                    help="also time a device-resident LM solve (LM iters/s, the second half of BASELINE.json's metric)")
+    ap.add_argument("--no-lm", dest="lm", action="store_false")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the 28 packed doubles are combined per step")
     ap.add_argument("--strong-total", type=int, default=0,
@@ -66,6 +68,25 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback"
+
+
+def ncu_traffic_bytes(n: int):
+    """DRAM bytes per launch of the moment kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    `ncu --set full` capture of this workload (profiles/); only meaningful for the size that capture was taken at."""
+    if n != 100_000_000:
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r1_p2p_moment_kernel_ncu_full.csv")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        tot = 0.0
+        for line in open(path):
+            f = line.strip().split(",")
+            if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                vals = [float(v) for v in f[2:]]
+                tot += scale[f[1]] * sum(vals) / len(vals)
+        return (tot or None), os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
 
 
 # ------------------------------------------------------------------------- clocks ----
@@ -325,14 +346,26 @@ def run_ours(args):
         v1, reps1, t1 = time_oracle(src, tgt, 1, args.cpu_seconds)
         cores = orc.hardware_concurrency() or (os.cpu_count() or 1)
         vt, repst, tt_ = time_oracle(src, tgt, cores, args.cpu_seconds / 2)
-        # parity spot check of the sample against the same rows on the device
+        # the reference's one multithreaded piece: parallelComputeCost (linearization.h:49-63, tst/parallel.cpp)
+        pc = oracle_cost(src, tgt)
+        pc.cost_threads = cores
+        orc.compute_cost(pc, [0.0] * 6, parallel=True)
+        t0, reps_pc = time.perf_counter(), 0
+        while reps_pc < 50 and time.perf_counter() - t0 < args.cpu_seconds / 4:
+            orc.compute_cost(pc, [0.0] * 6, parallel=True)
+            reps_pc += 1
+        t_pc = time.perf_counter() - t0
         cpu = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"first {m} correspondences of the same synthetic set, {reps1} serial fp64 linearizations "
                          f"in {t1:.1f} s (the reference's linearization loop is single-threaded, linearization.h:142)",
                "threaded": {"value": vt, "cores": cores, "reps": repst, "seconds": tt_,
-                            "note": "thread-local H/b on all host cores; the reference has no such variant"}}
+                            "note": "thread-local H/b on all host cores; the reference has no such variant"},
+               "parallel_cost": {"value": m * reps_pc / t_pc / 1e9, "cores": cores, "reps": reps_pc, "seconds": t_pc,
+                                 "note": "cost-only pass (sum r^T r), the reference's TBB parallel_reduce variant "
+                                         "(tst/parallel.cpp) restated with std::thread"}}
 
     if rank == 0:
+        traffic, traffic_src = ncu_traffic_bytes(n)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -348,7 +381,10 @@ def run_ours(args):
                                       "nccl": "ncclAllReduce(28 x f64) per step"}[collective]
                                      + (f" (p2p unavailable: {collective_note})" if collective_note else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                         "achieved_from": "24 B x n_per_gpu / (CUDA-event time of the K timed steps / K) on the "
+                                          "context's stream; a step = setup kernel (~3 us) + this kernel",
                          "kernel": "p2p_moment_kernel<float,float,HUBER,QROT>",
                          "algorithmic_bytes_per_launch": BYTES_PER_RES * n},
             "clocks": sampler.summary(),

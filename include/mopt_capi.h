@@ -134,8 +134,13 @@ typedef struct mopt_problem {
   double covariance[MOPT_MAX_OUTPUTS * MOPT_MAX_OUTPUTS]; /* O x O column-major, symmetric (setCovariance, cost_function.h:38-40) */
   double consts[32];                                       /* model constants, see mopt_model */
   int32_t manifold; /* mopt_manifold: how x + delta is formed and what the Jacobian differentiates */
-  int32_t reserved;
+  int32_t flags;    /* mopt_problem_flags, 0 by default */
 } mopt_problem;
+/* MOPT_FLAG_GENERIC_KERNEL: evaluate with the generic per-residual kernel even where a specialised one applies.
+ * Point2point finite differences normally run on the moment kernel: r is affine in the source point, so
+ * (r(x + h e_j) - r(x)) / h = ((R_j - R) p + (t_j - t)) / h exactly; the generic kernel forms the difference per
+ * residual in floating point as linearization.h:97-111 does (same Jacobian up to that subtraction's rounding). */
+typedef enum mopt_problem_flags { MOPT_FLAG_GENERIC_KERNEL = 1 } mopt_problem_flags;
 
 /* Optimizer knobs: optimizer.h:19,33-37, levenberg_marquadt_dyn.cpp:9,16, levenberg_marquadt_dyn.h:22-24. */
 typedef struct mopt_lm_options {

@@ -23,6 +23,7 @@ F32, F64 = 0, 1
 JAC_ANALYTICAL, JAC_FORWARD, JAC_CENTRAL = range(3)
 P2P_EXACT, P2P_REFTEST, P2P_REFTEST_COLMAJOR, P2P_LEFT = range(4)
 MANIFOLD_ADDITIVE, MANIFOLD_SO3_LEFT = 0, 1
+FLAG_GENERIC_KERNEL = 1
 LOSS_NONE, LOSS_GEMAN_MCCLURE, LOSS_HUBER = range(3)
 STATUS = ["CONVERGED", "MAXIMUM_ITERATIONS_REACHED", "SMALL_DELTA", "NUMERIC_ERROR", "FATAL_ERROR"]
 MODEL_SHAPE = {  # model -> (P, O, ncomp_a, ncomp_b)
@@ -52,7 +53,7 @@ class Problem(C.Structure):
                 ("num_outputs", C.c_int32), ("jacobian", C.c_int32), ("compute_dtype", C.c_int32),
                 ("loss", C.c_int32), ("has_covariance", C.c_int32), ("loss_param", C.c_double),
                 ("covariance", C.c_double * (MAX_OUTPUTS * MAX_OUTPUTS)), ("consts", C.c_double * 32),
-                ("manifold", C.c_int32), ("reserved", C.c_int32)]
+                ("manifold", C.c_int32), ("flags", C.c_int32)]
 
 
 class LmOptions(C.Structure):
@@ -162,10 +163,11 @@ def _dp(a: np.ndarray):
 
 def make_problem(model: int, jacobian: int = JAC_ANALYTICAL, compute_dtype: int = F64, loss: int = LOSS_NONE,
                  loss_param: float = 0.0, variant: int = P2P_EXACT, covariance: Optional[np.ndarray] = None,
-                 consts: Optional[Sequence[float]] = None, manifold: int = 0) -> Problem:
+                 consts: Optional[Sequence[float]] = None, manifold: int = 0, flags: int = 0) -> Problem:
     P, O, _, _ = MODEL_SHAPE[model]
     p = Problem()
     p.manifold = manifold
+    p.flags = flags
     p.model, p.variant, p.num_parameters, p.num_outputs = model, variant, P, O
     p.jacobian, p.compute_dtype, p.loss, p.loss_param = jacobian, compute_dtype, loss, float(loss_param)
     p.has_covariance = 0

@@ -264,6 +264,11 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
   if (p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL)
     return launch_p2p_moment(L, st->dtype, p->compute_dtype, p->loss,
                              p->variant == MOPT_P2P_EXACT || p->variant == MOPT_P2P_LEFT, a);
+  // finite differences of an affine residual are affine in the source point: moment kernel with q = p
+  // (mopt_setup.cuh fills the affine pieces); cost-only passes of this model take the same kernel
+  if (p->model == MOPT_MODEL_POINT2POINT && !(p->flags & MOPT_FLAG_GENERIC_KERNEL) &&
+      !(st->dtype == MOPT_F64 && p->compute_dtype == MOPT_F32))
+    return launch_p2p_moment(L, st->dtype, p->compute_dtype, p->loss, false, a);
   if (p->model == MOPT_MODEL_PINHOLE_DISTORT) return launch_wide(L, p->model, st->dtype, p->compute_dtype, a);
   return launch_dense(L, p->model, p->jacobian != MOPT_JAC_ANALYTICAL, st->dtype, p->compute_dtype, a);
 }

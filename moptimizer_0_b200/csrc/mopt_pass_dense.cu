@@ -23,7 +23,7 @@ int launch_one(const PassLaunch& L, const PassArgs& a) {
 #ifdef MOPT_TUNE_DENSE
   // tuning build: register-cap / CTA-shape variants of the fp32 finite-difference kernels, selected with
   // mopt_ctx_set_launch(ctas_per_sm, threads)
-  if constexpr (NUMERIC && sizeof(CT) == 4 && sizeof(ST) == 4 && M::P > 0) {
+  if constexpr (NUMERIC && sizeof(ST) == 4 && M::P >= 4) {
     if (L.threads == 128) {
       if (L.ctas_per_sm == 6) return launch_shape<M, ST, CT, NUMERIC, 128, 6>(L, a);
       return launch_shape<M, ST, CT, NUMERIC, 128, 4>(L, a);
@@ -33,7 +33,12 @@ int launch_one(const PassLaunch& L, const PassArgs& a) {
     if (L.ctas_per_sm == 4) return launch_shape<M, ST, CT, NUMERIC, 256, 4>(L, a);
   }
 #endif
-  return launch_shape<M, ST, CT, NUMERIC, kThreads, 1>(L, a);
+  // Finite-difference kernels of the 6-parameter models want all 1 + 2P parameter sets in registers (247-255
+  // registers, one 256-thread CTA per SM, issue slots 34 % busy).  Capping them at 80 registers (3 CTAs per SM)
+  // turns the hoisted sets into L1-resident local loads and triples the warps that hide the division / MUFU
+  // latency: camera 50 M central 2.55 -> 1.37 ms, forward 2.12 -> 0.96 ms (profiles/r1_tune_dense.txt).
+  constexpr int kMinB = (NUMERIC && sizeof(CT) == 4 && M::P >= 4) ? 3 : 1;
+  return launch_shape<M, ST, CT, NUMERIC, kThreads, kMinB>(L, a);
 }
 
 template <class M, bool NUMERIC>

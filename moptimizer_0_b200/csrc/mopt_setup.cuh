@@ -222,9 +222,31 @@ __device__ inline void setup_cost(const CostDev& c, const double* x, ParamBlock*
     }
     setup_one_set(c, xs, pb->sets[s]);
   }
+  __syncwarp();  // the sets written by the other lanes are read below
   if (lane == 0) {
     for (int i = 0; i < P; ++i) pb->x[i] = x[i];
     if (c.model == MOPT_MODEL_POINT2POINT && c.jacobian == MOPT_JAC_ANALYTICAL) setup_p2p_affine(c, x, pb->jaff);
+    if (c.model == MOPT_MODEL_POINT2POINT && c.jacobian != MOPT_JAC_ANALYTICAL) {
+      // r = R p + t - y is affine in p, so the finite-difference Jacobian of linearization.h:97-111 is too:
+      //   (r(x + h_j e_j) - r(x)) / h_j = ((R_j - R) p + (t_j - t)) / h_j        (central: +- sets, 2 h_j)
+      // which lets the numerical linearization run on the moment kernel (q = p) at the analytical kernel's cost.
+      const bool central = (c.jacobian == MOPT_JAC_CENTRAL);
+      for (int k = 0; k < 4; ++k)
+        for (int i = 0; i < 18; ++i) pb->jaff[k][i] = 0.0;
+      for (int j = 0; j < P; ++j) {
+        const double* sp = pb->sets[1 + j];
+        const double* sm = central ? pb->sets[1 + P + j] : pb->sets[0];
+        const double inv = 1.0 / (central ? 2.0 * pb->h[j] : pb->h[j]);
+        for (int r = 0; r < 3; ++r) {
+          const double dt = f32 ? double(float(sp[9 + r])) - double(float(sm[9 + r])) : sp[9 + r] - sm[9 + r];
+          pb->jaff[0][r * 6 + j] = dt * inv;
+          for (int k = 0; k < 3; ++k) {
+            const double dr = f32 ? double(float(sp[r * 3 + k])) - double(float(sm[r * 3 + k])) : sp[r * 3 + k] - sm[r * 3 + k];
+            pb->jaff[k + 1][r * 6 + j] = dr * inv;
+          }
+        }
+      }
+    }
   }
 }
 

@@ -83,19 +83,43 @@ def test_p2p_robust_loss_and_covariance(ctx, loss, param, store_dtype, compute_d
 
 
 # ---- numerical Jacobians (linearization.h:65-124), fp64 compute --------------------------------
+# flags 0: point2point finite differences on the moment kernel (the difference quotient of an affine residual is
+# affine in the source point); FLAG_GENERIC_KERNEL: the per-residual difference quotient as the reference forms it
+@pytest.mark.parametrize("flags", [0, 1])
 @pytest.mark.parametrize("jac", [1, 2])
 @pytest.mark.parametrize("store_dtype", [0, 1])
-def test_p2p_numerical_matches_oracle(ctx, jac, store_dtype):
+def test_p2p_numerical_matches_oracle(ctx, jac, store_dtype, flags):
     src, tgt, _, _ = fachada()
     st = p2p_store(ctx, src, tgt, store_dtype)
     osrc, otgt = oracle_data(src, tgt, store_dtype)
     n = src.shape[0]
     for x in X_TEST:
-        prob = capi.make_problem(capi.MODEL_POINT2POINT, jac, capi.F64)
+        prob = capi.make_problem(capi.MODEL_POINT2POINT, jac, capi.F64, flags=flags)
         H, b, s = ctx.linearize(st, prob, x)
         Ho, bo, so = orc.linearize(orc.Cost(orc.P2P, 6, 3, n, a=osrc, b=otgt, jac_mode=jac), x)
         # finite differences amplify rounding by 1/h ~ 7e7: agreement to ~1e-7 is what fp64 allows
         assert rel_err(H, Ho) < 1e-6 and rel_err(b, bo) < 1e-6 and abs(s - so) <= 1e-10 * abs(so)
+    st.close()
+
+
+@pytest.mark.parametrize("jac", [1, 2])
+def test_p2p_numerical_fp32_moment_vs_generic_kernel(ctx, jac):
+    """fp32 compute, Huber + covariance: the moment-kernel finite differences against the per-residual ones and the
+    oracle run in float (same step rule h = sqrt(eps_f32) |x_j|).  The per-residual quotient carries the fp32
+    subtraction's rounding (~eps/h per entry), the moment form does not: agreement is to that noise."""
+    src, tgt, _, _ = fachada()
+    st = p2p_store(ctx, src, tgt, 0)
+    osrc, otgt = oracle_data(src, tgt, 0)
+    x = [9.5, 10.0, 0.3, 0.35, 0.3, 0.5]
+    cov = np.array([[2.0, 0.3, 0.1], [0.3, 1.5, -0.2], [0.1, -0.2, 0.7]])
+    kw = dict(loss=capi.LOSS_HUBER, loss_param=0.5, covariance=cov)
+    Hm, bm, sm = ctx.linearize(st, capi.make_problem(capi.MODEL_POINT2POINT, jac, capi.F32, **kw), x)
+    Hg, bg, sg = ctx.linearize(st, capi.make_problem(capi.MODEL_POINT2POINT, jac, capi.F32, flags=1, **kw), x)
+    oc = orc.Cost(orc.P2P, 6, 3, src.shape[0], a=osrc, b=otgt, jac_mode=jac, loss=orc.LOSS_HUBER, loss_param=0.5, cov=cov)
+    Ho, bo, so = orc.linearize(oc, x, orc.F32)
+    assert abs(sm - sg) <= 1e-6 * sg and abs(sm - so) <= 1e-4 * so
+    assert rel_err(Hm, Hg) < 5e-3 and rel_err(bm, bg) < 5e-3, (rel_err(Hm, Hg), rel_err(bm, bg))
+    assert rel_err(Hm, Ho) < 5e-3 and rel_err(bm, bo) < 5e-3, (rel_err(Hm, Ho), rel_err(bm, bo))
     st.close()
 
 

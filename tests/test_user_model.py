@@ -197,9 +197,13 @@ def test_user_p2p_with_setup_matches_builtin_and_oracle(ctx, store_dtype, comput
         st.upload(1, tgt)
         for jac in (capi.JAC_FORWARD, capi.JAC_CENTRAL):
             # consts[0] tells the user setup which Scalar the reference would run so3::Exp in (its eps guard)
-            prob = capi.make_problem(model, jac, compute_dtype, consts=[1.0 if compute_dtype == 0 else 0.0])
+            # the builtin model is held to the generic per-residual kernel (its default for finite differences is
+            # the moment kernel), which is the code a user model is compiled into
+            prob = capi.make_problem(model, jac, compute_dtype, consts=[1.0 if compute_dtype == 0 else 0.0],
+                                     flags=capi.FLAG_GENERIC_KERNEL)
             out[(model, jac)] = ctx.linearize(st, prob, x)
-        prob = capi.make_problem(model, capi.JAC_FORWARD, compute_dtype, consts=[1.0 if compute_dtype == 0 else 0.0])
+        prob = capi.make_problem(model, capi.JAC_FORWARD, compute_dtype, consts=[1.0 if compute_dtype == 0 else 0.0],
+                                 flags=capi.FLAG_GENERIC_KERNEL)
         out[(model, "lm")] = ctx.lm_minimize([st], [prob], [0.0] * 6, max_iterations=50)
         if model != capi.MODEL_POINT2POINT:  # manifold update works for user models that name a rotation block
             probm = capi.make_problem(model, capi.JAC_FORWARD, compute_dtype, manifold=capi.MANIFOLD_SO3_LEFT,
@@ -216,7 +220,8 @@ def test_user_p2p_with_setup_matches_builtin_and_oracle(ctx, store_dtype, comput
         oc = orc.Cost(orc.P2P, 6, 3, n, a=src, b=tgt, jac_mode=orc.JAC_FORWARD)
         Ho, bo, so = orc.linearize(oc, x)
         Hu, bu, su = out[(um.model, capi.JAC_FORWARD)]
-        assert rel_err(Hu, Ho) < 1e-10 and rel_err(bu, bo) < 1e-10 and abs(su - so) <= 1e-10 * so
+        # finite differences amplify rounding by 1/h ~ 7e7: agreement to ~1e-7 is what fp64 allows
+        assert rel_err(Hu, Ho) < 1e-6 and rel_err(bu, bo) < 1e-6 and abs(su - so) <= 1e-10 * so
         gt = FX["fachada"]["lm_numerical"]["x"] if "lm_numerical" in FX["fachada"] else None
         assert lu.status == "CONVERGED" and lu.executed_iterations == 5 and lu.sequence == "AAAAA"
         if gt is not None:
