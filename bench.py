@@ -37,7 +37,7 @@ NOISE_SIGMA, OUTLIER_FRACTION, OUTLIER_RANGE = 0.01, 0.05, 1.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", "--per-gpu", dest="n", type=int, default=100_000_000, help="correspondences per GPU")
@@ -326,6 +326,7 @@ def run_ours(args):
     # ---- optional: device-resident LM solve (LM iters/s) --------------------------------------------
     lm = None
     if args.lm:
+        ctx.lm_minimize([store], [prob], x0, max_iterations=2)  # untimed: first launches of the optimizer kernels
         barrier()
         t0 = time.perf_counter()
         r = ctx.lm_minimize([store], [prob], x0, max_iterations=50)

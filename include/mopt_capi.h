@@ -166,8 +166,9 @@ typedef struct mopt_lm_report {
   mopt_lm_trial trials[MOPT_MAX_TRACE];
 } mopt_lm_report;
 
-/* Synthetic workloads generated on the device by a counter-based hash of (seed, global index);
- * the generator is specified bit-exactly in include/mopt_synth.h so a host can reproduce it. */
+/* Synthetic workloads generated on the device by a counter-based hash of (seed, global index) — the value of
+ * element i does not depend on how the set is sharded (csrc/mopt_store.cu); read it back with
+ * mopt_store_download to run a host implementation on identical data. */
 typedef struct mopt_synth {
   uint64_t seed;
   int64_t first_index; /* global index of this store's element 0 (rank offset when sharded) */

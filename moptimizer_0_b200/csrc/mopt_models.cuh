@@ -93,20 +93,34 @@ struct PinholeModel {
 struct PinholeDistortModel {
   static constexpr int P = 15, O = 2, NS = 5, NA = 3, SETN = 21;
   static constexpr bool HAS_JAC = false;
+  // Two-stage residual for the wide kernel: the extrinsics (x[0..6) -> set[0..12)) only enter the rigid transform
+  // and the perspective division; perturbing an intrinsic or distortion parameter re-runs stage 2 alone.
+  static constexpr int STAGE1_PARAMS = 6, STAGE1_VALUES = 3;
   template <typename CT>
-  static __device__ __forceinline__ void residual(const CT* s, const CT (&e)[5], CT (&r)[2]) {
+  static __device__ __forceinline__ void stage1(const CT* s, const CT (&e)[5], CT (&t)[3]) {
     CT p[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) p[k] = fma(s[k * 4 + 0], e[0], fma(s[k * 4 + 1], e[1], fma(s[k * 4 + 2], e[2], s[k * 4 + 3])));
     const CT iz = CT(1) / p[2];
-    const CT xn = p[0] * iz, yn = p[1] * iz;
-    const CT r2 = fma(xn, xn, yn * yn);
+    t[0] = p[0] * iz;
+    t[1] = p[1] * iz;
+    t[2] = fma(t[0], t[0], t[1] * t[1]);
+  }
+  template <typename CT>
+  static __device__ __forceinline__ void stage2(const CT* s, const CT (&e)[5], const CT (&t)[3], CT (&r)[2]) {
+    const CT xn = t[0], yn = t[1], r2 = t[2];
     const CT radial = fma(r2, fma(r2, fma(r2, s[20], s[17]), s[16]), CT(1));  // 1 + k1 r2 + k2 r2^2 + k3 r2^3
     const CT xy2 = CT(2) * xn * yn;
     const CT xd = fma(xn, radial, fma(s[18], xy2, s[19] * fma(CT(2) * xn, xn, r2)));
     const CT yd = fma(yn, radial, fma(s[18], fma(CT(2) * yn, yn, r2), s[19] * xy2));
     r[0] = e[3] - fma(s[12], xd, s[14]);
     r[1] = e[4] - fma(s[13], yd, s[15]);
+  }
+  template <typename CT>
+  static __device__ __forceinline__ void residual(const CT* s, const CT (&e)[5], CT (&r)[2]) {
+    CT t[3];
+    stage1<CT>(s, e, t);
+    stage2<CT>(s, e, t, r);
   }
   template <typename CT>
   static __device__ __forceinline__ void residual_jacobian(const CT*, const CT (&)[5], CT (&)[2], CT (&)[30]) {}

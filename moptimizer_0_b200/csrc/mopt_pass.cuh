@@ -52,23 +52,17 @@ struct PassArgs {
 //   NRAW raw sums; V = values per transposing-reduce chunk (power of two <= 32)
 // After the call, in the LAST CTA only, s_tot[0..NRAW) holds the grid totals (fp64) and the
 // function returns true for every thread of that CTA.
-template <int NRAW, int V, int NCH, int THREADS>
-__device__ __forceinline__ bool grid_reduce(const double (&lane_val)[NCH], const PassArgs& a, double* s_tot,
-                                            double* s_warp /* [THREADS/32][NCH*V] */) {
+// Part 2: s_warp[w * STRIDE + i] holds warp w's total of raw sum i (all warps written, CTA synchronised).
+template <int NRAW, int STRIDE, int THREADS>
+__device__ __forceinline__ bool grid_reduce_shared(const PassArgs& a, double* s_tot, const double* s_warp) {
   constexpr int NW = THREADS / 32;
-  constexpr int SHIFT = 5 - Log2<V>::value;  // owner lane of index i is (i << SHIFT)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ bool s_last;
-  if ((lane & ((1 << SHIFT) - 1)) == 0) {
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) s_warp[warp * (NCH * V) + ch * V + (lane >> SHIFT)] = lane_val[ch];
-  }
-  __syncthreads();
   const int G = gridDim.x;
   for (int i = threadIdx.x; i < NRAW; i += THREADS) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) s += s_warp[w * (NCH * V) + i];
+    for (int w = 0; w < NW; ++w) s += s_warp[w * STRIDE + i];
     a.partials[size_t(i) * G + blockIdx.x] = s;
   }
   __threadfence();
@@ -92,6 +86,19 @@ __device__ __forceinline__ bool grid_reduce(const double (&lane_val)[NCH], const
   if (threadIdx.x == 0) *a.ticket = 0u;  // ready for the next launch (stream-ordered)
   __syncthreads();
   return true;
+}
+
+template <int NRAW, int V, int NCH, int THREADS>
+__device__ __forceinline__ bool grid_reduce(const double (&lane_val)[NCH], const PassArgs& a, double* s_tot,
+                                            double* s_warp /* [THREADS/32][NCH*V] */) {
+  constexpr int SHIFT = 5 - Log2<V>::value;  // owner lane of index i is (i << SHIFT)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((lane & ((1 << SHIFT) - 1)) == 0) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) s_warp[warp * (NCH * V) + ch * V + (lane >> SHIFT)] = lane_val[ch];
+  }
+  __syncthreads();
+  return grid_reduce_shared<NRAW, NCH * V, THREADS>(a, s_tot, s_warp);
 }
 
 // Last CTA of a pass, after `out` is complete: push the packed result into this rank's slot on every rank.
@@ -580,39 +587,105 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
   peer_push(a, NRAW);
 }
 
+#endif  // __CUDACC__
+
 // =============================================================================================
 // Wide pass kernel: models whose packed size P(P+1)/2 + P + 1 exceeds 32 (the n x n calibration case,
-// e.g. P = 15 -> 136 + 15 + 1 = 152 sums).  152 per-thread accumulators do not fit in registers next to a
-// 2 x 15 Jacobian, so the accumulators are distributed over the LANES of each warp instead:
-//   1. every lane evaluates one residual and its finite-difference Jacobian (same code as the dense kernel)
-//      and writes the row  [ J (O x P) | w C J (O x P) | w C r (O) | r^T r ]  into the warp's shared tile;
-//   2. lane l owns packed entries l, l+32, ... and sweeps the 32 rows of the tile, so a warp finishes 32
-//      residuals with ~30 shared-memory instructions per residual and 5 accumulators per lane.
-// The lane-owned layout is exactly what grid_reduce() expects, so no transposing shuffle is needed.
+// e.g. P = 15 -> 120 + 15 + 1 = 136 sums).  That many per-thread accumulators do not fit in registers next
+// to a 2 x 15 Jacobian, so each warp works in two phases on 32 residuals at a time:
+//   1. every lane evaluates ONE residual and its Jacobian (finite differences or the model's f_df) and
+//      stores the row  [ J (O x PA) | B = w C [J | r] (O x PB) ]  into the warp's shared tile with 16-byte
+//      stores (row stride an odd number of 16-byte units: conflict-free);
+//   2. the warp computes  C += J^T B  over the 32 rows as a register-tiled product: lane (ti, tj) of an
+//      LI x LJ lane grid owns the TI x 4 block C[ti TI.., 4 tj..] and reads TI values of J and one 16-byte
+//      vector of B per (row, output): 8 FMA per 2 shared loads for P = 15.  Columns 0..P-1 of C are H
+//      (the upper triangle is kept), column P is b.
+// Models may split their residual into a stage that depends only on the first STAGE1_PARAMS parameters
+// (e.g. the rigid transform + perspective division) and a cheap second stage; perturbations of the
+// remaining parameters then re-run only the second stage (bit-identical to the full evaluation).
 // =============================================================================================
+struct WideLayout {
+  int LJ, LI, TI, PA, PB, ROW;  // ROW in elements
+};
+__host__ __device__ constexpr WideLayout wide_layout(int P, int O, int elem_bytes) {
+  const int vpe = 16 / elem_bytes;            // elements per 16-byte unit
+  const int LJ = (P + 1 + 3) / 4;             // lanes across the columns of B (4 columns each)
+  const int LI = 32 / LJ;                     // lanes down the rows of J^T
+  const int TI = (P + LI - 1) / LI;           // rows of J^T per lane
+  const int PA = ((LI * TI + vpe - 1) / vpe) * vpe;
+  const int PB = LJ * 4;
+  int row = O * PA + O * PB;                  // multiple of vpe
+  if (((row / vpe) & 1) == 0) row += vpe;     // odd number of 16-byte units per row
+  return WideLayout{LJ, LI, TI, PA, PB, row};
+}
+__host__ __device__ constexpr size_t wide_smem_bytes_rt(int P, int O, int setn, int elem_bytes, int threads) {
+  return size_t(elem_bytes) * (size_t(threads / 32) * 32 * wide_layout(P, O, elem_bytes).ROW + size_t(1 + 2 * P) * setn + P + O * O) + 16;
+}
+
+#ifdef __CUDACC__
+// Does model M declare a two-stage residual?
+template <class M, class = void>
+struct WideStage {
+  static constexpr int PARAMS = M::P;  // every parameter feeds the whole residual
+  static constexpr int NT = 1;
+};
+template <class M>
+struct WideStage<M, decltype(void(M::STAGE1_PARAMS))> {
+  static constexpr int PARAMS = M::STAGE1_PARAMS;
+  static constexpr int NT = M::STAGE1_VALUES;
+};
+
+template <typename CT>
+__device__ __forceinline__ void lds16(const CT* p, CT (&v)[16 / sizeof(CT)]);
+template <>
+__device__ __forceinline__ void lds16<float>(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void lds16<double>(const double* p, double (&v)[2]) {
+  const double2 t = *reinterpret_cast<const double2*>(p);
+  v[0] = t.x; v[1] = t.y;
+}
+template <typename CT>
+__device__ __forceinline__ void sts16(CT* p, const CT* v);
+template <>
+__device__ __forceinline__ void sts16<float>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void sts16<double>(double* p, const double* v) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+
 template <class M, typename ST, typename CT, int THREADS, bool NUMERIC = true>
-__global__ void __launch_bounds__(THREADS, 1) wide_pass_kernel(const PassArgs a) {
+__global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_kernel(const PassArgs a) {
   const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
   if (mode == PASS_SKIP) return;
   constexpr int P = M::P, O = M::O, NS = M::NS;
   constexpr int NRAW = P * (P + 1) / 2 + P + 1;
   constexpr int NCH = (NRAW + 31) / 32;
+  constexpr int STRIDE = NCH * 32;              // doubles per warp in s_warp
   constexpr int NW = THREADS / 32;
-  constexpr int ROW = 2 * O * P + O + 1;        // values per residual row
-  constexpr int ROWP = ROW | 1;                 // odd stride: lanes writing their own row hit distinct banks
+  constexpr WideLayout L = wide_layout(P, O, int(sizeof(CT)));
+  constexpr int LJ = L.LJ, LI = L.LI, TI = L.TI, PA = L.PA, PB = L.PB, ROW = L.ROW;
+  constexpr int VPE = 16 / int(sizeof(CT));     // elements per 16-byte shared-memory access
+  constexpr int NACC = TI * 4;
   constexpr bool kFp32Acc = (sizeof(CT) == 4);
   constexpr int FLUSH_GROUPS = 8;               // fp32 lane partials are folded into fp64 every 8*32 residuals
   constexpr int NSETS = 1 + 2 * P;
   constexpr int SETN = M::SETN;
+  constexpr int S1P = WideStage<M>::PARAMS;     // parameters >= S1P only feed the model's second stage
+  constexpr int NT = WideStage<M>::NT;
+  static_assert(LI * LJ <= 32 && LI * TI >= P && LJ * 4 >= P + 1, "wide_pass_kernel: lane grid does not cover J^T B");
 
   extern __shared__ __align__(16) unsigned char wide_smem[];
-  CT* s_tile = reinterpret_cast<CT*>(wide_smem);                       // [NW][32][ROWP]
-  CT* s_sets = s_tile + size_t(NW) * 32 * ROWP;                        // [NSETS][SETN]
+  CT* s_tile = reinterpret_cast<CT*>(wide_smem);                       // [NW][32][ROW]
+  CT* s_sets = s_tile + size_t(NW) * 32 * ROW;                         // [NSETS][SETN]
   CT* s_invh = s_sets + NSETS * SETN;                                  // [P]
   CT* s_cov = s_invh + P;                                              // [O*O]
-  unsigned char* s_idx = reinterpret_cast<unsigned char*>(s_cov + O * O);  // [NRAW][2] (i, j) of each packed entry
-  __shared__ double s_warp[NW * NCH * 32];
-  __shared__ double s_tot[NCH * 32];
+  __shared__ double s_warp[NW * STRIDE];
+  __shared__ double s_tot[STRIDE];
 
   const int jac = a.cost->jacobian;
   const bool central = (jac == MOPT_JAC_CENTRAL);
@@ -621,33 +694,24 @@ __global__ void __launch_bounds__(THREADS, 1) wide_pass_kernel(const PassArgs a)
   if (NUMERIC)
     for (int i = threadIdx.x; i < P; i += THREADS) s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
   for (int i = threadIdx.x; i < O * O; i += THREADS) s_cov[i] = CT(a.cost->cov[i]);
-  for (int e = threadIdx.x; e < NRAW; e += THREADS) {
-    int i = 0, j = 0;
-    if (e < P * (P + 1) / 2) {
-      int rem = e;
-      while (rem >= P - i) { rem -= P - i; ++i; }
-      j = i + rem;
-    } else if (e < NRAW - 1) {
-      i = e - P * (P + 1) / 2;
-    }
-    s_idx[2 * e] = (unsigned char)i;
-    s_idx[2 * e + 1] = (unsigned char)j;
-  }
+  for (int i = threadIdx.x; i < NW * STRIDE; i += THREADS) s_warp[i] = 0.0;
   const int loss = a.cost->loss;
   const CT lossp = CT(a.cost->loss_param);
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  CT* tile = s_tile + size_t(warp) * 32 * ROWP;
-  CT* my_row = tile + lane * ROWP;
+  const int ti = lane / LJ, tj = lane - ti * LJ;
+  const bool owner = lane < LI * LJ;            // lanes beyond the LI x LJ grid only take part in phase 1
+  CT* tile = s_tile + size_t(warp) * 32 * ROW;
+  CT* my_row = tile + lane * ROW;
   const ST* __restrict__ sp[NS];
 #pragma unroll
   for (int s = 0; s < NS; ++s) sp[s] = static_cast<const ST*>(a.streams.p[s]);
 
-  CT acc[NCH];
-  double dacc[NCH];
+  CT acc[NACC], acc_e2 = CT(0);
+  double dacc[NACC], dacc_e2 = 0.0;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) { acc[c] = CT(0); dacc[c] = 0.0; }
+  for (int c = 0; c < NACC; ++c) { acc[c] = CT(0); dacc[c] = 0.0; }
 
   // warps stride over groups of 32 consecutive residuals
   const int64_t ngroups = (a.n + 31) / 32;
@@ -661,93 +725,142 @@ __global__ void __launch_bounds__(THREADS, 1) wide_pass_kernel(const PassArgs a)
 #pragma unroll
     for (int s = 0; s < NS; ++s) e[s] = valid ? CT(sp[s][i]) : CT(0);
     CT r[O];
-    M::template residual<CT>(s_sets, e, r);
+    CT tmp[NT];
+    if constexpr (S1P < P) {
+      M::template stage1<CT>(s_sets, e, tmp);
+      M::template stage2<CT>(s_sets, e, tmp, r);
+    } else {
+      M::template residual<CT>(s_sets, e, r);
+    }
     CT e2 = CT(0);
 #pragma unroll
     for (int o = 0; o < O; ++o) e2 = fma(r[o], r[o], e2);
     CT w = valid ? loss_weight<CT>(loss, lossp, e2) : CT(0);
     if (!valid) e2 = CT(0);
-    if (mode == PASS_COST) {
-      CT s = e2;  // cost-only: the warp's 32 squared norms go to the lane that owns the `sum` entry
+    {
+      CT s = e2;  // the warp's 32 squared norms
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) s += shfl_xor(s, off);
-      if (lane == (NRAW - 1) % 32) acc[(NRAW - 1) / 32] += s;
-    } else {
-      CT J[O * P];
-      if constexpr (NUMERIC) {
+      acc_e2 += s;  // identical on every lane; lane 0's copy is the one reduced
+    }
+    if (mode != PASS_COST) {
+      CT rowA[O * PA], rowB[O * PB];
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-          CT rp[O];
-          M::template residual<CT>(s_sets + (1 + j) * SETN, e, rp);
-          if (central) {
-            CT rm[O];
-            M::template residual<CT>(s_sets + (1 + P + j) * SETN, e, rm);
+      for (int k = 0; k < O * PA; ++k) rowA[k] = CT(0);
 #pragma unroll
-            for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - rm[o]) * s_invh[j];
-          } else {
+      for (int k = 0; k < O * PB; ++k) rowB[k] = CT(0);
+      {
+        CT J[O * P];
+        if constexpr (NUMERIC) {
 #pragma unroll
-            for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - r[o]) * s_invh[j];
+          for (int j = 0; j < P; ++j) {
+            CT rp[O];
+            auto eval = [&](const CT* set, CT (&out)[O]) {
+              if constexpr (S1P < P) {
+                if (j >= S1P) M::template stage2<CT>(set, e, tmp, out);
+                else M::template residual<CT>(set, e, out);
+              } else {
+                M::template residual<CT>(set, e, out);
+              }
+            };
+            eval(s_sets + (1 + j) * SETN, rp);
+            if (central) {
+              CT rm[O];
+              eval(s_sets + (1 + P + j) * SETN, rm);
+#pragma unroll
+              for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - rm[o]) * s_invh[j];
+            } else {
+#pragma unroll
+              for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - r[o]) * s_invh[j];
+            }
+          }
+        } else {
+          CT ra[O];  // the model's f_df (computeHessian, linearization.h:144); r above is the same f value
+          M::template residual_jacobian<CT>(s_sets, e, ra, J);
+        }
+        // B = w C [J | r]   (C is the identity unless setCovariance was called; s_cov holds it)
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+          CT cr = CT(0);
+#pragma unroll
+          for (int k = 0; k < O; ++k) cr = fma(s_cov[o + k * O], r[k], cr);
+          rowB[o * PB + P] = valid ? w * cr : CT(0);
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            CT cj = CT(0);
+#pragma unroll
+            for (int k = 0; k < O; ++k) cj = fma(s_cov[o + k * O], J[k * P + p], cj);
+            rowA[o * PA + p] = valid ? J[o * P + p] : CT(0);
+            rowB[o * PB + p] = valid ? w * cj : CT(0);
           }
         }
-      } else {
-        CT ra[O];  // the model's f_df (computeHessian, linearization.h:144); r above is the same f value
-        M::template residual_jacobian<CT>(s_sets, e, ra, J);
       }
-      // row = [ J | w C J | w C r | e2 ]   (C is the identity unless setCovariance was called; s_cov holds it)
 #pragma unroll
-      for (int o = 0; o < O; ++o) {
-        CT cr = CT(0);
+      for (int k = 0; k < O * PA; k += VPE) sts16<CT>(my_row + k, rowA + k);
 #pragma unroll
-        for (int k = 0; k < O; ++k) cr = fma(s_cov[o + k * O], r[k], cr);
-        my_row[2 * O * P + o] = w * cr;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          CT cj = CT(0);
-#pragma unroll
-          for (int k = 0; k < O; ++k) cj = fma(s_cov[o + k * O], J[k * P + p], cj);
-          my_row[o * P + p] = J[o * P + p];
-          my_row[O * P + o * P + p] = w * cj;
-        }
-      }
-      my_row[2 * O * P + O] = e2;
+      for (int k = 0; k < O * PB; k += VPE) sts16<CT>(my_row + O * PA + k, rowB + k);
       __syncwarp();
-      // ---- 2. lane-owned packed entries sweep the 32 rows -------------------------------------------
+      // ---- 2. C += J^T B over the 32 rows, register-tiled over the LI x LJ lane grid ----------------
+      if (owner) {
+#pragma unroll 4
+        for (int row = 0; row < 32; ++row) {
+          const CT* rw = tile + row * ROW;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int k = c * 32 + lane;
-        if (k < NRAW) {
-          const int ii = s_idx[2 * k], jj = s_idx[2 * k + 1];
-          CT s = acc[c];
-          if (k < P * (P + 1) / 2) {
-            for (int row = 0; row < 32; ++row) {
-              const CT* rw = tile + row * ROWP;
+          for (int o = 0; o < O; ++o) {
+            CT av[TI], bv[4];
+            if constexpr (TI * sizeof(CT) == 8 && sizeof(CT) == 4) {
+              const float2 t2 = *reinterpret_cast<const float2*>(rw + o * PA + ti * TI);
+              av[0] = t2.x; av[1] = t2.y;
+            } else {
 #pragma unroll
-              for (int o = 0; o < O; ++o) s = fma(rw[o * P + ii], rw[O * P + o * P + jj], s);
+              for (int q = 0; q < TI; ++q) av[q] = rw[o * PA + ti * TI + q];
             }
-          } else if (k < NRAW - 1) {
-            for (int row = 0; row < 32; ++row) {
-              const CT* rw = tile + row * ROWP;
 #pragma unroll
-              for (int o = 0; o < O; ++o) s = fma(rw[o * P + ii], rw[2 * O * P + o], s);
+            for (int q = 0; q < 4; q += VPE) {
+              CT t[VPE];
+              lds16<CT>(rw + O * PA + o * PB + tj * 4 + q, t);
+#pragma unroll
+              for (int u = 0; u < VPE; ++u) bv[q + u] = t[u];
             }
-          } else {
-            for (int row = 0; row < 32; ++row) s += tile[row * ROWP + 2 * O * P + O];
+#pragma unroll
+            for (int q = 0; q < TI; ++q)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) acc[q * 4 + u] = fma(av[q], bv[u], acc[q * 4 + u]);
           }
-          acc[c] = s;
         }
       }
       __syncwarp();
     }
     if (kFp32Acc && ++since_flush >= FLUSH_GROUPS) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) { dacc[c] += double(acc[c]); acc[c] = CT(0); }
+      for (int c = 0; c < NACC; ++c) { dacc[c] += double(acc[c]); acc[c] = CT(0); }
+      dacc_e2 += double(acc_e2);
+      acc_e2 = CT(0);
       since_flush = 0;
     }
   }
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) dacc[c] += double(acc[c]);
+  for (int c = 0; c < NACC; ++c) dacc[c] += double(acc[c]);
+  dacc_e2 += double(acc_e2);
 
-  if (!grid_reduce<NRAW, 32, NCH, THREADS>(dacc, a, s_tot, s_warp)) return;
+  // scatter the lane-owned block of C into the packed layout (H upper row-major, b, sum) of this warp
+  double* mine = s_warp + warp * STRIDE;
+  if (owner) {
+#pragma unroll
+    for (int q = 0; q < TI; ++q) {
+      const int ii = ti * TI + q;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = tj * 4 + u;
+        if (ii < P && jj < P && ii <= jj) mine[tri_index(P, ii, jj)] = dacc[q * 4 + u];
+        else if (ii < P && jj == P) mine[P * (P + 1) / 2 + ii] = dacc[q * 4 + u];
+      }
+    }
+  }
+  if (lane == 0) mine[NRAW - 1] = dacc_e2;
+  __syncthreads();
+
+  if (!grid_reduce_shared<NRAW, STRIDE, THREADS>(a, s_tot, s_warp)) return;
   if (mode == PASS_COST) {
     if (threadIdx.x == 0) a.out->v[NRAW - 1] = a.accumulate ? a.out->v[NRAW - 1] + s_tot[NRAW - 1] : s_tot[NRAW - 1];
   } else {
@@ -758,9 +871,7 @@ __global__ void __launch_bounds__(THREADS, 1) wide_pass_kernel(const PassArgs a)
 
 template <class M, typename CT, int THREADS>
 constexpr size_t wide_smem_bytes() {
-  constexpr int ROWP = (2 * M::O * M::P + M::O + 1) | 1;
-  constexpr int NRAW = M::P * (M::P + 1) / 2 + M::P + 1;
-  return sizeof(CT) * (size_t(THREADS / 32) * 32 * ROWP + (1 + 2 * M::P) * M::SETN + M::P + M::O * M::O) + 2 * NRAW + 16;
+  return wide_smem_bytes_rt(M::P, M::O, M::SETN, int(sizeof(CT)), THREADS);
 }
 
 #endif  // __CUDACC__

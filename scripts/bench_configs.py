@@ -75,6 +75,52 @@ print(json.dumps({"case": "camera50M_lm_central_f64", "status": r.status, "iters
                   "x_err": float(np.max(np.abs(r.x - x_gt)))}), flush=True)
 st.close()
 
+# ---- the n x n calibration case: pinhole + distortion, P = 15 (BASELINE configs[4]) -----------------------
+x15 = np.concatenate([x_gt, [600.0, 600.0, 320.0, 240.0, 0.05, -0.02, 0.001, -0.001, 0.005]])
+C44 = consts[12:]
+st = capi.Store(ctx, capi.MODEL_PINHOLE_DISTORT, n, capi.F32)
+st.generate(seed=3, gt=x15, lo=(2.0, -1.0, -0.5), hi=(5.0, 1.0, 1.0), noise_sigma=0.5, consts=C44)
+for jac, jn in ((capi.JAC_CENTRAL, "central"), (capi.JAC_FORWARD, "forward")):
+    for cd, cn in ((capi.F32, "f32"), (capi.F64, "f64")):
+        prob = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, jac, cd, consts=C44)
+        report(f"camera15_50M_{jn}_{cn}", n, 20, time_pass(st, prob, x15 * 0.999, steps=5, warm=3))
+x0 = x15.copy()
+x0[:6] = 0.0
+x0[6:10] *= 1.02
+x0[10:] = 0.0
+prob = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL, capi.F64, consts=C44)
+r, dt = lm_time([st], [prob], x0, max_iterations=50)
+print(json.dumps({"case": "camera15_50M_lm_central_f64", "status": r.status, "iters": r.executed_iterations,
+                  "passes": r.num_passes, "seconds": dt, "lm_iters_per_s": r.executed_iterations / dt,
+                  "x_err_extrinsics": float(np.max(np.abs(r.x[:6] - x15[:6]))),
+                  "x_err_focal_rel": float(np.max(np.abs(r.x[6:8] / x15[6:8] - 1.0)))}), flush=True)
+st.close()
+
+# ---- a user model compiled at run time (NVRTC) next to the builtin it restates --------------------------
+n = 10_000_000
+SRC = """
+template <typename T> __device__ void mopt_f(const T* s, const T* a, const T* b, T* r) { r[0] = b[0] - exp(fma(s[0], a[0], s[1])); }
+template <typename T> __device__ void mopt_f_df(const T* s, const T* a, const T* b, T* r, T* J) {
+  const T ex = exp(fma(s[0], a[0], s[1])); r[0] = b[0] - ex; J[0] = -a[0] * ex; J[1] = -ex; }
+"""
+t0 = time.perf_counter()
+um = capi.UserModel(SRC, 2, 1, 1, 1, has_jacobian=True)
+t_compile = time.perf_counter() - t0
+bst = capi.Store(ctx, capi.MODEL_EXP_CURVE, n, capi.F32)
+bst.generate(seed=1, gt=[0.3, 0.1], lo=(0, 0, 0), hi=(5, 0, 0), n_total=n, noise_sigma=0.2)
+ust = capi.Store(ctx, um.model, n, capi.F32)
+ust.upload(0, bst.download(0, np.float32))
+ust.upload(1, bst.download(1, np.float32))
+for jac, jn in ((capi.JAC_CENTRAL, "central"), (capi.JAC_ANALYTICAL, "analytical")):
+    t0 = time.perf_counter()
+    ctx.linearize(ust, capi.make_problem(um.model, jac, capi.F32), [0.25, 0.15])
+    t_first = time.perf_counter() - t0
+    mb = time_pass(bst, capi.make_problem(capi.MODEL_EXP_CURVE, jac, capi.F32), [0.25, 0.15])
+    mu = time_pass(ust, capi.make_problem(um.model, jac, capi.F32), [0.25, 0.15])
+    report(f"user_curve10M_{jn}_f32", n, 8, mu, {"builtin_ms_per_pass": mb, "first_call_s_incl_nvrtc": t_first,
+                                                 "initial_compile_s": t_compile})
+bst.close(); ust.close()
+
 # ---- point2point variants ------------------------------------------------------------------------
 n = 100_000_000
 X_GT = [0.5, -0.3, 0.2, 0.10, -0.05, 0.08]
@@ -84,6 +130,10 @@ for jac, jn in ((capi.JAC_ANALYTICAL, "analytical"), (capi.JAC_FORWARD, "forward
     for cd, cn in ((capi.F32, "f32"), (capi.F64, "f64")):
         prob = capi.make_problem(capi.MODEL_POINT2POINT, jac, cd, loss=capi.LOSS_HUBER, loss_param=0.05)
         report(f"p2p100M_f32store_{jn}_{cn}", n, 24, time_pass(st, prob, [0.0] * 6, steps=10, warm=10))
+        if jac != capi.JAC_ANALYTICAL:  # per-residual difference quotient instead of the moment kernel
+            prob = capi.make_problem(capi.MODEL_POINT2POINT, jac, cd, loss=capi.LOSS_HUBER, loss_param=0.05,
+                                     flags=capi.FLAG_GENERIC_KERNEL)
+            report(f"p2p100M_f32store_{jn}_{cn}_generic_kernel", n, 24, time_pass(st, prob, [0.0] * 6, steps=10, warm=10))
 st.close()
 n = 50_000_000
 st = capi.Store(ctx, capi.MODEL_POINT2POINT, n, capi.F64)
