@@ -174,6 +174,17 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
   return r;
 }
 
+// 16-byte shared-memory load that the compiler may neither hoist out of a loop nor merge with an earlier one:
+// used to RE-READ loop-invariant parameter sets per use instead of keeping them live in (spilled) registers.
+__device__ __forceinline__ void lds16_reload(const float* p, float (&v)[4]) {
+  const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(p));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void lds16_reload(const double* p, double (&v)[2]) {
+  const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(p));
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
+}
+
 // TMA bulk prefetch of `bytes` (multiple of 16, 16-byte aligned source) into L2.
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");

@@ -406,18 +406,24 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
   constexpr bool kFp32Acc = (sizeof(CT) == 4);
   constexpr int FLUSH_ROUNDS = 8;
   constexpr int NSETS = 1 + 2 * (P > 0 ? P : 0);
-  constexpr int SETN = M::SETN > 0 ? M::SETN : 1;
+  constexpr int VPE = 16 / int(sizeof(CT));                       // elements per 16-byte shared-memory access
+  constexpr int SETN = ((M::SETN > 0 ? M::SETN : 1) + VPE - 1) / VPE * VPE;  // sets padded to 16-byte units
+  // Finite differences of the larger models (1 + 2P sets of SETN values, e.g. 13 x 12 for the pinhole camera) do not
+  // fit in registers next to J and the accumulators; left alone the compiler hoists them all out of the streaming
+  // loop and spills them to local memory.  They are re-read from shared memory with 16-byte loads at every use.
+  constexpr bool kReloadSets = NUMERIC && (NSETS * SETN > 32);
 
   __shared__ double s_warp[(THREADS / 32) * V];
   __shared__ double s_tot[V];
-  __shared__ CT s_sets[NSETS][SETN];
+  __shared__ __align__(16) CT s_sets[NSETS][SETN];
   __shared__ CT s_invh[P > 0 ? P : 1];
   __shared__ CT s_cov[O * O];
 
   const int jac = a.cost->jacobian;
   const bool central = (jac == MOPT_JAC_CENTRAL);
   const int nsets = !NUMERIC ? 1 : (central ? 1 + 2 * P : 1 + P);
-  for (int i = threadIdx.x; i < nsets * SETN; i += THREADS) s_sets[i / SETN][i % SETN] = CT(a.pb->sets[i / SETN][i % SETN]);
+  for (int i = threadIdx.x; i < nsets * SETN; i += THREADS)
+    s_sets[i / SETN][i % SETN] = (i % SETN < M::SETN) ? CT(a.pb->sets[i / SETN][i % SETN]) : CT(0);
   for (int i = threadIdx.x; i < P; i += THREADS)
     s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
   const bool has_cov = a.cost->has_cov != 0;
@@ -461,13 +467,28 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
     CT J[O * (P > 0 ? P : 1)];
     if (NUMERIC) {
       M::template residual<CT>(s_sets[0], e, r);
+      auto eval = [&](int idx, CT (&out)[O]) {
+        if constexpr (kReloadSets) {
+          CT sr[SETN];
+#pragma unroll
+          for (int k = 0; k < SETN; k += VPE) {
+            CT t[VPE];
+            lds16_reload(&s_sets[idx][k], t);
+#pragma unroll
+            for (int u = 0; u < VPE; ++u) sr[k + u] = t[u];
+          }
+          M::template residual<CT>(sr, e, out);
+        } else {
+          M::template residual<CT>(s_sets[idx], e, out);
+        }
+      };
 #pragma unroll
       for (int j = 0; j < P; ++j) {
         CT rp[O];
-        M::template residual<CT>(s_sets[1 + j], e, rp);  // perturbed f's bool is ignored, linearization.h:104
+        eval(1 + j, rp);  // perturbed f's bool is ignored, linearization.h:104
         if (central) {
           CT rm[O];
-          M::template residual<CT>(s_sets[1 + P + j], e, rm);
+          eval(1 + P + j, rm);
 #pragma unroll
           for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - rm[o]) * s_invh[j];
         } else {
@@ -618,8 +639,12 @@ __host__ __device__ constexpr WideLayout wide_layout(int P, int O, int elem_byte
   if (((row / vpe) & 1) == 0) row += vpe;     // odd number of 16-byte units per row
   return WideLayout{LJ, LI, TI, PA, PB, row};
 }
+__host__ __device__ constexpr int wide_set_stride(int setn, int elem_bytes) {  // parameter sets padded to 16-byte units
+  return ((setn + 16 / elem_bytes - 1) / (16 / elem_bytes)) * (16 / elem_bytes);
+}
 __host__ __device__ constexpr size_t wide_smem_bytes_rt(int P, int O, int setn, int elem_bytes, int threads) {
-  return size_t(elem_bytes) * (size_t(threads / 32) * 32 * wide_layout(P, O, elem_bytes).ROW + size_t(1 + 2 * P) * setn + P + O * O) + 16;
+  return size_t(elem_bytes) * (size_t(threads / 32) * 32 * wide_layout(P, O, elem_bytes).ROW +
+                               size_t(1 + 2 * P) * wide_set_stride(setn, elem_bytes) + P + O * O) + 16;
 }
 
 #ifdef __CUDACC__
@@ -674,7 +699,7 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
   constexpr bool kFp32Acc = (sizeof(CT) == 4);
   constexpr int FLUSH_GROUPS = 8;               // fp32 lane partials are folded into fp64 every 8*32 residuals
   constexpr int NSETS = 1 + 2 * P;
-  constexpr int SETN = M::SETN;
+  constexpr int SETN = wide_set_stride(M::SETN, int(sizeof(CT)));  // padded: a set is read with 16-byte loads
   constexpr int S1P = WideStage<M>::PARAMS;     // parameters >= S1P only feed the model's second stage
   constexpr int NT = WideStage<M>::NT;
   static_assert(LI * LJ <= 32 && LI * TI >= P && LJ * 4 >= P + 1, "wide_pass_kernel: lane grid does not cover J^T B");
@@ -690,11 +715,13 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
   const int jac = a.cost->jacobian;
   const bool central = (jac == MOPT_JAC_CENTRAL);
   const int nsets = !NUMERIC ? 1 : (central ? 1 + 2 * P : 1 + P);
-  for (int i = threadIdx.x; i < nsets * SETN; i += THREADS) s_sets[i] = CT(a.pb->sets[i / SETN][i % SETN]);
+  for (int i = threadIdx.x; i < nsets * SETN; i += THREADS)
+    s_sets[i] = (i % SETN < M::SETN) ? CT(a.pb->sets[i / SETN][i % SETN]) : CT(0);
   if (NUMERIC)
     for (int i = threadIdx.x; i < P; i += THREADS) s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
   for (int i = threadIdx.x; i < O * O; i += THREADS) s_cov[i] = CT(a.cost->cov[i]);
   for (int i = threadIdx.x; i < NW * STRIDE; i += THREADS) s_warp[i] = 0.0;
+  const bool has_cov = a.cost->has_cov != 0;
   const int loss = a.cost->loss;
   const CT lossp = CT(a.cost->loss_param);
   __syncthreads();
@@ -726,11 +753,26 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
     for (int s = 0; s < NS; ++s) e[s] = valid ? CT(sp[s][i]) : CT(0);
     CT r[O];
     CT tmp[NT];
-    if constexpr (S1P < P) {
-      M::template stage1<CT>(s_sets, e, tmp);
-      M::template stage2<CT>(s_sets, e, tmp, r);
-    } else {
-      M::template residual<CT>(s_sets, e, r);
+    // a parameter set travels shared memory -> registers in 16-byte loads (loads of values the inlined model
+    // does not read are dropped by the compiler)
+    auto load_set = [&](int idx, CT (&sr)[SETN]) {
+#pragma unroll
+      for (int k = 0; k < SETN; k += VPE) {
+        CT t[VPE];
+        lds16<CT>(s_sets + idx * SETN + k, t);
+#pragma unroll
+        for (int u = 0; u < VPE; ++u) sr[k + u] = t[u];
+      }
+    };
+    {
+      CT sr[SETN];
+      load_set(0, sr);
+      if constexpr (S1P < P) {
+        M::template stage1<CT>(sr, e, tmp);
+        M::template stage2<CT>(sr, e, tmp, r);
+      } else {
+        M::template residual<CT>(sr, e, r);
+      }
     }
     CT e2 = CT(0);
 #pragma unroll
@@ -755,18 +797,20 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
 #pragma unroll
           for (int j = 0; j < P; ++j) {
             CT rp[O];
-            auto eval = [&](const CT* set, CT (&out)[O]) {
+            auto eval = [&](int idx, CT (&out)[O]) {
+              CT sr[SETN];
+              load_set(idx, sr);
               if constexpr (S1P < P) {
-                if (j >= S1P) M::template stage2<CT>(set, e, tmp, out);
-                else M::template residual<CT>(set, e, out);
+                if (j >= S1P) M::template stage2<CT>(sr, e, tmp, out);
+                else M::template residual<CT>(sr, e, out);
               } else {
-                M::template residual<CT>(set, e, out);
+                M::template residual<CT>(sr, e, out);
               }
             };
-            eval(s_sets + (1 + j) * SETN, rp);
+            eval(1 + j, rp);
             if (central) {
               CT rm[O];
-              eval(s_sets + (1 + P + j) * SETN, rm);
+              eval(1 + P + j, rm);
 #pragma unroll
               for (int o = 0; o < O; ++o) J[o * P + j] = (rp[o] - rm[o]) * s_invh[j];
             } else {
@@ -776,23 +820,43 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
           }
         } else {
           CT ra[O];  // the model's f_df (computeHessian, linearization.h:144); r above is the same f value
-          M::template residual_jacobian<CT>(s_sets, e, ra, J);
+          CT sr[SETN];
+          load_set(0, sr);
+          M::template residual_jacobian<CT>(sr, e, ra, J);
         }
         // B = w C [J | r]   (C is the identity unless setCovariance was called; s_cov holds it)
+        if (has_cov) {
 #pragma unroll
-        for (int o = 0; o < O; ++o) {
-          CT cr = CT(0);
+          for (int o = 0; o < O; ++o) {
+            CT cr = CT(0);
 #pragma unroll
-          for (int k = 0; k < O; ++k) cr = fma(s_cov[o + k * O], r[k], cr);
-          rowB[o * PB + P] = valid ? w * cr : CT(0);
+            for (int k = 0; k < O; ++k) cr = fma(s_cov[o + k * O], r[k], cr);
+            rowB[o * PB + P] = w * cr;
 #pragma unroll
-          for (int p = 0; p < P; ++p) {
-            CT cj = CT(0);
+            for (int p = 0; p < P; ++p) {
+              CT cj = CT(0);
 #pragma unroll
-            for (int k = 0; k < O; ++k) cj = fma(s_cov[o + k * O], J[k * P + p], cj);
-            rowA[o * PA + p] = valid ? J[o * P + p] : CT(0);
-            rowB[o * PB + p] = valid ? w * cj : CT(0);
+              for (int k = 0; k < O; ++k) cj = fma(s_cov[o + k * O], J[k * P + p], cj);
+              rowA[o * PA + p] = J[o * P + p];
+              rowB[o * PB + p] = w * cj;
+            }
           }
+        } else {
+#pragma unroll
+          for (int o = 0; o < O; ++o) {
+            rowB[o * PB + P] = w * r[o];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              rowA[o * PA + p] = J[o * P + p];
+              rowB[o * PB + p] = w * J[o * P + p];
+            }
+          }
+        }
+        if (!valid) {  // past the end of the store (last group only): an all-zero row
+#pragma unroll
+          for (int k = 0; k < O * PA; ++k) rowA[k] = CT(0);
+#pragma unroll
+          for (int k = 0; k < O * PB; ++k) rowB[k] = CT(0);
         }
       }
 #pragma unroll
