@@ -389,7 +389,8 @@ def run_ours(args):
                          "kernel": "p2p_moment_kernel<float,float,HUBER,QROT>",
                          "algorithmic_bytes_per_launch": BYTES_PER_RES * n},
             "clocks": sampler.summary(),
-            "gpu_launches": 2 * args.steps,
+            # per step: setup kernel + pass kernel (+ the one-warp exchange consumer, or NCCL's kernel, when N > 1)
+            "gpu_launches": (2 + (1 if world > 1 else 0)) * args.steps,
             "check": {"sum_rtr": s, "H00": float(H[0, 0]), "b0": float(b[0])},
         }
         if local_ms is not None:

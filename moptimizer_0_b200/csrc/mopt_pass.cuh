@@ -617,27 +617,28 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
 //   1. every lane evaluates ONE residual and its Jacobian (finite differences or the model's f_df) and
 //      stores the row  [ J (O x PA) | B = w C [J | r] (O x PB) ]  into the warp's shared tile with 16-byte
 //      stores (row stride an odd number of 16-byte units: conflict-free);
-//   2. the warp computes  C += J^T B  over the 32 rows as a register-tiled product: lane (ti, tj) of an
-//      LI x LJ lane grid owns the TI x 4 block C[ti TI.., 4 tj..] and reads TI values of J and one 16-byte
-//      vector of B per (row, output): 8 FMA per 2 shared loads for P = 15.  Columns 0..P-1 of C are H
-//      (the upper triangle is kept), column P is b.
+//   2. the warp computes  C += J^T B  over the 32 rows as a register-tiled product over the 4x4 tiles on or
+//      above the block diagonal (10 tiles for P = 15; columns 0..P-1 of C are H, column P is b): lane
+//      (group g, tile t) accumulates tile t over rows g, g + NG, ... with two 16-byte shared loads per
+//      16 FMAs; the NG row groups of a tile are merged in a fixed order at the end.
 // Models may split their residual into a stage that depends only on the first STAGE1_PARAMS parameters
 // (e.g. the rigid transform + perspective division) and a cheap second stage; perturbations of the
 // remaining parameters then re-run only the second stage (bit-identical to the full evaluation).
 // =============================================================================================
 struct WideLayout {
-  int LJ, LI, TI, PA, PB, ROW;  // ROW in elements
+  int NBI, NBJ, NT, NG, PA, PB, ROW;  // ROW in elements
 };
 __host__ __device__ constexpr WideLayout wide_layout(int P, int O, int elem_bytes) {
   const int vpe = 16 / elem_bytes;            // elements per 16-byte unit
-  const int LJ = (P + 1 + 3) / 4;             // lanes across the columns of B (4 columns each)
-  const int LI = 32 / LJ;                     // lanes down the rows of J^T
-  const int TI = (P + LI - 1) / LI;           // rows of J^T per lane
-  const int PA = ((LI * TI + vpe - 1) / vpe) * vpe;
-  const int PB = LJ * 4;
+  const int NBI = (P + 3) / 4;                // 4-row blocks of J^T
+  const int NBJ = (P + 1 + 3) / 4;            // 4-column blocks of B = [w C J | w C r]
+  int NT = 0;                                 // 4x4 tiles on or above the block diagonal (the b column lives in the last block column)
+  for (int bi = 0; bi < NBI; ++bi) NT += NBJ - bi;
+  const int NG = 32 / NT;                     // row groups: lane = group * NT + tile, group g takes rows g, g + NG, ...
+  const int PA = NBI * 4, PB = NBJ * 4;
   int row = O * PA + O * PB;                  // multiple of vpe
-  if (((row / vpe) & 1) == 0) row += vpe;     // odd number of 16-byte units per row
-  return WideLayout{LJ, LI, TI, PA, PB, row};
+  if (((row / vpe) & 1) == 0) row += vpe;     // odd number of 16-byte units per row: conflict-free 16-byte row stores
+  return WideLayout{NBI, NBJ, NT, NG, PA, PB, row};
 }
 __host__ __device__ constexpr int wide_set_stride(int setn, int elem_bytes) {  // parameter sets padded to 16-byte units
   return ((setn + 16 / elem_bytes - 1) / (16 / elem_bytes)) * (16 / elem_bytes);
@@ -693,16 +694,16 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
   constexpr int STRIDE = NCH * 32;              // doubles per warp in s_warp
   constexpr int NW = THREADS / 32;
   constexpr WideLayout L = wide_layout(P, O, int(sizeof(CT)));
-  constexpr int LJ = L.LJ, LI = L.LI, TI = L.TI, PA = L.PA, PB = L.PB, ROW = L.ROW;
+  constexpr int NBJ = L.NBJ, NT = L.NT, NG = L.NG, PA = L.PA, PB = L.PB, ROW = L.ROW;
   constexpr int VPE = 16 / int(sizeof(CT));     // elements per 16-byte shared-memory access
-  constexpr int NACC = TI * 4;
+  constexpr int NACC = 16;
   constexpr bool kFp32Acc = (sizeof(CT) == 4);
   constexpr int FLUSH_GROUPS = 8;               // fp32 lane partials are folded into fp64 every 8*32 residuals
   constexpr int NSETS = 1 + 2 * P;
   constexpr int SETN = wide_set_stride(M::SETN, int(sizeof(CT)));  // padded: a set is read with 16-byte loads
   constexpr int S1P = WideStage<M>::PARAMS;     // parameters >= S1P only feed the model's second stage
-  constexpr int NT = WideStage<M>::NT;
-  static_assert(LI * LJ <= 32 && LI * TI >= P && LJ * 4 >= P + 1, "wide_pass_kernel: lane grid does not cover J^T B");
+  constexpr int NTMP = WideStage<M>::NT;        // values the first stage hands to the second
+  static_assert(NT >= 1 && NT <= 32 && NG >= 1, "wide_pass_kernel: more than 32 tiles of J^T B");
 
   extern __shared__ __align__(16) unsigned char wide_smem[];
   CT* s_tile = reinterpret_cast<CT*>(wide_smem);                       // [NW][32][ROW]
@@ -727,8 +728,14 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ti = lane / LJ, tj = lane - ti * LJ;
-  const bool owner = lane < LI * LJ;            // lanes beyond the LI x LJ grid only take part in phase 1
+  const bool owner = lane < NT * NG;            // lanes beyond the tile x group grid only take part in phase 1
+  const int grp = lane / NT;
+  int bi = 0, bj = 0;                           // this lane's tile: block row bi, block column bj >= bi
+  {
+    int t = lane - grp * NT;
+    while (t >= NBJ - bi) { t -= NBJ - bi; ++bi; }
+    bj = bi + t;
+  }
   CT* tile = s_tile + size_t(warp) * 32 * ROW;
   CT* my_row = tile + lane * ROW;
   const ST* __restrict__ sp[NS];
@@ -752,7 +759,7 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
 #pragma unroll
     for (int s = 0; s < NS; ++s) e[s] = valid ? CT(sp[s][i]) : CT(0);
     CT r[O];
-    CT tmp[NT];
+    CT tmp[NTMP];
     // a parameter set travels shared memory -> registers in 16-byte loads (loads of values the inlined model
     // does not read are dropped by the compiler)
     auto load_set = [&](int idx, CT (&sr)[SETN]) {
@@ -866,28 +873,24 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
       __syncwarp();
       // ---- 2. C += J^T B over the 32 rows, register-tiled over the LI x LJ lane grid ----------------
       if (owner) {
-#pragma unroll 4
-        for (int row = 0; row < 32; ++row) {
+#pragma unroll 2
+        for (int row = grp; row < 32; row += NG) {
           const CT* rw = tile + row * ROW;
 #pragma unroll
           for (int o = 0; o < O; ++o) {
-            CT av[TI], bv[4];
-            if constexpr (TI * sizeof(CT) == 8 && sizeof(CT) == 4) {
-              const float2 t2 = *reinterpret_cast<const float2*>(rw + o * PA + ti * TI);
-              av[0] = t2.x; av[1] = t2.y;
-            } else {
-#pragma unroll
-              for (int q = 0; q < TI; ++q) av[q] = rw[o * PA + ti * TI + q];
-            }
+            CT av[4], bv[4];
 #pragma unroll
             for (int q = 0; q < 4; q += VPE) {
               CT t[VPE];
-              lds16<CT>(rw + O * PA + o * PB + tj * 4 + q, t);
+              lds16<CT>(rw + o * PA + bi * 4 + q, t);
+#pragma unroll
+              for (int u = 0; u < VPE; ++u) av[q + u] = t[u];
+              lds16<CT>(rw + O * PA + o * PB + bj * 4 + q, t);
 #pragma unroll
               for (int u = 0; u < VPE; ++u) bv[q + u] = t[u];
             }
 #pragma unroll
-            for (int q = 0; q < TI; ++q)
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
               for (int u = 0; u < 4; ++u) acc[q * 4 + u] = fma(av[q], bv[u], acc[q * 4 + u]);
           }
@@ -907,19 +910,23 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
   for (int c = 0; c < NACC; ++c) dacc[c] += double(acc[c]);
   dacc_e2 += double(acc_e2);
 
-  // scatter the lane-owned block of C into the packed layout (H upper row-major, b, sum) of this warp
+  // merge the row groups of every tile, in group order, into the packed layout (H upper row-major, b, sum) of
+  // this warp (s_warp was zeroed at kernel start)
   double* mine = s_warp + warp * STRIDE;
-  if (owner) {
+  for (int g = 0; g < NG; ++g) {
+    if (owner && grp == g) {
 #pragma unroll
-    for (int q = 0; q < TI; ++q) {
-      const int ii = ti * TI + q;
+      for (int q = 0; q < 4; ++q) {
+        const int ii = bi * 4 + q;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int jj = tj * 4 + u;
-        if (ii < P && jj < P && ii <= jj) mine[tri_index(P, ii, jj)] = dacc[q * 4 + u];
-        else if (ii < P && jj == P) mine[P * (P + 1) / 2 + ii] = dacc[q * 4 + u];
+        for (int u = 0; u < 4; ++u) {
+          const int jj = bj * 4 + u;
+          if (ii < P && jj < P && ii <= jj) mine[tri_index(P, ii, jj)] += dacc[q * 4 + u];
+          else if (ii < P && jj == P) mine[P * (P + 1) / 2 + ii] += dacc[q * 4 + u];
+        }
       }
     }
+    __syncwarp();
   }
   if (lane == 0) mine[NRAW - 1] = dacc_e2;
   __syncthreads();

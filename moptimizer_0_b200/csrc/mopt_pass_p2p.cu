@@ -25,8 +25,11 @@ struct ShapeF32 {
 struct ShapeF32Small {  // 2 CTAs/SM x 256 threads, 2 rounds in flight; selectable with mopt_ctx_set_launch(.., 256)
   static constexpr int THREADS = 256, MINB = 2, UNROLL = 2, FLUSH = 16;
 };
+// fp64 compute (the reference's default Scalar): capped at 128 registers so two CTAs stay resident — 16 warps hide the
+// DFMA latency that 8 could not.  f32 store 873 -> 622 us per 100 M, f64 store 553 -> 380 us per 50 M (6.3 TB/s)
+// (profiles/r1_tune_p2p_f64.txt).
 struct ShapeF64 {
-  static constexpr int THREADS = 256, MINB = 1, UNROLL = 2, FLUSH = 8;
+  static constexpr int THREADS = 256, MINB = 2, UNROLL = 2, FLUSH = 8;
 };
 
 template <typename ST, typename CT, int LOSS, bool QROT, class S>

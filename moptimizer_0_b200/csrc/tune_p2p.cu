@@ -123,6 +123,35 @@ void run_variant(Env& E, int ctas_per_sm, int mode = PASS_LINEARIZE) {
   std::fflush(stdout);
 }
 
+// fp64-compute variants (the reference's default Scalar is double): ST = float or double streams
+template <typename ST, int THREADS, int MINB, int UNROLL, int FLUSH>
+void run_variant64(Env& E, const PassArgs& a64, int ctas_per_sm) {
+  auto kern = p2p_moment_kernel<ST, double, MOPT_LOSS_HUBER, true, THREADS, MINB, UNROLL, FLUSH, 0, false>;
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  const int per_sm = std::min(occ, ctas_per_sm);
+  if (per_sm < ctas_per_sm) {
+    std::printf("moment64 store=%s threads=%3d minb=%d unroll=%d: only %d CTAs/SM reachable (regs=%d), skipped\n",
+                sizeof(ST) == 4 ? "f32" : "f64", THREADS, MINB, UNROLL, occ, fa.numRegs);
+    return;
+  }
+  const int grid = per_sm * E.num_sms;
+  PassArgs a = a64;
+  a.mode_override = PASS_LINEARIZE;
+  const float ms = time_launch(E, [&] { kern<<<grid, THREADS, 0, E.stream>>>(a); });
+  const double bytes = 6.0 * sizeof(ST) * double(a.n);
+  std::printf("moment64 store=%s threads=%3d minb=%d unroll=%d ctas/sm=%d regs=%3d local=%zu occ=%d  %8.1f us  %7.1f GB/s  %6.1f Gres/s\n",
+              sizeof(ST) == 4 ? "f32" : "f64", THREADS, MINB, UNROLL, per_sm, fa.numRegs, (size_t)fa.localSizeBytes, occ, ms * 1e3,
+              bytes / (ms * 1e-3) / 1e9, double(a.n) / (ms * 1e-3) / 1e9);
+  std::fflush(stdout);
+}
+
+__global__ void widen_kernel(const float* in, double* out, int64_t n) {
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) out[i] = double(in[i]);
+}
+
 template <int THREADS, int UNROLL>
 void run_ceiling(Env& E, int ctas_per_sm) {
   auto kern = read_sum_kernel<THREADS, UNROLL>;
@@ -176,6 +205,43 @@ int main(int argc, char** argv) {
   CK(cudaStreamSynchronize(E.stream));
   std::printf("%s, %d SMs, n = %lld, data = %s\n", prop.name, E.num_sms, (long long)n, argc > 2 ? argv[2] : "random");
 
+  if (argc > 2 && std::string(argv[2]) == "f64") {  // fp64-compute launch shapes
+    make_targets_kernel<<<148 * 8, 256, 0, E.stream>>>((const float*)E.a.streams.p[0], (const float*)E.a.streams.p[1],
+                                                       (const float*)E.a.streams.p[2], (float*)E.a.streams.p[3],
+                                                       (float*)E.a.streams.p[4], (float*)E.a.streams.p[5], n);
+    CK(cudaStreamSynchronize(E.stream));
+    PassArgs af = E.a;
+    for (int rep = 0; rep < 2; ++rep) {
+      run_variant64<float, 256, 1, 2, 8>(E, af, 1);  // shipped
+      run_variant64<float, 256, 1, 1, 8>(E, af, 1);
+      run_variant64<float, 256, 2, 1, 8>(E, af, 2);
+      run_variant64<float, 256, 2, 2, 8>(E, af, 2);
+      run_variant64<float, 512, 1, 1, 8>(E, af, 1);
+      run_variant64<float, 128, 4, 1, 8>(E, af, 4);
+      run_variant64<float, 256, 3, 1, 8>(E, af, 3);
+      run_variant64<float, 1024, 1, 1, 8>(E, af, 1);
+    }
+    // fp64 store: half as many elements so the six double streams fit next to the float ones
+    PassArgs ad = E.a;
+    ad.n = n / 2;
+    for (int k = 0; k < 6; ++k) {
+      double* p;
+      CK(cudaMalloc(&p, size_t(ad.n) * 8 + 512));
+      widen_kernel<<<148 * 8, 256, 0, E.stream>>>((const float*)E.a.streams.p[k], p, ad.n);
+      ad.streams.p[k] = p;
+    }
+    CK(cudaStreamSynchronize(E.stream));
+    for (int rep = 0; rep < 2; ++rep) {
+      run_variant64<double, 256, 1, 2, 8>(E, ad, 1);  // shipped
+      run_variant64<double, 256, 1, 1, 8>(E, ad, 1);
+      run_variant64<double, 256, 2, 1, 8>(E, ad, 2);
+      run_variant64<double, 256, 2, 2, 8>(E, ad, 2);
+      run_variant64<double, 512, 1, 1, 8>(E, ad, 1);
+      run_variant64<double, 128, 4, 1, 8>(E, ad, 4);
+      run_variant64<double, 256, 3, 1, 8>(E, ad, 3);
+    }
+    return 0;
+  }
   if (argc > 3) {  // sustained-clock experiment: long pre-warm, then the variants that separate ALU from HBM limits
     auto kern = p2p_moment_kernel<float, float, MOPT_LOSS_HUBER, true, 1024, 1, 1, 16>;
     PassArgs a = E.a;
