@@ -37,7 +37,9 @@ int launch_one(const PassLaunch& L, const PassArgs& a) {
   // registers, one 256-thread CTA per SM, issue slots 34 % busy).  Capping them at 80 registers (3 CTAs per SM)
   // turns the hoisted sets into L1-resident local loads and triples the warps that hide the division / MUFU
   // latency: camera 50 M central 2.55 -> 1.37 ms, forward 2.12 -> 0.96 ms (profiles/r1_tune_dense.txt).
-  constexpr int kMinB = (NUMERIC && M::P >= 4) ? (sizeof(CT) == 4 ? 3 : 2) : 1;
+  // fp64 compute: 2 CTAs/SM (128 registers) pays off while the Jacobian is small (camera O x P = 12: 3.88 -> 2.82 ms);
+  // with the 3 x 6 point2point Jacobian in doubles the cap spills 400 bytes and loses (3.4 -> 4.6 ms), so that stays at 1.
+  constexpr int kMinB = (NUMERIC && M::P >= 4) ? (sizeof(CT) == 4 ? 3 : (M::O * M::P <= 12 ? 2 : 1)) : 1;
   return launch_shape<M, ST, CT, NUMERIC, kThreads, kMinB>(L, a);
 }
 
