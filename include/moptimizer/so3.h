@@ -1,5 +1,7 @@
-// Mirrors the on-path part of include/moptimizer/so3.h + src/so3.cpp:7-19,43-57 with raw-array signatures
-// (row-major), no Eigen.  The device copies used by the kernels live in csrc/mopt_setup.cuh.
+// Mirrors include/moptimizer/so3.h + src/so3.cpp with raw-array signatures (3x3 / 4x4 row-major), no Eigen.
+// convert6DOFParameterToMatrix and Exp are on the hot path (the device copies the kernels use live in
+// csrc/mopt_setup.cuh); the rest of src/so3.cpp:21-155 is the kept API surface around the manifold update, restated
+// with the reference's own thresholds and formulas — including its first-order right/left Jacobians.
 #pragma once
 
 #include <cmath>
@@ -36,6 +38,110 @@ inline void convert6DOFParameterToMatrix(const Scalar* x, Scalar* T16) {
   }
   T16[12] = T16[13] = T16[14] = Scalar(0);
   T16[15] = Scalar(1);
+}
+
+/// x = omega(3) -> 4x4 homogeneous transform with zero translation (src/so3.cpp:21-31).
+template <typename Scalar>
+inline void convert3DOFParameterToMatrix(const Scalar* x, Scalar* T16) {
+  Scalar R[9];
+  Exp<Scalar>(x, R);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) T16[r * 4 + c] = R[r * 3 + c];
+    T16[r * 4 + 3] = Scalar(0);
+  }
+  T16[12] = T16[13] = T16[14] = Scalar(0);
+  T16[15] = Scalar(1);
+}
+
+/// x = omega(3) -> 3x3 rotation (src/so3.cpp:33-40).
+template <typename Scalar>
+inline void convert3DOFParameterToMatrix3(const Scalar* x, Scalar* R9) {
+  Exp<Scalar>(x, R9);
+}
+
+/// `Matrix3 Exp(const Vector3& ang_vel, const Scalar& dt)` (src/so3.cpp:76-94): rotation by |ang_vel| dt about
+/// ang_vel, identity below |ang_vel| = 1e-7.  `Matrix3 Exp(const Vector3& ang)` (:60-74) is the dt = 1 case.
+template <typename Scalar>
+inline void Exp(const Scalar* ang_vel, const Scalar& dt, Scalar* R) {
+  const Scalar n = std::sqrt(ang_vel[0] * ang_vel[0] + ang_vel[1] * ang_vel[1] + ang_vel[2] * ang_vel[2]);
+  for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? Scalar(1) : Scalar(0);
+  if (n > Scalar(0.0000001)) {
+    const Scalar a[3] = {ang_vel[0] / n, ang_vel[1] / n, ang_vel[2] / n};
+    const Scalar K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+    const Scalar ang = n * dt;
+    const Scalar s = std::sin(ang), c = std::cos(ang);
+    for (int r = 0; r < 3; ++r)
+      for (int col = 0; col < 3; ++col) {
+        Scalar kk = 0;
+        for (int k = 0; k < 3; ++k) kk += K[r * 3 + k] * K[k * 3 + col];
+        R[r * 3 + col] += s * K[r * 3 + col] + (Scalar(1.0) - c) * kk;
+      }
+  }
+}
+template <typename Scalar>
+inline void ExpAng(const Scalar* ang, Scalar* R) {
+  Exp<Scalar>(ang, Scalar(1), R);
+}
+
+/// delta = Log(R) (src/so3.cpp:96-105): theta = 0 when trace(R) > 3 - 1e-6, first-order branch below theta = 1e-3.
+template <typename Scalar>
+inline void Log(const Scalar* R, Scalar* delta) {
+  const Scalar tr = R[0] + R[4] + R[8];
+  const Scalar theta = (tr > Scalar(3.0 - 1e-6)) ? Scalar(0) : std::acos(Scalar(0.5) * (tr - Scalar(1)));
+  const Scalar K[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  const Scalar f = (std::abs(theta) < Scalar(0.001)) ? Scalar(0.5) : Scalar(0.5) * theta / std::sin(theta);
+  for (int i = 0; i < 3; ++i) delta[i] = f * K[i];
+}
+
+namespace detail {
+template <typename Scalar>
+inline void skew(const Scalar* v, Scalar* K) {
+  const Scalar k[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+  for (int i = 0; i < 9; ++i) K[i] = k[i];
+}
+}  // namespace detail
+
+/// src/so3.cpp:107-121: I + [r]x / 2 + (1/|r|^2 - (1 + cos|r|) / (2 |r| sin|r|)) [r]x^2, identity below |r|^2 = 1e-5.
+template <typename Scalar>
+inline void inverseRightJacobian(const Scalar* r, Scalar* J) {
+  const double theta_sq = double(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  for (int i = 0; i < 9; ++i) J[i] = (i % 4 == 0) ? Scalar(1) : Scalar(0);
+  if (theta_sq < 1e-5) return;
+  Scalar K[9];
+  detail::skew(r, K);
+  const Scalar n = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  const Scalar factor = Scalar(1) / (n * n) - (Scalar(1) + std::cos(n)) / (Scalar(2) * n * std::sin(n));
+  for (int row = 0; row < 3; ++row)
+    for (int col = 0; col < 3; ++col) {
+      Scalar kk = 0;
+      for (int k = 0; k < 3; ++k) kk += K[row * 3 + k] * K[k * 3 + col];
+      J[row * 3 + col] += Scalar(0.5) * K[row * 3 + col] + factor * kk;
+    }
+}
+
+/// src/so3.cpp:123-139: the reference's right Jacobian, I - (1 - cos|r|) / |r|^2 [r]x (no second-order term).
+template <typename Scalar>
+inline void rightJacobian(const Scalar* r, Scalar* J) {
+  const double theta_sq = double(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  for (int i = 0; i < 9; ++i) J[i] = (i % 4 == 0) ? Scalar(1) : Scalar(0);
+  if (theta_sq < 1e-5) return;
+  Scalar K[9];
+  detail::skew(r, K);
+  const Scalar factor = Scalar((1.0 - std::cos(std::sqrt(theta_sq))) / theta_sq);
+  for (int i = 0; i < 9; ++i) J[i] -= factor * K[i];
+}
+
+/// src/so3.cpp:141-155: the reference's left Jacobian, I + (1 - cos|r|) / |r|^2 [r]x (no second-order term; the
+/// device path's exact point2point Jacobian uses the full closed form, csrc/mopt_setup.cuh so3_left_jacobian_dev).
+template <typename Scalar>
+inline void leftJacobian(const Scalar* r, Scalar* J) {
+  const double theta_sq = double(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  for (int i = 0; i < 9; ++i) J[i] = (i % 4 == 0) ? Scalar(1) : Scalar(0);
+  if (theta_sq < 1e-5) return;
+  Scalar K[9];
+  detail::skew(r, K);
+  const Scalar factor = Scalar((1.0 - std::cos(std::sqrt(theta_sq))) / theta_sq);
+  for (int i = 0; i < 9; ++i) J[i] += factor * K[i];
 }
 
 }  // namespace so3

@@ -35,3 +35,13 @@ def test_cpp_reference_tests_pass_on_gpu():
     print(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert " 0 failed" in r.stdout
+
+
+def test_so3_mirror_host_only(tmp_path):
+    """include/moptimizer/so3.h (mirror of src/so3.cpp:7-155) against closed forms and Exp/Log round trips; pure host."""
+    exe = str(tmp_path / "so3_host_test")
+    src = os.path.join(ROOT, "tests", "cpp", "so3_host_test.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe],
+                   check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
