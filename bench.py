@@ -95,6 +95,7 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.samples, self.reasons, self._stop = [], set(), threading.Event()
+        self.times, self.window = [], None
         self.sm_max = None
         self._t = None
         try:
@@ -117,6 +118,7 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.times.append(time.perf_counter())
                 try:
                     r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 except Exception:
@@ -140,11 +142,26 @@ class ClockSampler:
             self._t.join()
             self._t = None
 
+    def mark(self):
+        """Start (first call) / end (second call) of the timed region on the host clock."""
+        t = time.perf_counter()
+        self.window = (t, None) if self.window is None else (self.window[0], t)
+
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        pairs = list(zip(self.times, self.samples))
+        where = "whole run"
+        if self.window and self.window[1]:
+            inside = [c for t, c in pairs if self.window[0] <= t <= self.window[1]]
+            if len(inside) >= 5:
+                pairs, where = [(0, c) for c in inside], "timed region"
+            else:  # a short timed region: add the samples of the identical back-to-back steps just before it
+                upto = [c for t, c in pairs if t <= self.window[1]]
+                pairs, where = [(0, c) for c in upto[-max(10, len(inside)):]], "timed region + the warm-up steps before it"
+        vals = [c for _, c in pairs]
+        return {"sm_mhz": float(np.median(vals)), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(vals), "window": where}
 
 
 # ------------------------------------------------------------------ CPU (oracle) arm ----
@@ -256,19 +273,21 @@ def run_ours(args):
     # Untimed pre-warm: the B200's clocks/power state take a few hundred ms of load to settle (measured:
     # the same kernel moves between 347 and 380 us during the first ~0.3 s), so a 20 ms timed region right
     # after an idle GPU does not measure the sustained rate.  Fixed step count => identical on every rank.
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.prewarm_steps):
         ctx.linearize_async(store, prob, x0)
     for _ in range(max(args.warmup, 3)):
         ctx.linearize_async(store, prob, x0)
     barrier()
-    sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
+    sampler.mark()
     ev0.record(stream)
     for _ in range(args.steps):
         ctx.linearize_async(store, prob, x0)
     ev1.record(stream)
     barrier()
+    sampler.mark()
     sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")

@@ -178,7 +178,10 @@ __device__ inline int lm_step_thread(LmState* st, const PassResult* trial, const
       }
     } else {  // :112-114
       for (int i = 0; i < P; ++i) st->x[i] = st->xi[i];
-      const double f = fmax(1.0 / 3.0, 1.0 - pow(double(S(2) * rho - S(1)), 3.0));
+      // std::pow(2 rho - 1, 3) evaluated in double (:113); v*v*v is within 1 ulp of it and keeps the library pow
+      // (hundreds of instructions of a kernel that is instruction-fetch bound) out of the step
+      const double v = double(S(2) * rho - S(1));
+      const double f = fmax(1.0 / 3.0, 1.0 - v * v * v);
       st->lambda = double(S(double(lam) * f));
       st->it += 1;
       if (st->it >= st->max_it) {
