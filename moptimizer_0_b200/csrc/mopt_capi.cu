@@ -256,6 +256,8 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
     a.peer.world = ctx->world;
     a.peer.rank = ctx->rank;
     a.peer.push = 1;
+    a.peer.fused = ctx->fused_consumer ? 1 : 0;
+    a.peer.err = ctx->d_xerr;
     a.peer.seq = ++ctx->xseq;
   }
   PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
@@ -276,6 +278,7 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
 int allreduce_trial(mopt_ctx* ctx, int P, int mode_override) {
   if (ctx->world <= 1 || !ctx->exchange_enabled) return MOPT_OK;
   if (ctx->peers_open) {
+    if (ctx->fused_consumer) return MOPT_OK;  // the pass kernel's last CTA already wrote the totals (peer_push)
     peer_reduce_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_xbuf, ctx->world, ctx->xseq, ctx->d_trial, packed_size(P),
                                                   &ctx->d_lm->pass_mode, mode_override, ctx->d_xerr);
     MOPT_CUDA_TRY(cudaGetLastError());
@@ -511,6 +514,8 @@ int mopt_ctx_open_peers(mopt_ctx* ctx, const void* handles) {
     ctx->peer_base[r] = static_cast<XSlot*>(p);
   }
   ctx->peers_open = true;
+  const char* mode = getenv("MOPT_PEER_CONSUMER");  // "kernel": keep the separate one-warp consumer kernel (A/B)
+  ctx->fused_consumer = !(mode && std::string(mode) == "kernel");
   return MOPT_OK;
 }
 

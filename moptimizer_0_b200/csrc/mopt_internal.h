@@ -45,6 +45,7 @@ struct mopt_ctx {
   mopt::XSlot* peer_base[mopt::kMaxWorld] = {nullptr};
   bool peers_open = false;
   bool exchange_enabled = true;                  // diagnostics: false = rank-local results, no collective
+  bool fused_consumer = true;                    // the pushing warp also consumes (MOPT_PEER_CONSUMER=kernel: separate kernel)
   unsigned long long xseq = 0;
   int* h_xerr = nullptr;                         // mapped: set by the consumer kernel on a wait timeout
   int* d_xerr = nullptr;

@@ -25,7 +25,10 @@ struct XSlot {
 struct PeerArgs {
   XSlot* base[kMaxWorld];  // exchange buffer of rank r as mapped in this process (base[rank] is local)
   int world, rank, push;
+  int fused;               // 1: the pushing warp also waits for every rank's slot and writes the totals to `out`
+                           //    (no separate consumer kernel); 0: peer_reduce_kernel does that
   unsigned long long seq;  // sequence number of this exchange (>= 1)
+  int* err;                // set to 1 when a peer's slot does not arrive in time (mapped host memory)
 };
 
 struct PassArgs {
@@ -121,6 +124,37 @@ __device__ __forceinline__ void peer_push(const PassArgs& a, int npk) {
       unsigned long long* flag = &a.peer.base[r][slot].seq;
       asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(a.peer.seq) : "memory");
     }
+  }
+  if (!a.peer.fused) return;
+  // Consumer side, same warp: lane r acquires rank r's flag in the LOCAL exchange buffer, then the warp sums the
+  // slots in rank order into `out` — identical bits on every rank.  Nothing on another GPU waits for this CTA, so
+  // spinning here cannot deadlock; a peer that died is reported after ~10 s instead of hanging the device.
+  __syncwarp();
+  XSlot* mine = a.peer.base[a.peer.rank] + int(a.peer.seq & 1ull) * kMaxWorld;
+  bool ok = true;
+  if (lane < a.peer.world) {
+    const unsigned long long* flag = &mine[lane].seq;
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+      if (v == a.peer.seq) break;
+      if (clock64() - t0 > 20000000000LL) {
+        ok = false;
+        break;
+      }
+      __nanosleep(32);
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);  // also orders every lane's slot reads after the acquiring lanes' flag reads
+  if (!ok) {
+    if (lane == 0) *a.peer.err = 1;
+    return;
+  }
+  for (int k = lane; k < npk; k += 32) {
+    double s = 0.0;
+    for (int r = 0; r < a.peer.world; ++r) s += *reinterpret_cast<volatile double*>(&mine[r].v[k]);
+    a.out->v[k] = s;
   }
 }
 

@@ -15,24 +15,27 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(nproc, collective="p2p"):
+def _run(nproc, collective="p2p", consumer=None):
     cmd = [sys.executable]
     if nproc > 1:
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
                 "--master-port", "29611"]
     cmd += [os.path.join(ROOT, "tests", "sharded_worker.py"), collective]
-    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
+    env = dict(os.environ)
+    if consumer:  # "kernel": separate one-warp consumer kernel instead of the one fused into the pass kernel
+        env["MOPT_PEER_CONSUMER"] = consumer
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
     return json.loads(line[len("RESULT "):])
 
 
-@pytest.mark.parametrize("collective", ["p2p", "nccl"])
-def test_two_ranks_match_single_gpu(collective):
+@pytest.mark.parametrize("collective,consumer", [("p2p", None), ("p2p", "kernel"), ("nccl", None)])
+def test_two_ranks_match_single_gpu(collective, consumer):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    one, two = _run(1), _run(2, collective)
+    one, two = _run(1), _run(2, collective, consumer)
     assert two["collective"] == collective
     f1, f2 = one["fachada"], two["fachada"]
     # fp64: different summation order only
