@@ -11,9 +11,9 @@ d=json.loads(sys.stdin.readline())
 print('$label', 'n/gpu', d['config']['n_per_gpu'], 'coupled us/step %.1f' % (d['ms_per_step']*1e3), 'uncoupled max %.1f' % (max(d['per_rank_uncoupled_ms_per_step'])*1e3), 'Gres/s %.1f' % d['value'])"
 }
 for rep in 1 2; do
-  run "fused   " "MOPT_X=1" --n 4096 --steps 500 --prewarm-steps 200
-  run "kernel  " "MOPT_PEER_CONSUMER=kernel" --n 4096 --steps 500 --prewarm-steps 200
-  run "nccl    " "MOPT_X=1" --n 4096 --steps 500 --prewarm-steps 200 --collective nccl
+  run "fused   " "MOPT_X=1" --per-gpu 4096 --steps 500 --prewarm-steps 200
+  run "kernel  " "MOPT_PEER_CONSUMER=kernel" --per-gpu 4096 --steps 500 --prewarm-steps 200
+  run "nccl    " "MOPT_X=1" --per-gpu 4096 --steps 500 --prewarm-steps 200 --collective nccl
 done
 run "fused   " "MOPT_X=1" --steps 200
 run "kernel  " "MOPT_PEER_CONSUMER=kernel" --steps 200
