@@ -10,10 +10,13 @@ template <class M, typename ST, typename CT>
 int launch_one(const PassLaunch& L, const PassArgs& a) {
   auto kern = wide_pass_kernel<M, ST, CT, kThreads>;
   constexpr size_t smem = wide_smem_bytes<M, CT, kThreads>();
-  static bool configured = false;
-  if (!configured) {
+  // function attributes are per device: opt in to the large dynamic shared-memory tile once on each
+  static bool configured[64] = {false};
+  int dev = 0;
+  MOPT_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     MOPT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   int occ = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
