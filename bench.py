@@ -4,8 +4,9 @@
 Workload (BASELINE.json configs[2]): point-to-point rigid registration,
 100 M correspondences per GPU, analytical Jacobian + Huber loss, fp32 planar streams resident in
 HBM (24 B per correspondence), fp32 residual math with fp64 accumulation.  A "step" is one
-linearization pass (H, b, sum r^T r) over every rank's shard plus, for N > 1, the fp64 all-reduce
-of the 28 packed values.  Weak scaling: every rank holds `--n` correspondences.
+linearization pass (H, b, sum r^T r) over every rank's shard plus, for N > 1, the exchange of the 28
+packed fp64 values (NVLink peer exchange fused into the pass kernel; `--collective nccl` for the
+NCCL all-reduce baseline).  Weak scaling: every rank holds `--n` correspondences.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          # our CUDA path
   python bench.py --impl reference ...                         # CPU restatement of the reference
@@ -397,7 +398,8 @@ def run_ours(args):
                        "prewarm_steps": args.prewarm_steps,
                        "l2": f"inputs {BYTES_PER_RES * n / 1e6:.0f} MB per GPU >> 126 MB L2, no flush needed",
                        "collective": {"none": "none",
-                                      "p2p": "NVLink peer exchange of 28 x f64, pushed by the pass kernel's last CTA",
+                                      "p2p": "NVLink peer exchange of 28 x f64, pushed and reduced by the pass kernel's last CTA"
+                                             + (" (separate consumer kernel)" if os.environ.get("MOPT_PEER_CONSUMER") == "kernel" else ""),
                                       "nccl": "ncclAllReduce(28 x f64) per step"}[collective]
                                      + (f" (p2p unavailable: {collective_note})" if collective_note else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -408,8 +410,8 @@ def run_ours(args):
                          "kernel": "p2p_moment_kernel<float,float,HUBER,QROT>",
                          "algorithmic_bytes_per_launch": BYTES_PER_RES * n},
             "clocks": sampler.summary(),
-            # per step: setup kernel + pass kernel (+ the one-warp exchange consumer, or NCCL's kernel, when N > 1)
-            "gpu_launches": (2 + (1 if world > 1 else 0)) * args.steps,
+            # per step: setup kernel + pass kernel (+ NCCL's kernel or the separate consumer kernel when selected)
+            "gpu_launches": (2 + (1 if world > 1 and (collective == "nccl" or os.environ.get("MOPT_PEER_CONSUMER") == "kernel") else 0)) * args.steps,
             "check": {"sum_rtr": s, "H00": float(H[0, 0]), "b0": float(b[0])},
         }
         if local_ms is not None:

@@ -194,7 +194,9 @@ MOPT_API int mopt_ctx_create(int device, mopt_ctx** out);
 MOPT_API int mopt_ctx_create_sharded(int device, int rank, int world_size, const void* nccl_unique_id, mopt_ctx** out);
 MOPT_API int mopt_comm_unique_id(void* out_id);
 /* NVLink peer exchange instead of NCCL: the last CTA of every pass stores the packed result straight into every
- * rank's exchange buffer (P2P stores through NVSwitch) and a one-warp consumer sums the slots in rank order.
+ * rank's exchange buffer (P2P stores through NVSwitch), then waits for every rank's slot in its own buffer and sums
+ * the slots in rank order — pass and collective are one kernel (MOPT_PEER_CONSUMER=kernel in the environment keeps
+ * the consumer as a separate one-warp kernel, for A/B).
  * Each rank publishes mopt_ctx_peer_handle (MOPT_PEER_HANDLE_BYTES bytes, a CUDA IPC handle), the host gathers
  * them in rank order and every rank calls mopt_ctx_open_peers.  With this open, `nccl_unique_id` of
  * mopt_ctx_create_sharded may be NULL. */

@@ -10,12 +10,12 @@
 
 namespace mopt {
 
-// Cross-GPU exchange of the packed result over NVLink peer memory (fused into the pass kernel's last CTA
-// instead of a separate NCCL all-reduce): every rank owns slots[parity][source rank]; the last CTA of a pass
-// stores its packed (H, b, sum) into its slot on EVERY rank (P2P stores through NVSwitch), fences, then
-// releases a sequence flag; a one-warp consumer on each rank acquires the flags and sums the slots in rank
-// order, so all ranks obtain bit-identical totals.  Two parities suffice: a rank can only be two passes ahead
-// of a peer after that peer has consumed the older slot.
+// Cross-GPU exchange of the packed result over NVLink peer memory, fused into the pass kernel's last CTA instead
+// of a separate NCCL all-reduce: every rank owns slots[parity][source rank]; the last CTA of a pass stores its
+// packed (H, b, sum) into its slot on EVERY rank (P2P stores through NVSwitch), fences once at system scope, then
+// writes a sequence flag next to each copy; the same warp then acquires every rank's flag in its OWN buffer and
+// sums the slots in rank order, so all ranks obtain bit-identical totals (peer_push below).  Two parities suffice:
+// a rank can only be two passes ahead of a peer after that peer has consumed the older slot.
 constexpr int kMaxWorld = 8;
 struct XSlot {
   double v[kPackedMax];
