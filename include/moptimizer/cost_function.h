@@ -63,17 +63,13 @@ class CostFunctionBase {
     p->jacobian = jacobian;
     p->compute_dtype = device::dtypeOf<Scalar>();
     p->manifold = manifold_;
-    if (dynamic_cast<const loss::NoLoss<Scalar>*>(loss_function_.get())) {
-      p->loss = MOPT_LOSS_NONE;
-    } else if (auto* gm = dynamic_cast<const loss::GemmanMCClure<Scalar>*>(loss_function_.get())) {
-      p->loss = MOPT_LOSS_GEMAN_MCCLURE;
-      p->loss_param = double(gm->threshold());
-    } else if (auto* hb = dynamic_cast<const loss::Huber<Scalar>*>(loss_function_.get())) {
-      p->loss = MOPT_LOSS_HUBER;
-      p->loss_param = double(hb->k());
-    } else {
-      throw Exception("cost function: only NoLoss, GemmanMCClure and Huber are implemented on the device");
-    }
+    int loss_kind = MOPT_LOSS_NONE;
+    double loss_parameter = 0.0;
+    if (!loss_function_ || !loss_function_->deviceLoss(&loss_kind, &loss_parameter))
+      throw Exception("cost function: this loss has no device implementation (ILossFunction::deviceLoss); NoLoss, "
+                      "GemmanMCClure and Huber are implemented by the kernels");
+    p->loss = loss_kind;
+    p->loss_param = loss_parameter;
     const int O = num_outputs;
     if (covariance_ && covariance_->rows() == O && covariance_->cols() == O) {
       bool identity = true;

@@ -12,7 +12,7 @@
 namespace moptimizer::device {
 
 inline void check(int status, const char* what) {
-  if (status != MOPT_OK) throw moptimizer::Exception(std::string(what) + ": " + mopt_last_error());
+  if (status != MOPT_OK) throw moptimizer::Exception(std::string(what) + ": " + mopt_last_error(), status);
 }
 
 /// One GPU.  Fails loudly (exception) when no CUDA device / library is available: there is no CPU path.

@@ -26,18 +26,11 @@ class LevenbergMarquadtDynamic : public Optimizer<Scalar> {
   OptimizationStatus minimize(Scalar* x0) override {
     this->checkCosts();
     prepare(x0);
-    const int n = int(costs_.size());
-    if (n > MOPT_MAX_COSTS) throw Exception("LevenbergMarquadtDynamic: too many cost functions for the device path");
-    std::vector<mopt_problem> problems(n);
-    std::vector<device::Store::Ptr> stores(n);
-    std::vector<mopt_store*> raw(n);
-    for (int i = 0; i < n; ++i) {
-      costs_[i]->update(x0);  // model->update(x) (:54); a no-op for the builtin device models
-      costs_[i]->deviceProblem(&problems[i], &stores[i]);
-      raw[i] = stores[i]->get();
-      if (stores[i]->context() != stores[0]->context())
-        throw Exception("LevenbergMarquadtDynamic: all cost functions must live on the same device context");
-    }
+    std::vector<mopt_problem> problems;
+    std::vector<device::Store::Ptr> stores;
+    std::vector<mopt_store*> raw;
+    this->gatherDeviceProblems(x0, &problems, &stores, &raw);  // cost->update(x0) (:54) + device descriptions
+    const int n = int(raw.size());
     mopt_lm_options opt;
     mopt_lm_default_options(&opt);
     opt.max_iterations = int(maximum_iterations_);

@@ -1,4 +1,5 @@
-// Mirrors include/moptimizer/loss_function/geman_mcclure.h:7-19 (class name as spelled there).
+// Geman-McClure weight, class name as the reference spells it (include/moptimizer/loss_function/geman_mcclure.h:7-19):
+//   w(e2) = th^2 / (e2 + th)^2
 #pragma once
 
 #include "loss_function.h"
@@ -10,9 +11,15 @@ class GemmanMCClure : public ILossFunction<T> {
  public:
   using Ptr = std::shared_ptr<GemmanMCClure>;
   explicit GemmanMCClure(T threshold) : threshold_(threshold) {}
+
   T weight(T errorSquaredNorm) override {
-    const T d = errorSquaredNorm + threshold_;
-    return (threshold_ * threshold_) / (d * d);
+    const T shifted = errorSquaredNorm + threshold_;
+    return (threshold_ * threshold_) / (shifted * shifted);
+  }
+  bool deviceLoss(int* kind, double* parameter) const override {
+    *kind = MOPT_LOSS_GEMAN_MCCLURE;
+    *parameter = double(threshold_);
+    return true;
   }
   T threshold() const { return threshold_; }
 

@@ -16,6 +16,11 @@ class Huber : public ILossFunction<T> {
   T weight(T errorSquaredNorm) override {
     return (errorSquaredNorm <= k_ * k_) ? T(1) : k_ / std::sqrt(errorSquaredNorm);
   }
+  bool deviceLoss(int* kind, double* parameter) const override {
+    *kind = MOPT_LOSS_HUBER;
+    *parameter = double(k_);
+    return true;
+  }
   T k() const { return k_; }
 
  private:

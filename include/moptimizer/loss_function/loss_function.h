@@ -1,9 +1,12 @@
-// Mirrors include/moptimizer/loss_function/loss_function.h:7-23.  The host `weight` is kept for API
-// parity; on the device path the cost function recognises the concrete type and selects the
-// corresponding kernel-side weight (mopt_loss in mopt_capi.h).
+// IRLS loss interface of the reference (include/moptimizer/loss_function/loss_function.h:7-23): weight(|r|^2).
+// On the device path no virtual call can run per residual, so a loss additionally DESCRIBES itself to the cost
+// function (deviceLoss): the kernels implement the weight of the named kind (mopt_loss in mopt_capi.h).  A loss
+// that does not override deviceLoss() is a host-only loss and is rejected loudly — there is no CPU fallback.
 #pragma once
 
 #include <memory>
+
+#include "mopt_capi.h"
 
 namespace moptimizer::loss {
 
@@ -12,15 +15,31 @@ class ILossFunction {
  public:
   using Ptr = std::shared_ptr<ILossFunction>;
   using ConstPtr = std::shared_ptr<const ILossFunction>;
+
   ILossFunction() = default;
   virtual ~ILossFunction() = default;
+
+  /// w(e2) applied to J^T C J and J^T C r (linearization.h:112-115,149-152); host copy kept for API parity.
   virtual T weight(T errorSquaredNorm) = 0;
+
+  /// Kernel-side kind and parameter of this loss; false = not implemented on the device.
+  virtual bool deviceLoss(int* kind, double* parameter) const {
+    (void)kind;
+    (void)parameter;
+    return false;
+  }
 };
 
+/// w = 1 (loss_function.h:20-23).
 template <typename T>
 class NoLoss : public ILossFunction<T> {
  public:
-  T weight(T) override { return T(1.0); }
+  T weight(T) override { return T(1); }
+  bool deviceLoss(int* kind, double* parameter) const override {
+    *kind = MOPT_LOSS_NONE;
+    *parameter = 0.0;
+    return true;
+  }
 };
 
 }  // namespace moptimizer::loss

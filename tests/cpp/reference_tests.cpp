@@ -480,6 +480,9 @@ struct HostOnlyModel : BaseModel<double, HostOnlyModel> {
     return true;
   }
 };
+struct HostOnlyLoss : loss::ILossFunction<double> {  // a user loss with no device description
+  double weight(double e2) override { return 1.0 / (1.0 + e2); }
+};
 }  // namespace
 
 TEST(ApiMisuse, ErrorsAreLoud) {
@@ -493,6 +496,22 @@ TEST(ApiMisuse, ErrorsAreLoud) {
   CostFunctionNumericalDynamic<double> host_cost(std::make_shared<HostOnlyModel>(), 2, 1, 4);
   double H[4], b[2];
   EXPECT_THROW(host_cost.linearize(x0, H, b), moptimizer::Exception);
+  // a user-defined host loss has no kernel: loud failure as well (ILossFunction::deviceLoss)
+  {
+    const auto cd = interleave(fx("curve_t"), fx("curve_y"));
+    CostFunctionNumericalDynamic<double> c(device::ExpCurve<double>::Ptr(new device::ExpCurve<double>(g_ctx, cd.data(), 67)), 2, 1, 67);
+    c.setLossFunction(std::make_shared<HostOnlyLoss>());
+    EXPECT_THROW(c.linearize(x0, H, b), moptimizer::Exception);
+    c.setLossFunction(std::make_shared<loss::Huber<double>>(0.5));
+    c.linearize(x0, H, b);  // a device loss works
+    try {
+      device::Context::create(1 << 20);
+      EXPECT_TRUE(false);
+    } catch (const moptimizer::Exception& e) {
+      EXPECT_TRUE(e.status() != MOPT_OK);  // the C-ABI status travels with the exception
+    }
+    EXPECT_EQ(std::string(toString(OptimizationStatus::SMALL_DELTA)), std::string("SMALL_DELTA"));
+  }
   // analytical linearization of a Jacobian-free model: BaseModel::f_df throws (model.h:66-70)
   const auto data = interleave(fx("camera_points"), fx("camera_points"));
   double K[12] = {0}, C[16] = {0};
