@@ -28,6 +28,7 @@ void set_last_error(const std::string& msg);
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \
     if (_e != cudaSuccess) {                                                                 \
+      (void)cudaGetLastError(); /* reported here: must not resurface in a later launch check */ \
       ::mopt::set_last_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) +     \
                              " (" __FILE__ ":" + std::to_string(__LINE__) + ")");            \
       return (_e == cudaErrorMemoryAllocation) ? MOPT_ERR_OUT_OF_MEMORY : MOPT_ERR_CUDA;     \

@@ -357,6 +357,14 @@ def test_error_paths(ctx):
     with pytest.raises(capi.MoptError, match="symmetric"):
         ctx.linearize(st, bad, [0.0] * 6)
     st.close()
+    # a failed CUDA call is reported once and must not resurface in the next launch check
+    with pytest.raises(capi.MoptError, match="invalid device"):
+        capi.Context(1 << 20)
+    src, tgt, _, _ = fachada()
+    ok = p2p_store(ctx, src[:100], tgt[:100], capi.F64)
+    H, b, s = ctx.linearize(ok, capi.make_problem(capi.MODEL_POINT2POINT, capi.JAC_ANALYTICAL, capi.F64), [0.0] * 6)
+    assert np.isfinite(s) and H[0, 0] == 100.0
+    ok.close()
 
 
 def test_device_ldlt_matches_oracle(ctx):
