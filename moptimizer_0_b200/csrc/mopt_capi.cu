@@ -109,13 +109,31 @@ __global__ void lm_init_kernel(LmState* st, CostSlot* slots, LmInit in) {
 // One optimizer transition between passes; also publishes the done flag of this slot to the host.
 __global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* slots, int* flag) {
   __shared__ int s_act;
-  if (threadIdx.x == 0) s_act = st->scalar_f32 ? lm_step_thread<float>(st, trial, slots[0].cost) : lm_step_thread<double>(st, trial, slots[0].cost);
-  __syncthreads();
+  __shared__ LmSolveScratch s_scratch;
+  const int lane = threadIdx.x;
+  if (lane == 0) s_act = st->scalar_f32 ? lm_step_thread<float>(st, trial, slots[0].cost) : lm_step_thread<double>(st, trial, slots[0].cost);
+  __syncthreads();  // lane 0's state writes are visible to the warp below
+  if (s_act == 2) {  // damped solve + proposal, the lanes sharing the factorization
+    if (st->scalar_f32) lm_solve_propose_warp<float>(st, slots[0].cost, &s_scratch, lane);
+    else lm_solve_propose_warp<double>(st, slots[0].cost, &s_scratch, lane);
+    __threadfence_block();
+  }
   if (s_act) {
     const int nc = st->n_costs;
-    for (int c = 0; c < nc; ++c) setup_cost(slots[c].cost, st->x_eval, &slots[c].pb, threadIdx.x, blockDim.x);
+    for (int c = 0; c < nc; ++c) setup_cost(slots[c].cost, st->x_eval, &slots[c].pb, lane, blockDim.x);
   }
-  if (threadIdx.x == 0) *flag = st->done;
+  if (lane == 0) *flag = st->done;
+}
+
+// The same solve through the warp-cooperative LDL^T (mopt_ldlt_solve with cooperative = 1; for tests).
+__global__ void ldlt_warp_test_kernel(int n, const double* A, const double* rhs, double* out) {
+  __shared__ LmSolveScratch sc;
+  const int lane = threadIdx.x;
+  for (int i = lane; i < n * n; i += 32) sc.A[i] = A[i];
+  if (lane < n) sc.nb[lane] = rhs[lane];
+  __syncwarp();
+  ldlt_solve_warp<double>(n, sc.A, sc.nb, sc.d, sc.tmp, sc.y, sc.tr, lane);
+  if (lane < n) out[lane] = sc.d[lane];
 }
 
 // Consumer side of the NVLink peer exchange (mopt_pass.cuh peer_push): acquire every rank's sequence flag for
@@ -744,10 +762,22 @@ int mopt_ldlt_solve(int n, const double* A, const double* rhs, double* out) {
   MOPT_CUDA_TRY(cudaMalloc(&dout, sizeof(double) * n));
   MOPT_CUDA_TRY(cudaMemcpy(dA, A, sizeof(double) * n * n, cudaMemcpyHostToDevice));
   MOPT_CUDA_TRY(cudaMemcpy(dr, rhs, sizeof(double) * n, cudaMemcpyHostToDevice));
-  ldlt_test_kernel<<<1, 1>>>(n, dA, dr, dout);
+  // the warp-cooperative factorization the LM step kernel uses, then the serial restatement on a scratch copy:
+  // the two must agree to the last bit (same summation order per row)
+  double out_warp[kMaxP], *dA2 = nullptr;
+  ldlt_warp_test_kernel<<<1, 32>>>(n, dA, dr, dout);
+  MOPT_CUDA_TRY(cudaGetLastError());
+  MOPT_CUDA_TRY(cudaMemcpy(out_warp, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  MOPT_CUDA_TRY(cudaMalloc(&dA2, sizeof(double) * n * n));
+  MOPT_CUDA_TRY(cudaMemcpy(dA2, A, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+  ldlt_test_kernel<<<1, 1>>>(n, dA2, dr, dout);
   MOPT_CUDA_TRY(cudaGetLastError());
   MOPT_CUDA_TRY(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
-  cudaFree(dA); cudaFree(dr); cudaFree(dout);
+  cudaFree(dA); cudaFree(dA2); cudaFree(dr); cudaFree(dout);
+  if (std::memcmp(out, out_warp, sizeof(double) * n) != 0) {
+    set_last_error("internal error: warp-cooperative and serial LDL^T disagree");
+    return MOPT_ERR_CUDA;
+  }
   return MOPT_OK;
 }
 
