@@ -139,7 +139,10 @@ typedef struct mopt_problem {
 /* MOPT_FLAG_GENERIC_KERNEL: evaluate with the generic per-residual kernel even where a specialised one applies.
  * Point2point finite differences normally run on the moment kernel: r is affine in the source point, so
  * (r(x + h e_j) - r(x)) / h = ((R_j - R) p + (t_j - t)) / h exactly; the generic kernel forms the difference per
- * residual in floating point as linearization.h:97-111 does (same Jacobian up to that subtraction's rounding). */
+ * residual in floating point as linearization.h:97-111 does (same Jacobian up to that subtraction's rounding).
+ * The camera models (pinhole, pinhole + distortion) with fp32 compute likewise form the same quotient
+ * (f(x + h e_j) - f_ref) / H over a common denominator / from the parameter-wise affine structure of the residual
+ * instead of subtracting two float-rounded ~1e3-pixel projections; with this flag they use the per-residual form. */
 typedef enum mopt_problem_flags { MOPT_FLAG_GENERIC_KERNEL = 1 } mopt_problem_flags;
 
 /* Optimizer knobs: optimizer.h:19,33-37, levenberg_marquadt_dyn.cpp:9,16, levenberg_marquadt_dyn.h:22-24. */

@@ -279,6 +279,7 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
     a.peer.seq = ++ctx->xseq;
   }
   PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
+  L.affine_fd = !(p->flags & MOPT_FLAG_GENERIC_KERNEL);
   if (p->model >= MOPT_MODEL_USER_BASE)
     return launch_user(L, ctx->device, p->model, p->jacobian != MOPT_JAC_ANALYTICAL, st->dtype, p->compute_dtype, a);
   if (p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL)

@@ -186,6 +186,18 @@ __device__ __forceinline__ void lds16_reload(const double* p, double (&v)[2]) {
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
 }
 
+// Reciprocal for Jacobian entries whose numerator already carries a few ulp: one MUFU.RCP (<= 1 ulp) in fp32.
+__host__ __device__ __forceinline__ float fast_rcp(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+__host__ __device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
+
 // TMA bulk prefetch of `bytes` (multiple of 16, 16-byte aligned source) into L2.
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");

@@ -69,6 +69,8 @@ struct PassLaunch {
   int num_sms;
   int ctas_per_sm;  // 0 = occupancy-derived default
   int threads;      // 0 = default launch shape
+  bool affine_fd = true;  // finite differences over a common denominator where the model allows it
+                          // (dense_pass_kernel AFFINE_FD); false with MOPT_FLAG_GENERIC_KERNEL
 };
 
 // mopt_pass_p2p.cu

@@ -12,6 +12,9 @@ namespace mopt {
 
 #ifdef __CUDACC__
 
+// hooks that tests/cpp/affine_fd_host_test.cu also runs on the host (nvcc -x cu, no GPU needed)
+#define MOPT_HD __host__ __device__ __forceinline__
+
 // tst/point2point.cpp:24-84.  streams: src x,y,z | tgt x,y,z.  set = R (9, row-major), t (3).
 struct P2PModel {
   static constexpr int P = 6, O = 3, NS = 6, NA = 3, SETN = 12;
@@ -76,13 +79,33 @@ struct MichaelisMentenModel {
 struct PinholeModel {
   static constexpr int P = 6, O = 2, NS = 5, NA = 3, SETN = 12;
   static constexpr bool HAS_JAC = false;
+  // The residual is finish(affine(set, e)) with a first stage that is LINEAR in the set (u = M [X Y Z 1]^T), so
+  // the difference of two first stages is the first stage of the difference of the sets.  The AFFINE_FD mode of
+  // the pass kernels uses that to form the finite-difference quotient without subtracting two rounded quotients.
+  static constexpr int NAFF = 3;
   template <typename CT>
-  static __device__ __forceinline__ void residual(const CT* s, const CT (&e)[5], CT (&r)[2]) {
-    CT u[3];
+  static MOPT_HD void affine(const CT* s, const CT (&e)[5], CT (&u)[3]) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) u[k] = fma(s[k * 4 + 0], e[0], fma(s[k * 4 + 1], e[1], fma(s[k * 4 + 2], e[2], s[k * 4 + 3])));
+  }
+  template <typename CT>
+  static MOPT_HD void finish(const CT*, const CT (&u)[3], const CT (&e)[5], CT (&r)[2]) {
     r[0] = e[3] - (u[0] / u[2]);
     r[1] = e[4] - (u[1] / u[2]);
+  }
+  // (finish(ua + H du) - finish(ua)) / H for the perspective division, over the common denominator:
+  //   ((ua0 + H du0) / (ua2 + H du2) - ua0 / ua2) / H = (du0 ua2 - ua0 du2) / (ua2 (ua2 + H du2))
+  template <typename CT>
+  static MOPT_HD void finish_diff(const CT*, const CT (&ua)[3], const CT (&du)[3], CT H, const CT (&)[5], CT (&d)[2]) {
+    const CT inv = fast_rcp(ua[2] * fma(H, du[2], ua[2]));
+    d[0] = fma(ua[0], du[2], -(du[0] * ua[2])) * inv;  // r = pix - u0/u2: the sign is flipped
+    d[1] = fma(ua[1], du[2], -(du[1] * ua[2])) * inv;
+  }
+  template <typename CT>
+  static MOPT_HD void residual(const CT* s, const CT (&e)[5], CT (&r)[2]) {
+    CT u[3];
+    affine<CT>(s, e, u);
+    finish<CT>(s, u, e, r);
   }
   template <typename CT>
   static __device__ __forceinline__ void residual_jacobian(const CT*, const CT (&)[5], CT (&)[2], CT (&)[12]) {}
@@ -121,6 +144,58 @@ struct PinholeDistortModel {
     CT t[3];
     stage1<CT>(s, e, t);
     stage2<CT>(s, e, t, r);
+  }
+  // ---- hooks of the AFFINE_FD mode (see PinholeModel): u = (T C) [X Y Z 1]^T is linear in set[0..12) ----------
+  static constexpr int NAFF = 3;
+  template <typename CT>
+  static MOPT_HD void affine(const CT* s, const CT (&e)[5], CT (&u)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u[k] = fma(s[k * 4 + 0], e[0], fma(s[k * 4 + 1], e[1], fma(s[k * 4 + 2], e[2], s[k * 4 + 3])));
+  }
+  // (f(ua + H du) - f(ua)) / H for the parameters that enter through u (the extrinsics), every difference taken
+  // in product form: D(a b) = Da b_b + a_a Db, D(a^2) = (a_b + a_a) Da, D(a^3) = (a_b^2 + a_b a_a + a_a^2) Da,
+  // so nothing is obtained by subtracting two nearly equal rounded values.  `s` is the base set (fx .. k3).
+  template <typename CT>
+  static MOPT_HD void finish_diff(const CT* s, const CT (&ua)[3], const CT (&du)[3], CT H, const CT (&)[5], CT (&d)[2]) {
+    const CT ia = fast_rcp(ua[2]), ib = fast_rcp(fma(H, du[2], ua[2]));
+    const CT xa = ua[0] * ia, ya = ua[1] * ia;
+    const CT iab = ia * ib;
+    const CT Dx = fma(du[0], ua[2], -(ua[0] * du[2])) * iab;  // (x_b - x_a) / H over the common denominator
+    const CT Dy = fma(du[1], ua[2], -(ua[1] * du[2])) * iab;
+    const CT xb = fma(H, Dx, xa), yb = fma(H, Dy, ya);
+    const CT sx = xb + xa, sy = yb + ya;
+    const CT r2a = fma(xa, xa, ya * ya);
+    const CT Dr2 = fma(sx, Dx, sy * Dy);
+    const CT r2b = fma(H, Dr2, r2a);
+    const CT k1 = s[16], k2 = s[17], p1 = s[18], p2 = s[19], k3 = s[20];
+    const CT radial_a = fma(r2a, fma(r2a, fma(r2a, k3, k2), k1), CT(1));
+    const CT Dradial = Dr2 * fma(k3, fma(r2b, r2b, fma(r2b, r2a, r2a * r2a)), fma(k2, r2b + r2a, k1));
+    const CT radial_b = fma(H, Dradial, radial_a);
+    const CT Dxy2 = CT(2) * fma(Dx, yb, xa * Dy);
+    const CT Dxx = fma(CT(2) * sx, Dx, Dr2);  // D(2 x^2 + r2)
+    const CT Dyy = fma(CT(2) * sy, Dy, Dr2);  // D(2 y^2 + r2)
+    const CT Dxd = fma(Dx, radial_b, fma(xa, Dradial, fma(p1, Dxy2, p2 * Dxx)));
+    const CT Dyd = fma(Dy, radial_b, fma(ya, Dradial, fma(p1, Dyy, p2 * Dxy2)));
+    d[0] = -(s[12] * Dxd);
+    d[1] = -(s[13] * Dyd);
+  }
+  // Columns STAGE1_PARAMS .. P-1 of J (fx fy cx cy k1 k2 p1 p2 k3): the residual is affine in each of them taken
+  // alone, so the reference's difference quotient in that parameter (linearization.h:105; central likewise) IS the
+  // partial derivative, whatever the step.  t = stage1 values at the base set.  Jt row-major O x (P - STAGE1_PARAMS).
+  template <typename CT>
+  static MOPT_HD void tail_partials(const CT* s, const CT (&t)[3], CT (&Jt)[18]) {
+    const CT xn = t[0], yn = t[1], r2 = t[2];
+    const CT fx = s[12], fy = s[13], k1 = s[16], k2 = s[17], p1 = s[18], p2 = s[19], k3 = s[20];
+    const CT radial = fma(r2, fma(r2, fma(r2, k3, k2), k1), CT(1));
+    const CT xy2 = CT(2) * xn * yn;
+    const CT xx = fma(CT(2) * xn, xn, r2), yy = fma(CT(2) * yn, yn, r2);
+    const CT xd = fma(xn, radial, fma(p1, xy2, p2 * xx));
+    const CT yd = fma(yn, radial, fma(p1, yy, p2 * xy2));
+    const CT fxx = fx * xn, fyy = fy * yn, r4 = r2 * r2, r6 = r4 * r2;
+    Jt[0] = -xd;        Jt[1] = CT(0);      Jt[2] = CT(-1);     Jt[3] = CT(0);
+    Jt[4] = -(fxx * r2); Jt[5] = -(fxx * r4); Jt[6] = -(fx * xy2); Jt[7] = -(fx * xx); Jt[8] = -(fxx * r6);
+    Jt[9] = CT(0);      Jt[10] = -yd;       Jt[11] = CT(0);     Jt[12] = CT(-1);
+    Jt[13] = -(fyy * r2); Jt[14] = -(fyy * r4); Jt[15] = -(fy * yy); Jt[16] = -(fy * xy2); Jt[17] = -(fyy * r6);
   }
   template <typename CT>
   static __device__ __forceinline__ void residual_jacobian(const CT*, const CT (&)[5], CT (&)[2], CT (&)[30]) {}

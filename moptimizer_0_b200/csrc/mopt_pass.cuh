@@ -428,7 +428,15 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
 // Jacobian in registers, optional O x O covariance, packed upper-triangular accumulation.
 // Raw layout == packed layout: H upper (row-major), b, sum.
 // =============================================================================================
-template <class M, typename ST, typename CT, bool NUMERIC, int THREADS, int MINB>
+//
+// AFFINE_FD (models that declare NAFF/affine/finish/finish_diff, i.e. residual = finish(affine(set, e)) with a first
+// stage linear in the set): the staged sets 1 + j hold D_j = (set(x + h_j e_j) - set_ref) / H_j formed in fp64
+// (set_ref = set(x - h_j e_j), H_j = 2 h_j for central differences; set(x), h_j for the reference's forward
+// scheme, linearization.h:97-111), and column j of J is M::finish_diff(affine(set_ref), affine(D_j), H_j): the same
+// difference quotient (f(x + h e_j) - f_ref) / H with the subtraction carried out over a common denominator
+// instead of between two rounded quotients -- one reciprocal per column instead of 2 O divisions, and none of
+// the eps / h amplification of the per-residual form (which MOPT_FLAG_GENERIC_KERNEL keeps selectable).
+template <class M, typename ST, typename CT, bool NUMERIC, int THREADS, int MINB, bool AFFINE_FD = false>
 __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArgs a) {
   const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
   if (mode == PASS_SKIP) return;
@@ -456,10 +464,19 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
   const int jac = a.cost->jacobian;
   const bool central = (jac == MOPT_JAC_CENTRAL);
   const int nsets = !NUMERIC ? 1 : (central ? 1 + 2 * P : 1 + P);
-  for (int i = threadIdx.x; i < nsets * SETN; i += THREADS)
-    s_sets[i / SETN][i % SETN] = (i % SETN < M::SETN) ? CT(a.pb->sets[i / SETN][i % SETN]) : CT(0);
-  for (int i = threadIdx.x; i < P; i += THREADS)
-    s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
+  for (int i = threadIdx.x; i < nsets * SETN; i += THREADS) {
+    const int si = i / SETN, k = i % SETN;
+    double v = (k < M::SETN) ? a.pb->sets[si][k] : 0.0;
+    if (AFFINE_FD && si >= 1 && si <= P && k < M::SETN) {
+      const int j = si - 1;
+      v = central ? (v - a.pb->sets[1 + P + j][k]) / (2.0 * a.pb->h[j]) : (v - a.pb->sets[0][k]) / a.pb->h[j];
+    }
+    s_sets[si][k] = CT(v);
+  }
+  for (int i = threadIdx.x; i < P; i += THREADS) {
+    if (AFFINE_FD) s_invh[i] = CT(central ? 2.0 * a.pb->h[i] : a.pb->h[i]);  // H_j itself in this mode
+    else s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
+  }
   const bool has_cov = a.cost->has_cov != 0;
   for (int i = threadIdx.x; i < O * O; i += THREADS) s_cov[i] = CT(a.cost->cov[i]);
   const int loss = a.cost->loss;
@@ -499,7 +516,41 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
       return;
     }
     CT J[O * (P > 0 ? P : 1)];
-    if (NUMERIC) {
+    if constexpr (NUMERIC && AFFINE_FD) {
+      constexpr int NAFF = M::NAFF;
+      auto stage1 = [&](int idx, CT (&u)[NAFF]) {
+        if constexpr (kReloadSets) {
+          CT sr[SETN];
+#pragma unroll
+          for (int k = 0; k < SETN; k += VPE) {
+            CT t[VPE];
+            lds16_reload(&s_sets[idx][k], t);
+#pragma unroll
+            for (int v = 0; v < VPE; ++v) sr[k + v] = t[v];
+          }
+          M::template affine<CT>(sr, e, u);
+        } else {
+          M::template affine<CT>(s_sets[idx], e, u);
+        }
+      };
+      CT u0[NAFF];
+      M::template affine<CT>(s_sets[0], e, u0);
+      M::template finish<CT>(s_sets[0], u0, e, r);
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        CT du[NAFF], d[O];
+        stage1(1 + j, du);
+        if (central) {
+          CT um[NAFF];
+          stage1(1 + P + j, um);
+          M::template finish_diff<CT>(s_sets[0], um, du, s_invh[j], e, d);
+        } else {
+          M::template finish_diff<CT>(s_sets[0], u0, du, s_invh[j], e, d);
+        }
+#pragma unroll
+        for (int o = 0; o < O; ++o) J[o * P + j] = d[o];
+      }
+    } else if constexpr (NUMERIC) {
       M::template residual<CT>(s_sets[0], e, r);
       auto eval = [&](int idx, CT (&out)[O]) {
         if constexpr (kReloadSets) {
@@ -718,7 +769,11 @@ __device__ __forceinline__ void sts16<double>(double* p, const double* v) {
   *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
 }
 
-template <class M, typename ST, typename CT, int THREADS, bool NUMERIC = true>
+// AFFINE_FD: as in dense_pass_kernel, for models with the affine / finish_diff hooks; parameters that only feed
+// the second stage take M::tail_partials (the residual is affine in each of them alone, so the difference quotient
+// in that parameter equals the partial derivative).  Used for fp32 compute, where the per-residual difference of
+// two rounded ~1e3-pixel projections over h_j = sqrt(eps) |x_j| is mostly rounding noise.
+template <class M, typename ST, typename CT, int THREADS, bool NUMERIC = true, bool AFFINE_FD = false>
 __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_kernel(const PassArgs a) {
   const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
   if (mode == PASS_SKIP) return;
@@ -750,10 +805,20 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
   const int jac = a.cost->jacobian;
   const bool central = (jac == MOPT_JAC_CENTRAL);
   const int nsets = !NUMERIC ? 1 : (central ? 1 + 2 * P : 1 + P);
-  for (int i = threadIdx.x; i < nsets * SETN; i += THREADS)
-    s_sets[i] = (i % SETN < M::SETN) ? CT(a.pb->sets[i / SETN][i % SETN]) : CT(0);
+  for (int i = threadIdx.x; i < nsets * SETN; i += THREADS) {
+    const int si = i / SETN, k = i % SETN;
+    double v = (k < M::SETN) ? a.pb->sets[si][k] : 0.0;
+    if (AFFINE_FD && si >= 1 && si <= P && k < M::SETN) {  // D_j = (set(x + h_j e_j) - set_ref) / H_j, in fp64
+      const int j = si - 1;
+      v = central ? (v - a.pb->sets[1 + P + j][k]) / (2.0 * a.pb->h[j]) : (v - a.pb->sets[0][k]) / a.pb->h[j];
+    }
+    s_sets[i] = CT(v);
+  }
   if (NUMERIC)
-    for (int i = threadIdx.x; i < P; i += THREADS) s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
+    for (int i = threadIdx.x; i < P; i += THREADS) {
+      if (AFFINE_FD) s_invh[i] = CT(central ? 2.0 * a.pb->h[i] : a.pb->h[i]);  // H_j itself in this mode
+      else s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
+    }
   for (int i = threadIdx.x; i < O * O; i += THREADS) s_cov[i] = CT(a.cost->cov[i]);
   for (int i = threadIdx.x; i < NW * STRIDE; i += THREADS) s_warp[i] = 0.0;
   const bool has_cov = a.cost->has_cov != 0;
@@ -834,7 +899,39 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
       for (int k = 0; k < O * PB; ++k) rowB[k] = CT(0);
       {
         CT J[O * P];
-        if constexpr (NUMERIC) {
+        if constexpr (NUMERIC && AFFINE_FD) {
+          constexpr int NAFF = M::NAFF;
+          CT s0[SETN], u0[NAFF];
+          load_set(0, s0);
+          M::template affine<CT>(s0, e, u0);
+#pragma unroll
+          for (int j = 0; j < S1P; ++j) {
+            CT du[NAFF], d[O];
+            {
+              CT sr[SETN];
+              load_set(1 + j, sr);
+              M::template affine<CT>(sr, e, du);
+            }
+            if (central) {
+              CT um[NAFF], sr[SETN];
+              load_set(1 + P + j, sr);
+              M::template affine<CT>(sr, e, um);
+              M::template finish_diff<CT>(s0, um, du, s_invh[j], e, d);
+            } else {
+              M::template finish_diff<CT>(s0, u0, du, s_invh[j], e, d);
+            }
+#pragma unroll
+            for (int o = 0; o < O; ++o) J[o * P + j] = d[o];
+          }
+          if constexpr (S1P < P) {
+            CT Jt[O * (P - S1P)];
+            M::template tail_partials<CT>(s0, tmp, Jt);
+#pragma unroll
+            for (int o = 0; o < O; ++o)
+#pragma unroll
+              for (int k = 0; k < P - S1P; ++k) J[o * P + S1P + k] = Jt[o * (P - S1P) + k];
+          }
+        } else if constexpr (NUMERIC) {
 #pragma unroll
           for (int j = 0; j < P; ++j) {
             CT rp[O];

@@ -6,9 +6,15 @@ namespace {
 
 constexpr int kThreads = 256;
 
-template <class M, typename ST, typename CT, bool NUMERIC, int THREADS, int MINB>
+// Does model M declare an affine first stage (NAFF / affine / finish / finish_diff)?
+template <class M, class = void>
+struct HasAffineStage { static constexpr bool value = false; };
+template <class M>
+struct HasAffineStage<M, decltype(void(M::NAFF))> { static constexpr bool value = true; };
+
+template <class M, typename ST, typename CT, bool NUMERIC, int THREADS, int MINB, bool AFFINE_FD = false>
 int launch_shape(const PassLaunch& L, const PassArgs& a) {
-  auto kern = dense_pass_kernel<M, ST, CT, NUMERIC, THREADS, MINB>;
+  auto kern = dense_pass_kernel<M, ST, CT, NUMERIC, THREADS, MINB, AFFINE_FD>;
   const int64_t groups = (M::NS == 0) ? 1 : a.n / VecOf<ST>::N;
   PassLaunch L2 = L;
   L2.ctas_per_sm = 0;
@@ -40,6 +46,12 @@ int launch_one(const PassLaunch& L, const PassArgs& a) {
   // fp64 compute: 2 CTAs/SM (128 registers) pays off while the Jacobian is small (camera O x P = 12: 3.88 -> 2.82 ms);
   // with the 3 x 6 point2point Jacobian in doubles the cap spills 400 bytes and loses (3.4 -> 4.6 ms), so that stays at 1.
   constexpr int kMinB = (NUMERIC && M::P >= 4) ? (sizeof(CT) == 4 ? 3 : (M::O * M::P <= 12 ? 2 : 1)) : 1;
+  // fp32 finite differences of a model with an affine first stage: common-denominator difference quotient
+  // (dense_pass_kernel AFFINE_FD) unless the caller asked for the per-residual form.  The fp64-compute path stays
+  // on the literal form: it is the one compared with the reference's fp64 arithmetic at 1e-10.
+  if constexpr (NUMERIC && HasAffineStage<M>::value && sizeof(CT) == 4) {
+    if (L.affine_fd) return launch_shape<M, ST, CT, NUMERIC, kThreads, kMinB, true>(L, a);
+  }
   return launch_shape<M, ST, CT, NUMERIC, kThreads, kMinB>(L, a);
 }
 

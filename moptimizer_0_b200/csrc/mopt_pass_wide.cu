@@ -6,9 +6,9 @@ namespace {
 
 constexpr int kThreads = 256;
 
-template <class M, typename ST, typename CT>
+template <class M, typename ST, typename CT, bool AFFINE_FD>
 int launch_one(const PassLaunch& L, const PassArgs& a) {
-  auto kern = wide_pass_kernel<M, ST, CT, kThreads>;
+  auto kern = wide_pass_kernel<M, ST, CT, kThreads, true, AFFINE_FD>;
   constexpr size_t smem = wide_smem_bytes<M, CT, kThreads>();
   // function attributes are per device: opt in to the large dynamic shared-memory tile once on each
   static bool configured[64] = {false};
@@ -32,9 +32,12 @@ int launch_one(const PassLaunch& L, const PassArgs& a) {
 
 template <class M>
 int launch_types(const PassLaunch& L, int store_dtype, int compute_dtype, const PassArgs& a) {
-  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F32) return launch_one<M, float, float>(L, a);
-  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F64) return launch_one<M, float, double>(L, a);
-  if (store_dtype == MOPT_F64 && compute_dtype == MOPT_F64) return launch_one<M, double, double>(L, a);
+  // fp32 compute: common-denominator finite differences (wide_pass_kernel AFFINE_FD) unless the caller asked for
+  // the per-residual form with MOPT_FLAG_GENERIC_KERNEL; fp64 compute is the literal restatement of the reference
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F32)
+    return L.affine_fd ? launch_one<M, float, float, true>(L, a) : launch_one<M, float, float, false>(L, a);
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F64) return launch_one<M, float, double, false>(L, a);
+  if (store_dtype == MOPT_F64 && compute_dtype == MOPT_F64) return launch_one<M, double, double, false>(L, a);
   set_last_error("store dtype f64 with compute dtype f32 is not supported");
   return MOPT_ERR_UNSUPPORTED;
 }

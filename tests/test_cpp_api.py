@@ -45,3 +45,16 @@ def test_so3_mirror_host_only(tmp_path):
                    check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
+
+
+def test_affine_fd_model_hooks_host_only(tmp_path):
+    """The camera models' AFFINE_FD hooks (csrc/mopt_models.cuh: affine / finish_diff / tail_partials) against the
+    literal difference quotient of linearization.h:97-111 taken in long double; nvcc-compiled, runs on the CPU."""
+    exe = str(tmp_path / "affine_fd_host_test")
+    src = os.path.join(ROOT, "tests", "cpp", "affine_fd_host_test.cu")
+    subprocess.run(["nvcc", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "moptimizer_0_b200", "csrc"),
+                    src, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout

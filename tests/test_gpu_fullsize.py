@@ -151,6 +151,13 @@ def test_camera_distort_50m_nxn_calibration(env):
     H32, b32, s32 = ctx.linearize(st, p32, x)
     assert abs(s32 - s) <= 1e-5 * s
     assert np.max(np.abs(H32 - H)[:10, :10] / scale[:10, :10]) < 5e-2
+    # ... which is why the fp32 throughput path forms the same quotients over a common denominator / from the
+    # parameter-wise affine structure instead (wide_pass_kernel AFFINE_FD): the whole 15 x 15 system then agrees to
+    # fp32 rounding; the per-residual form stays selectable (MOPT_FLAG_GENERIC_KERNEL) and keeps its noise floor.
+    assert np.max(np.abs(H32 - H) / scale) < 2e-4 and np.max(np.abs(b32 - b) / (d * np.sqrt(s))) < 2e-3
+    Hg, _, sg = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL, capi.F32, consts=Cm,
+                                                    flags=capi.FLAG_GENERIC_KERNEL), x)
+    assert sg == s32 and np.max(np.abs(Hg - H)[:10, :10] / scale[:10, :10]) < 5e-2
     # forward differences against central ones (fp64): first-order truncation only
     Hf, bf, sf = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_FORWARD, capi.F64, consts=Cm), x)
     assert sf == s and np.max(np.abs(Hf - H) / scale) < 1e-4

@@ -195,6 +195,72 @@ def test_camera_calibration_lm(ctx, x0, iters):
     st.close()
 
 
+def synthetic_camera(n, seed=5):
+    """Points in front of the camera of tst/camera_calibration.cpp:24-30 and their projections + 0.5 px noise."""
+    consts = camera_consts()
+    K, C = consts[:12].reshape(3, 4), consts[12:].reshape(4, 4)
+    x_gt = np.array([-0.01, 0.02, -0.06, 0.018, -0.0013, 0.027])
+    rng = np.random.default_rng(seed)
+    pts = np.column_stack([rng.uniform(2, 5, n), rng.uniform(-1, 1, n), rng.uniform(-0.5, 1, n)])
+    U = np.column_stack([pts, np.ones(n)]) @ (K @ orc.so3_convert6dof(x_gt) @ C).T
+    pix = U[:, :2] / U[:, 2:3] + rng.normal(0, 0.5, (n, 2))
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)  # noqa: E731  (what an fp32 store holds)
+    return f32(pts), f32(pix), consts, x_gt
+
+
+@pytest.mark.parametrize("jac", [1, 2])
+@pytest.mark.parametrize("x,tol", [([0.0] * 6, 1e-5), ([0.05, -0.03, 0.02, 0.01, 0.02, -0.015], 5e-4)])
+def test_camera_fp32_common_denominator_differences(ctx, jac, x, tol):
+    """fp32 compute of the reference's camera model (tst/camera_calibration.cpp:35-41) with finite differences.
+    The throughput path forms the quotient (f(x + h e_j) - f_ref) / H over a common denominator
+    (dense_pass_kernel AFFINE_FD), so it tracks the fp64 oracle to fp32 rounding of the residual itself: at x = 0
+    (where the staged K T C is exact in float) within the north star's 1e-5; elsewhere within the ~6e-8 * 640 px
+    representation error of the projection relative to the 0.5 px residuals.  The per-residual form
+    (MOPT_FLAG_GENERIC_KERNEL: two rounded ~640 px projections subtracted over h = sqrt(eps_f32) |x_j|) is what the
+    reference's float instantiation computes; it only agrees to that subtraction's noise."""
+    n = 200_000
+    pts, pix, consts, _ = synthetic_camera(n)
+    st = capi.Store(ctx, capi.MODEL_PINHOLE, n, capi.F32)
+    st.upload(0, pts)
+    st.upload(1, pix)
+    H, b, s = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE, jac, capi.F32, consts=consts), x)
+    Hg, bg, sg = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE, jac, capi.F32, consts=consts, flags=1), x)
+    # central differences are compared with the fp64 oracle's central ones; the forward quotient depends on the
+    # step at first order, so it is compared with the oracle run in float (same h = sqrt(eps_f32) |x_j|)
+    oc = orc.Cost(orc.PINHOLE, 6, 2, n, a=pts, b=pix, consts=consts, jac_mode=jac)
+    Ho, bo, so = orc.linearize(oc, x, orc.F64)
+    Hc, bc, _ = orc.linearize(orc.Cost(orc.PINHOLE, 6, 2, n, a=pts, b=pix, consts=consts, jac_mode=orc.JAC_CENTRAL), x)
+    errs = dict(H=rel_err(H, Ho), b=rel_err(b, bo), Hc=rel_err(H, Hc), bc=rel_err(b, bc), Hg=rel_err(Hg, Ho),
+                bg=rel_err(bg, bo))
+    print("camera fp32 jac=%d x0=%s:" % (jac, x[0]), {k: "%.2e" % v for k, v in errs.items()})
+    assert s == sg and abs(s - so) <= 1e-5 * so
+    if jac == capi.JAC_CENTRAL:
+        assert errs["H"] < tol and errs["b"] < tol, errs
+    else:
+        # forward: truncation O(h) differs between the float and the double step rule; the quotient itself is exact
+        assert errs["Hc"] < max(tol, 2e-4) and errs["bc"] < max(tol, 2e-4), errs
+    # the per-residual float form: only to its subtraction noise (and never better than the common-denominator one)
+    assert errs["Hg"] < 5e-2 and errs["bg"] < 5e-2, errs
+    assert errs["H"] <= 2 * errs["Hg"] + 1e-6, errs
+    st.close()
+
+
+def test_camera_fp32_lm_reaches_ground_truth(ctx):
+    """LM on the fp32 throughput path (fp32 store, fp32 residual/Jacobian arithmetic, fp64 accumulation and solve)."""
+    n = 200_000
+    pts, pix, consts, x_gt = synthetic_camera(n)
+    st = capi.Store(ctx, capi.MODEL_PINHOLE, n, capi.F32)
+    st.upload(0, pts)
+    st.upload(1, pix)
+    prob = capi.make_problem(capi.MODEL_PINHOLE, capi.JAC_CENTRAL, capi.F32, consts=consts)
+    r = ctx.lm_minimize([st], [prob], [0.0] * 6, max_iterations=50)
+    ro = orc.lm_minimize([orc.Cost(orc.PINHOLE, 6, 2, n, a=pts, b=pix, consts=consts, jac_mode=orc.JAC_CENTRAL,
+                                   cost_threads=8)], [0.0] * 6, 50)
+    assert np.max(np.abs(r.x - x_gt)) < 1e-3, r.x
+    assert np.max(np.abs(r.x - ro.x)) < 1e-4, (r.x, ro.x)
+    st.close()
+
+
 # ---- tst/simple_model.cpp, tst/loss_function.cpp, tst/covariance.cpp (float) ------------------
 def mm_store(ctx, n=7, dtype=0):
     t = np.array(FX["michaelis_menten"]["t%d" % n], dtype=np.float32)

@@ -83,6 +83,59 @@ def test_wide_covariance_and_loss(env):
     st.close()
 
 
+@pytest.mark.parametrize("jac", [1, 2])
+def test_wide_fp32_common_denominator_differences(env, jac):
+    """fp32 compute of the n x n case.  The per-residual float quotient (MOPT_FLAG_GENERIC_KERNEL; what a float
+    instantiation of linearization.h:97-111 does) is mostly rounding noise for the 1e-3-sized distortion parameters
+    (eps_f32 * 640 px / h_j with h_j = sqrt(eps_f32) |x_j|), which biases diag(H) by noise^2.  The throughput path
+    (wide_pass_kernel AFFINE_FD: extrinsic columns over a common denominator in product form, second-stage columns
+    from the parameter-wise affine structure) has no such term: the WHOLE 15 x 15 system agrees with the fp64-compute
+    path to fp32 rounding, in the natural per-entry scale sqrt(H_ii H_jj)."""
+    capi, ctx = env
+    n = 100_000
+    st, Cm = make_store(capi, ctx, n, capi.F32, sigma=0.5)
+    x = X_GT * (1.0 + 0.002 * np.cos(np.arange(15)))
+    H, b, s = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL, capi.F64, consts=Cm), x)
+    H32, b32, s32 = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE_DISTORT, jac, capi.F32, consts=Cm), x)
+    Hg, bg, sg = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE_DISTORT, jac, capi.F32, consts=Cm, flags=1), x)
+    d = np.sqrt(np.diag(H))
+    eH = np.max(np.abs(H32 - H) / np.outer(d, d))
+    eb = np.max(np.abs(b32 - b) / (d * np.sqrt(s)))
+    eHg = np.max(np.abs(Hg - H) / np.outer(d, d))
+    print("wide fp32 jac=%d: common-denominator H %.2e b %.2e | per-residual H %.2e" % (jac, eH, eb, eHg))
+    assert s32 == sg and abs(s32 - s) <= 1e-5 * s
+    tol = 2e-4 if jac == 2 else 1e-3  # forward: first-order truncation with the float step on top
+    assert eH < tol and eb < 2e-3, (eH, eb)
+    assert eHg > 10 * eH, (eHg, eH)  # the noise floor the new form removes
+    # the well-scaled block of the per-residual form still agrees loosely (it is the same quotient)
+    assert np.max(np.abs(Hg - H)[:10, :10] / np.outer(d, d)[:10, :10]) < 5e-2
+    st.close()
+
+
+def test_wide_fp32_lm_recovers_all_parameters(env):
+    """LM entirely on the fp32 throughput path (fp32 store and residual/Jacobian arithmetic; fp64 sums and solve)
+    recovers the generating parameters, including the distortion coefficients the per-residual float Jacobian
+    cannot resolve."""
+    capi, ctx = env
+    n = 2_000_000
+    st, Cm = make_store(capi, ctx, n, capi.F32, sigma=0.3)
+    x0 = X_GT.copy()
+    x0[:6] = 0.0
+    x0[6:10] *= np.array([1.03, 0.97, 1.01, 0.99])
+    x0[10:] = 0.0
+    p32 = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL, capi.F32, consts=Cm)
+    p64 = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL, capi.F64, consts=Cm)
+    r32 = ctx.lm_minimize([st], [p32], x0, max_iterations=50)
+    r64 = ctx.lm_minimize([st], [p64], x0, max_iterations=50)
+    print("wide fp32 LM:", r32.status, r32.executed_iterations, "fp64:", r64.status, r64.executed_iterations,
+          "max |x32 - x64| =", np.max(np.abs(r32.x - r64.x)))
+    err = np.abs(r32.x - X_GT)
+    assert np.all(err[:6] < 2e-3) and np.all(err[6:10] < 1.0) and np.all(err[10:] < 5e-3), r32.x
+    assert np.allclose(r32.x[:10], r64.x[:10], rtol=1e-4, atol=1e-4), (r32.x, r64.x)
+    assert np.allclose(r32.x[10:], r64.x[10:], atol=2e-3), (r32.x, r64.x)
+    st.close()
+
+
 def test_wide_lm_15x15_device_solve(env):
     capi, ctx = env
     n = 2_000_000
