@@ -71,6 +71,12 @@ struct ParamBlock {
   double h[kMaxP];                    // finite-difference steps (linearization.h:85-87)
   double sets[kMaxSets][kSetSize];    // [0] base, [1+j] x + h_j e_j, [1+P+j] x - h_j e_j
   double jaff[4][18];                 // point2point analytical J(q) = J0 + q_x J1 + q_y J2 + q_z J3 (3x6 row-major)
+  // Steps actually taken after rounding in the compute Scalar: (x_j + h_j) - x_j and (x_j + h_j) - (x_j - h_j).
+  // With a float Scalar they differ from h_j, 2 h_j by up to eps_f32 |x_j| / h_j ~ 1e-4 relative, which the
+  // reference's float quotient (it divides by the nominal h_j, linearization.h:105) inherits as a per-column scale
+  // error; the AFFINE_FD kernels divide by the step taken.
+  double hstep_fwd[kMaxP];
+  double hstep_cen[kMaxP];
 };
 
 // Per-cost constants that live on the device (copied once per call).

@@ -431,8 +431,9 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
 //
 // AFFINE_FD (models that declare NAFF/affine/finish/finish_diff, i.e. residual = finish(affine(set, e)) with a first
 // stage linear in the set): the staged sets 1 + j hold D_j = (set(x + h_j e_j) - set_ref) / H_j formed in fp64
-// (set_ref = set(x - h_j e_j), H_j = 2 h_j for central differences; set(x), h_j for the reference's forward
-// scheme, linearization.h:97-111), and column j of J is M::finish_diff(affine(set_ref), affine(D_j), H_j): the same
+// (set_ref = set(x - h_j e_j) for central differences, set(x) for the reference's forward scheme,
+// linearization.h:97-111; H_j = the step actually taken between the two parameter vectors after rounding in the
+// compute Scalar, ParamBlock::hstep_*), and column j of J is M::finish_diff(affine(set_ref), affine(D_j), H_j): the same
 // difference quotient (f(x + h e_j) - f_ref) / H with the subtraction carried out over a common denominator
 // instead of between two rounded quotients -- one reciprocal per column instead of 2 O divisions, and none of
 // the eps / h amplification of the per-residual form (which MOPT_FLAG_GENERIC_KERNEL keeps selectable).
@@ -469,12 +470,12 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArg
     double v = (k < M::SETN) ? a.pb->sets[si][k] : 0.0;
     if (AFFINE_FD && si >= 1 && si <= P && k < M::SETN) {
       const int j = si - 1;
-      v = central ? (v - a.pb->sets[1 + P + j][k]) / (2.0 * a.pb->h[j]) : (v - a.pb->sets[0][k]) / a.pb->h[j];
+      v = central ? (v - a.pb->sets[1 + P + j][k]) / a.pb->hstep_cen[j] : (v - a.pb->sets[0][k]) / a.pb->hstep_fwd[j];
     }
     s_sets[si][k] = CT(v);
   }
   for (int i = threadIdx.x; i < P; i += THREADS) {
-    if (AFFINE_FD) s_invh[i] = CT(central ? 2.0 * a.pb->h[i] : a.pb->h[i]);  // H_j itself in this mode
+    if (AFFINE_FD) s_invh[i] = CT(central ? a.pb->hstep_cen[i] : a.pb->hstep_fwd[i]);  // H_j itself in this mode
     else s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
   }
   const bool has_cov = a.cost->has_cov != 0;
@@ -810,13 +811,13 @@ __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_
     double v = (k < M::SETN) ? a.pb->sets[si][k] : 0.0;
     if (AFFINE_FD && si >= 1 && si <= P && k < M::SETN) {  // D_j = (set(x + h_j e_j) - set_ref) / H_j, in fp64
       const int j = si - 1;
-      v = central ? (v - a.pb->sets[1 + P + j][k]) / (2.0 * a.pb->h[j]) : (v - a.pb->sets[0][k]) / a.pb->h[j];
+      v = central ? (v - a.pb->sets[1 + P + j][k]) / a.pb->hstep_cen[j] : (v - a.pb->sets[0][k]) / a.pb->hstep_fwd[j];
     }
     s_sets[i] = CT(v);
   }
   if (NUMERIC)
     for (int i = threadIdx.x; i < P; i += THREADS) {
-      if (AFFINE_FD) s_invh[i] = CT(central ? 2.0 * a.pb->h[i] : a.pb->h[i]);  // H_j itself in this mode
+      if (AFFINE_FD) s_invh[i] = CT(central ? a.pb->hstep_cen[i] : a.pb->hstep_fwd[i]);  // H_j itself in this mode
       else s_invh[i] = CT(central ? 1.0 / (2.0 * a.pb->h[i]) : 1.0 / a.pb->h[i]);
     }
   for (int i = threadIdx.x; i < O * O; i += THREADS) s_cov[i] = CT(a.cost->cov[i]);

@@ -8,13 +8,19 @@
 
 namespace mopt {
 
-// src/so3.cpp:43-57 — Rodrigues, guard `norm > 10 eps`.  R row-major.
+// src/so3.cpp:43-57 — Rodrigues, guard `norm > 10 eps`.  R row-major.  S names the cost's compute Scalar.
+// The arithmetic here is fp64 for either S, so the guard is the fp64 one for both: the float threshold (1.2e-6)
+// makes R = I on a whole ball of rotation vectors, where every finite-difference column of the rotation block is
+// exactly zero — LM started at omega = 0 with a heavily damped first step (lambda_0 grows with N,
+// levenberg_marquadt_dyn.cpp:9,62-66) lands inside that ball and can never leave it (observed: camera, 50 M
+// observations, fp32 compute).  Inside the ball R differs from I by < 1.2e-6, i.e. below float resolution, so
+// values computed with a float Scalar are unaffected.
 template <typename S>
 __device__ inline void so3_exp_dev(const double w[3], double R[9]) {
   const double n = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
-  const double eps = (sizeof(S) == 4) ? 1.1920928955078125e-07 : 2.220446049250313e-16;
+  const double eps = 2.220446049250313e-16;
   if (n > 10.0 * eps) {
     const double a0 = w[0] / n, a1 = w[1] / n, a2 = w[2] / n;
     const double K[9] = {0.0, -a2, a1, a2, 0.0, -a0, -a1, a0, 0.0};
@@ -196,17 +202,23 @@ __device__ inline void setup_cost(const CostDev& c, const double* x, ParamBlock*
       const int j = (s - 1) % P;
       const bool minus = (s - 1) >= P;
       double h;
+      double step_fwd, step_cen;  // the steps actually taken (see ParamBlock::hstep_*)
       if (f32) {
         const float ms = sqrtf(1.1920928955078125e-07f);
         float hf = ms * fabsf(float(x[j]));
         if (hf == 0.0f) hf = ms;
         h = double(hf);
-        xs[j] = double(minus ? float(x[j]) - hf : float(x[j]) + hf);
+        const float xpl = float(x[j]) + hf, xmi = float(x[j]) - hf;
+        xs[j] = double(minus ? xmi : xpl);
+        step_fwd = double(xpl) - double(float(x[j]));
+        step_cen = double(xpl) - double(xmi);
       } else {
         const double ms = sqrt(2.220446049250313e-16);
         h = ms * fabs(x[j]);
         if (h == 0.0) h = ms;
         xs[j] = minus ? x[j] - h : x[j] + h;
+        step_fwd = (x[j] + h) - x[j];
+        step_cen = (x[j] + h) - (x[j] - h);
       }
       if (c.manifold == MOPT_MANIFOLD_SO3_LEFT && c.rot_offset >= 0 && j >= c.rot_offset && j < c.rot_offset + 3) {
         // tangent coordinate of the rotation block is 0 at x, so the reference's rule (:85-87) gives h = sqrt(eps)
@@ -217,8 +229,14 @@ __device__ inline void setup_cost(const CostDev& c, const double* x, ParamBlock*
         double base[kMaxP];
         for (int i = 0; i < P; ++i) base[i] = f32 ? double(float(x[i])) : x[i];
         retract_dev(c, base, d, xs, f32);
+        step_fwd = h;  // the tangent-space step is not a coordinate difference of x
+        step_cen = 2.0 * h;
       }
-      if (!minus) pb->h[j] = h;
+      if (!minus) {
+        pb->h[j] = h;
+        pb->hstep_fwd[j] = step_fwd;
+        pb->hstep_cen[j] = step_cen;
+      }
     }
     setup_one_set(c, xs, pb->sets[s]);
   }

@@ -154,7 +154,9 @@ def test_camera_distort_50m_nxn_calibration(env):
     # ... which is why the fp32 throughput path forms the same quotients over a common denominator / from the
     # parameter-wise affine structure instead (wide_pass_kernel AFFINE_FD): the whole 15 x 15 system then agrees to
     # fp32 rounding; the per-residual form stays selectable (MOPT_FLAG_GENERIC_KERNEL) and keeps its noise floor.
-    assert np.max(np.abs(H32 - H) / scale) < 2e-4 and np.max(np.abs(b32 - b) / (d * np.sqrt(s))) < 2e-3
+    e32 = (np.max(np.abs(H32 - H) / scale), np.max(np.abs(b32 - b) / (d * np.sqrt(s))))
+    print("camera15 50M fp32 vs fp64 compute: H %.2e b %.2e (scaled)" % e32)
+    assert e32[0] < 2e-5 and e32[1] < 2e-4, e32
     Hg, _, sg = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL, capi.F32, consts=Cm,
                                                     flags=capi.FLAG_GENERIC_KERNEL), x)
     assert sg == s32 and np.max(np.abs(Hg - H)[:10, :10] / scale[:10, :10]) < 5e-2

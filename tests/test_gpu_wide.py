@@ -104,8 +104,8 @@ def test_wide_fp32_common_denominator_differences(env, jac):
     eHg = np.max(np.abs(Hg - H) / np.outer(d, d))
     print("wide fp32 jac=%d: common-denominator H %.2e b %.2e | per-residual H %.2e" % (jac, eH, eb, eHg))
     assert s32 == sg and abs(s32 - s) <= 1e-5 * s
-    tol = 2e-4 if jac == 2 else 1e-3  # forward: first-order truncation with the float step on top
-    assert eH < tol and eb < 2e-3, (eH, eb)
+    tol = 1e-5 if jac == 2 else 1e-4  # forward: first-order truncation with the float step on top
+    assert eH < tol and eb < 2e-4, (eH, eb)
     assert eHg > 10 * eH, (eHg, eH)  # the noise floor the new form removes
     # the well-scaled block of the per-residual form still agrees loosely (it is the same quotient)
     assert np.max(np.abs(Hg - H)[:10, :10] / np.outer(d, d)[:10, :10]) < 5e-2
