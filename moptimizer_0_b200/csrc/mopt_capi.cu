@@ -429,7 +429,7 @@ int mopt_ctx_create(int device, mopt_ctx** out) {
   ctx->device = device;
   const int s = ctx_alloc(ctx);
   if (s != MOPT_OK) {
-    delete ctx;
+    mopt_ctx_destroy(ctx);  // releases whatever ctx_alloc got before it failed (every member starts null)
     return s;
   }
   *out = ctx;
@@ -451,11 +451,11 @@ int mopt_comm_unique_id(void* out_id) {
 int mopt_ctx_create_sharded(int device, int rank, int world_size, const void* nccl_unique_id, mopt_ctx** out) {
   MOPT_REQUIRE(out, "null out");
   MOPT_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad rank/world_size");
+  MOPT_REQUIRE(world_size <= kMaxWorld, "at most 8 ranks (one box) are supported");
   MOPT_TRY(mopt_ctx_create(device, out));
   mopt_ctx* ctx = *out;
   ctx->rank = rank;
   ctx->world = world_size;
-  MOPT_REQUIRE(world_size <= kMaxWorld, "at most 8 ranks (one box) are supported");
   if (world_size > 1 && nccl_unique_id) {  // without an id the caller must open the NVLink peer exchange instead
     if (!nccl().ok) {
       set_last_error(nccl().why);
