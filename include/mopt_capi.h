@@ -143,7 +143,11 @@ typedef struct mopt_problem {
  * The camera models (pinhole, pinhole + distortion) with fp32 compute likewise form the same quotient
  * (f(x + h e_j) - f_ref) / H over a common denominator / from the parameter-wise affine structure of the residual
  * instead of subtracting two float-rounded ~1e3-pixel projections; with this flag they use the per-residual form. */
-typedef enum mopt_problem_flags { MOPT_FLAG_GENERIC_KERNEL = 1 } mopt_problem_flags;
+/* MOPT_FLAG_STABLE_FD: opt the fp64-compute finite differences of the camera models into the same common-denominator
+ * form (by default fp64 compute is the literal per-residual restatement of linearization.h:97-111, the path compared
+ * with the reference at 1e-10 / 1e-6).  Same quotient without the eps/h rounding of the subtraction, and 26 IEEE
+ * divisions per observation fewer.  Ignored where no such form exists. */
+typedef enum mopt_problem_flags { MOPT_FLAG_GENERIC_KERNEL = 1, MOPT_FLAG_STABLE_FD = 2 } mopt_problem_flags;
 
 /* Optimizer knobs: optimizer.h:19,33-37, levenberg_marquadt_dyn.cpp:9,16, levenberg_marquadt_dyn.h:22-24. */
 typedef struct mopt_lm_options {

@@ -279,7 +279,9 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
     a.peer.seq = ++ctx->xseq;
   }
   PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
-  L.affine_fd = !(p->flags & MOPT_FLAG_GENERIC_KERNEL);
+  // finite differences over a common denominator (AFFINE_FD): the default with fp32 compute, opt-in with fp64
+  L.affine_fd = (p->compute_dtype == MOPT_F32) ? !(p->flags & MOPT_FLAG_GENERIC_KERNEL)
+                                               : ((p->flags & MOPT_FLAG_STABLE_FD) && !(p->flags & MOPT_FLAG_GENERIC_KERNEL));
   if (p->model >= MOPT_MODEL_USER_BASE)
     return launch_user(L, ctx->device, p->model, p->jacobian != MOPT_JAC_ANALYTICAL, st->dtype, p->compute_dtype, a);
   if (p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL)

@@ -46,10 +46,11 @@ int launch_one(const PassLaunch& L, const PassArgs& a) {
   // fp64 compute: 2 CTAs/SM (128 registers) pays off while the Jacobian is small (camera O x P = 12: 3.88 -> 2.82 ms);
   // with the 3 x 6 point2point Jacobian in doubles the cap spills 400 bytes and loses (3.4 -> 4.6 ms), so that stays at 1.
   constexpr int kMinB = (NUMERIC && M::P >= 4) ? (sizeof(CT) == 4 ? 3 : (M::O * M::P <= 12 ? 2 : 1)) : 1;
-  // fp32 finite differences of a model with an affine first stage: common-denominator difference quotient
-  // (dense_pass_kernel AFFINE_FD) unless the caller asked for the per-residual form.  The fp64-compute path stays
-  // on the literal form: it is the one compared with the reference's fp64 arithmetic at 1e-10.
-  if constexpr (NUMERIC && HasAffineStage<M>::value && sizeof(CT) == 4) {
+  // Finite differences of a model with an affine first stage: common-denominator difference quotient
+  // (dense_pass_kernel AFFINE_FD).  launch_pass sets L.affine_fd: on by default with fp32 compute (off with
+  // MOPT_FLAG_GENERIC_KERNEL), off by default with fp64 compute — the literal form is the one compared with the
+  // reference's fp64 arithmetic — and on with MOPT_FLAG_STABLE_FD.
+  if constexpr (NUMERIC && HasAffineStage<M>::value) {
     if (L.affine_fd) return launch_shape<M, ST, CT, NUMERIC, kThreads, kMinB, true>(L, a);
   }
   return launch_shape<M, ST, CT, NUMERIC, kThreads, kMinB>(L, a);

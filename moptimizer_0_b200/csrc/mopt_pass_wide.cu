@@ -32,12 +32,15 @@ int launch_one(const PassLaunch& L, const PassArgs& a) {
 
 template <class M>
 int launch_types(const PassLaunch& L, int store_dtype, int compute_dtype, const PassArgs& a) {
-  // fp32 compute: common-denominator finite differences (wide_pass_kernel AFFINE_FD) unless the caller asked for
-  // the per-residual form with MOPT_FLAG_GENERIC_KERNEL; fp64 compute is the literal restatement of the reference
+  // L.affine_fd (launch_pass): common-denominator finite differences (wide_pass_kernel AFFINE_FD) — the default
+  // with fp32 compute unless MOPT_FLAG_GENERIC_KERNEL asks for the per-residual form; fp64 compute is the literal
+  // restatement of the reference unless MOPT_FLAG_STABLE_FD opts in
   if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F32)
     return L.affine_fd ? launch_one<M, float, float, true>(L, a) : launch_one<M, float, float, false>(L, a);
-  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F64) return launch_one<M, float, double, false>(L, a);
-  if (store_dtype == MOPT_F64 && compute_dtype == MOPT_F64) return launch_one<M, double, double, false>(L, a);
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F64)
+    return L.affine_fd ? launch_one<M, float, double, true>(L, a) : launch_one<M, float, double, false>(L, a);
+  if (store_dtype == MOPT_F64 && compute_dtype == MOPT_F64)
+    return L.affine_fd ? launch_one<M, double, double, true>(L, a) : launch_one<M, double, double, false>(L, a);
   set_last_error("store dtype f64 with compute dtype f32 is not supported");
   return MOPT_ERR_UNSUPPORTED;
 }

@@ -89,6 +89,9 @@ if section("camera"):
             if cd == capi.F32:  # per-residual float quotient instead of the common-denominator form
                 prob = capi.make_problem(capi.MODEL_PINHOLE, jac, cd, consts=consts, flags=capi.FLAG_GENERIC_KERNEL)
                 report(f"camera50M_{jn}_{cn}_generic_kernel", n, 20, time_pass(st, prob, [0.0] * 6, steps=10, warm=10))
+            else:  # fp64 compute opted into the common-denominator form
+                prob = capi.make_problem(capi.MODEL_PINHOLE, jac, cd, consts=consts, flags=capi.FLAG_STABLE_FD)
+                report(f"camera50M_{jn}_{cn}_stable_fd", n, 20, time_pass(st, prob, [0.0] * 6, steps=10, warm=10))
     prob = capi.make_problem(capi.MODEL_PINHOLE, capi.JAC_CENTRAL, capi.F64, consts=consts)
     r, dt = lm_time([st], [prob], [0.0] * 6, max_iterations=50)
     print(json.dumps({"case": "camera50M_lm_central_f64", "status": r.status, "iters": r.executed_iterations,
@@ -114,6 +117,9 @@ if section("camera15"):
             if cd == capi.F32:
                 prob = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, jac, cd, consts=C44, flags=capi.FLAG_GENERIC_KERNEL)
                 report(f"camera15_50M_{jn}_{cn}_generic_kernel", n, 20, time_pass(st, prob, x15 * 0.999, steps=5, warm=3))
+            else:
+                prob = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, jac, cd, consts=C44, flags=capi.FLAG_STABLE_FD)
+                report(f"camera15_50M_{jn}_{cn}_stable_fd", n, 20, time_pass(st, prob, x15 * 0.999, steps=5, warm=3))
     x0 = x15.copy()
     x0[:6] = 0.0
     x0[6:10] *= 1.02

@@ -112,6 +112,22 @@ def test_wide_fp32_common_denominator_differences(env, jac):
     st.close()
 
 
+@pytest.mark.parametrize("jac", [1, 2])
+@pytest.mark.parametrize("n,dtype", [(33, 1), (4097, 1), (50_000, 0)])
+def test_wide_fp64_stable_fd_opt_in(env, jac, n, dtype):
+    """MOPT_FLAG_STABLE_FD on the n x n case: fp64 compute in the common-denominator form against the oracle, with
+    the same tolerance model as the literal form (per-entry scale + the literal quotient's rounding floor)."""
+    capi, ctx = env
+    st, Cm = make_store(capi, ctx, n, dtype)
+    pts, pix = st.download(0), st.download(1)
+    x = X_GT * (1.0 + 0.01 * np.cos(np.arange(15)))
+    prob = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, jac, capi.F64, consts=Cm, flags=capi.FLAG_STABLE_FD)
+    H, b, s = ctx.linearize(st, prob, x)
+    Ho, bo, so = orc.linearize(orc.Cost(orc.PINHOLE_DISTORT, 15, 2, n, a=pts, b=pix, consts=Cm, jac_mode=jac), x)
+    assert_close_fd(H, b, s, Ho, bo, so, x, n)
+    st.close()
+
+
 def test_wide_fp32_lm_recovers_all_parameters(env):
     """LM entirely on the fp32 throughput path (fp32 store and residual/Jacobian arithmetic; fp64 sums and solve)
     recovers the generating parameters, including the distortion coefficients the per-residual float Jacobian
