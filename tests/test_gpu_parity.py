@@ -249,7 +249,7 @@ def test_camera_fp32_common_denominator_differences(ctx, jac, x, tol):
 def test_camera_fp64_stable_fd_opt_in(ctx, jac, store_dtype):
     """MOPT_FLAG_STABLE_FD: the fp64-compute camera finite differences in the common-denominator form.  Same quotient
     as the literal default (which the oracle restates); the two differ by the literal form's subtraction rounding,
-    eps_f64 * 640 px / h_j per entry, so they agree like any two fp64 evaluations of a finite difference (1e-6)."""
+    eps_f64 * 640 px / h_j per entry, so they agree like any two fp64 evaluations of a finite difference (a few 1e-6 here)."""
     n = 50_000
     pts, pix, consts, _ = synthetic_camera(n)
     st = capi.Store(ctx, capi.MODEL_PINHOLE, n, store_dtype)
@@ -261,8 +261,9 @@ def test_camera_fp64_stable_fd_opt_in(ctx, jac, store_dtype):
         Hl, bl, sl = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE, jac, capi.F64, consts=consts), x)
         Ho, bo, so = orc.linearize(orc.Cost(orc.PINHOLE, 6, 2, n, a=pts, b=pix, consts=consts, jac_mode=jac), x)
         assert ss == sl and abs(ss - so) <= 1e-10 * so
-        assert rel_err(Hl, Ho) < 1e-6 and rel_err(bl, bo) < 1e-6
-        assert rel_err(Hs, Ho) < 1e-6 and rel_err(bs, bo) < 1e-6, (rel_err(Hs, Ho), rel_err(bs, bo))
+        # two literal evaluations (device, oracle) already differ by that rounding: 1.7e-6 at x = 0, forward
+        assert rel_err(Hl, Ho) < 5e-6 and rel_err(bl, bo) < 5e-6, (rel_err(Hl, Ho), rel_err(bl, bo))
+        assert rel_err(Hs, Ho) < 5e-6 and rel_err(bs, bo) < 5e-6, (rel_err(Hs, Ho), rel_err(bs, bo))
     r = ctx.lm_minimize([st], [capi.make_problem(capi.MODEL_PINHOLE, jac, capi.F64, consts=consts,
                                                  flags=capi.FLAG_STABLE_FD)], [0.0] * 6, max_iterations=50)
     ro = orc.lm_minimize([orc.Cost(orc.PINHOLE, 6, 2, n, a=pts, b=pix, consts=consts, jac_mode=jac, cost_threads=8)],
