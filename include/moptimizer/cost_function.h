@@ -39,6 +39,10 @@ class CostFunctionBase {
   /// with so3::Exp/Log instead of adding delta (the reference's "TODO Manifold operation"); Jacobians are then
   /// taken in the tangent space (use the MOPT_P2P_LEFT variant for analytical point2point).
   inline void setManifold(int manifold) { manifold_ = manifold; }
+  /// New (opt-in): mopt_problem_flags for the device pass, e.g. MOPT_FLAG_STABLE_FD (double: finite differences of
+  /// the camera models over a common denominator) or MOPT_FLAG_GENERIC_KERNEL (always the per-residual quotient of
+  /// linearization.h:97-111).  0 by default.
+  inline void setKernelFlags(int flags) { kernel_flags_ = flags; }
 
   virtual void update(const Scalar* x) { model_->update(x); }
   virtual Scalar computeCost(const Scalar* x) = 0;
@@ -63,6 +67,7 @@ class CostFunctionBase {
     p->jacobian = jacobian;
     p->compute_dtype = device::dtypeOf<Scalar>();
     p->manifold = manifold_;
+    p->flags = kernel_flags_;
     int loss_kind = MOPT_LOSS_NONE;
     double loss_parameter = 0.0;
     if (!loss_function_ || !loss_function_->deviceLoss(&loss_kind, &loss_parameter))
@@ -89,6 +94,7 @@ class CostFunctionBase {
 
   int num_residuals_;
   int manifold_ = MOPT_MANIFOLD_ADDITIVE;
+  int kernel_flags_ = 0;
   ModelPtr model_;
   LossFunctionPtr loss_function_;
   covariance::MatrixPtr<Scalar> covariance_;

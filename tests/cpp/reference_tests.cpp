@@ -139,6 +139,19 @@ TEST(CameraCalibration, BadWeather) {
   for (int i = 0; i < 6; ++i) EXPECT_NEAR(x0[i], fx("camera_ceres")[i], 5e-5);
 }
 
+// The same known answer through the opt-in common-denominator finite differences (setKernelFlags; new API).
+TEST(CameraCalibration, GoodWeatherStableFiniteDifferences) {
+  CameraFixture f;
+  f.cost->setKernelFlags(MOPT_FLAG_STABLE_FD);
+  double x0[6] = {0};
+  f.optimizer.minimize(x0);
+  for (int i = 0; i < 6; ++i) EXPECT_NEAR(x0[i], fx("camera_ceres")[i], 5e-5);
+  CameraFixture g;  // and the literal default reaches the same point
+  double x1[6] = {0};
+  g.optimizer.minimize(x1);
+  for (int i = 0; i < 6; ++i) EXPECT_NEAR(x0[i], x1[i], 1e-6);
+}
+
 // ----------------------------------- tst/simple_model.cpp:28-82, tst/loss_function.cpp:45-60 (float) ----
 namespace {
 struct SimpleModelFixture {
