@@ -505,6 +505,8 @@ int mopt_ctx_destroy(mopt_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
+  (void)cudaGetLastError();  // teardown of a half-built context (bad device id) must not leave an error behind for
+                             // the next launch check of another context
   return MOPT_OK;
 }
 
