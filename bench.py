@@ -413,7 +413,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if args.strong_total else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "point2point 100M correspondences/GPU, analytical Jacobian + Huber(k=0.05), x0=0",
+            "config": {"workload": f"point2point {n / 1e6:.0f}M correspondences/GPU, analytical Jacobian + Huber(k=0.05), x0=0",
                        "n_per_gpu": n, "n_total": n_total, "store": "fp32 planar (SoA) streams, 24 B/correspondence",
                        "accumulate": "fp32 partials folded into fp64 every 64 residuals/thread",
                        "prewarm_steps": args.prewarm_steps,
