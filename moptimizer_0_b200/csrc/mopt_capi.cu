@@ -266,9 +266,20 @@ PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate
 
 // `push`: this pass completes the rank-local result (last cost term), so its last CTA also pushes the packed
 // result to every peer when the NVLink exchange is open.
+// Host-driven passes of the analytical point2point model carry x into the kernel, which runs setup(x) itself
+// (PassArgs::fused_setup): the step is one kernel instead of setup kernel + pass kernel.
+bool can_fuse_setup(const mopt_problem* p) {
+  return p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL &&
+         p->manifold == MOPT_MANIFOLD_ADDITIVE;
+}
+
 int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int slot, int accumulate, int mode_override,
-                bool push) {
+                bool push, const XArg* fused_x = nullptr) {
   PassArgs a = make_args(ctx, st, slot, accumulate, mode_override);
+  if (fused_x) {
+    a.fused_setup = 1;
+    a.x = *fused_x;
+  }
   if (push && ctx->world > 1 && ctx->peers_open && ctx->exchange_enabled) {
     for (int r = 0; r < ctx->world; ++r) a.peer.base[r] = ctx->peer_base[r];
     a.peer.world = ctx->world;
@@ -337,11 +348,15 @@ int enqueue_pass(mopt_ctx* ctx, mopt_store* st, const mopt_problem* p, const dou
     MOPT_REQUIRE(x != nullptr, "null parameter vector");
     for (int i = 0; i < P; ++i) xa.v[i] = x[i];
   }
-  setup_kernel<<<1, 32, 0, ctx->stream>>>(&ctx->d_slots[0], xa);
-  MOPT_CUDA_TRY(cudaGetLastError());
-  if (user_model_has_setup(p->model))
-    MOPT_TRY(launch_user_setup(ctx->stream, ctx->device, p->model, &ctx->d_slots[0], nullptr, xa.v, P));
-  MOPT_TRY(launch_pass(ctx, st, p, 0, 0, mode, true));
+  if (can_fuse_setup(p)) {
+    MOPT_TRY(launch_pass(ctx, st, p, 0, 0, mode, true, &xa));
+  } else {
+    setup_kernel<<<1, 32, 0, ctx->stream>>>(&ctx->d_slots[0], xa);
+    MOPT_CUDA_TRY(cudaGetLastError());
+    if (user_model_has_setup(p->model))
+      MOPT_TRY(launch_user_setup(ctx->stream, ctx->device, p->model, &ctx->d_slots[0], nullptr, xa.v, P));
+    MOPT_TRY(launch_pass(ctx, st, p, 0, 0, mode, true));
+  }
   MOPT_TRY(allreduce_trial(ctx, P, mode));
   return MOPT_OK;
 }

@@ -7,6 +7,7 @@
 #pragma once
 
 #include "mopt_common.cuh"
+#include "mopt_setup.cuh"
 
 namespace mopt {
 
@@ -45,6 +46,11 @@ struct PassArgs {
   int mode_override;
   int masked;                // 1: a NaN in the first B-group stream marks "no correspondence" (model f returned
                              // false, linearization.h:102,144): the residual is skipped entirely
+  // Host-driven point2point analytical passes (mopt_linearize & co): model->setup(x) runs INSIDE the pass kernel —
+  // every CTA derives (R, t) from x itself and the last CTA derives the affine Jacobian pieces — instead of in a
+  // one-warp kernel launched before it (6.8 us + a dependent-launch gap per step).  `pb` is then not read.
+  int fused_setup;
+  XArg x;
 };
 
 #ifdef __CUDACC__
@@ -209,8 +215,43 @@ __device__ __forceinline__ void p2p_cost_only(bool masked, const CT (&R)[9], con
   acc[22] += (masked && (yx != yx)) ? CT(0) : e2;
 }
 
+// ---- model->setup(x) fused into the pass (PassArgs::fused_setup) -------------------------------------------
+// Set 0 of the point2point model, exactly as setup_cost / setup_one_set (mopt_setup.cuh) build it.
+static __device__ __noinline__ void p2p_fused_set0(const CostDev* c, const double* x, double* set) {
+  const bool f32 = (c->compute_dtype == MOPT_F32);
+  double xs[6];
+  for (int i = 0; i < 6; ++i) xs[i] = f32 ? double(float(x[i])) : x[i];
+  const double w[3] = {xs[3], xs[4], xs[5]};
+  double R[9];
+  if (f32) so3_exp_dev<float>(w, R); else so3_exp_dev<double>(w, R);
+  for (int i = 0; i < 9; ++i) set[i] = R[i];
+  set[9] = xs[0]; set[10] = xs[1]; set[11] = xs[2];
+}
+// J_l(omega) for the exact variant, identity otherwise (first lines of setup_p2p_affine).
+static __device__ __noinline__ void p2p_fused_left_jacobian(const CostDev* c, const double* x, double* Jl) {
+  for (int i = 0; i < 9; ++i) Jl[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if (c->variant == MOPT_P2P_EXACT) {
+    const double w[3] = {x[3], x[4], x[5]};
+    so3_left_jacobian_dev(w, Jl);
+  }
+}
+// One entry of J(q) = J0 + q_x J1 + q_y J2 + q_z J3 (setup_p2p_affine, same summation order).
+__device__ inline double p2p_affine_entry(int variant, const double* Jl, int k, int idx) {
+  int r = idx / 6, col = idx % 6;
+  if (variant == MOPT_P2P_REFTEST_COLMAJOR) {  // tst/point2point.cpp:18,71 (see setup_p2p_affine)
+    const int cc = idx / 3, rr = idx % 3;
+    r = rr; col = cc;
+  }
+  if (k == 0) return (col < 3 && r == col) ? 1.0 : 0.0;
+  if (col < 3) return 0.0;
+  const double E[3][9] = {{0, 0, 0, 0, 0, 1, 0, -1, 0}, {0, 0, -1, 0, 0, 0, 1, 0, 0}, {0, 1, 0, -1, 0, 0, 0, 0, 0}};
+  double s = 0.0;
+  for (int m = 0; m < 3; ++m) s += E[k - 1][r * 3 + m] * Jl[m * 3 + (col - 3)];
+  return s;
+}
+
 // Assemble packed (H upper, b, sum) of the 6-parameter problem from the 23 moment totals.
-__device__ inline void p2p_assemble(const double* tot, const ParamBlock* pb, const CostDev* cost, PassResult* out,
+__device__ inline void p2p_assemble(const double* tot, const double (*jaff)[18], const CostDev* cost, PassResult* out,
                                     int accumulate, int tid, int nthreads) {
   constexpr int P = 6;
   // augmented moment matrix Mt (4x4, q~ = (1, q)) and St (4x3) = sum w q~ r^T
@@ -235,14 +276,14 @@ __device__ inline void p2p_assemble(const double* tot, const ParamBlock* pb, con
         for (int l = 0; l < 4; ++l) {
           double s = 0.0;
           for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b) s += pb->jaff[k][a * 6 + i] * C[a + 3 * b] * pb->jaff[l][b * 6 + j];
+            for (int b = 0; b < 3; ++b) s += jaff[k][a * 6 + i] * C[a + 3 * b] * jaff[l][b * 6 + j];
           val += Mt[k][l] * s;
         }
     } else if (e < npk - 1) {
       const int i = e - P * (P + 1) / 2;
       for (int k = 0; k < 4; ++k)
         for (int a = 0; a < 3; ++a)
-          for (int b = 0; b < 3; ++b) val += pb->jaff[k][a * 6 + i] * C[a + 3 * b] * St[k][b];
+          for (int b = 0; b < 3; ++b) val += jaff[k][a * 6 + i] * C[a + 3 * b] * St[k][b];
     } else {
       val = tot[22];
     }
@@ -250,8 +291,9 @@ __device__ inline void p2p_assemble(const double* tot, const ParamBlock* pb, con
   }
 }
 
+// FUSED: model->setup(x) runs inside the kernel (PassArgs::x; host-driven analytical passes), `pb` is not read.
 template <typename ST, typename CT, int LOSS, bool QROT, int THREADS, int MINB, int UNROLL = 2, int FLUSH_ROUNDS = 8,
-          int PF = 0, bool SWP = false>
+          int PF = 0, bool SWP = false, bool FUSED = false>
 __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArgs a) {
   const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
   if (mode == PASS_SKIP) return;
@@ -262,11 +304,22 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
   __shared__ double s_warp[(THREADS / 32) * 32];
   __shared__ double s_tot[32];
 
+  __shared__ double s_set0[FUSED ? 12 : 1];
+  const double* set0 = FUSED ? s_set0 : a.pb->sets[0];
+  if constexpr (FUSED) {
+    if (threadIdx.x == 0) {
+      double xl[6];  // a copy: taking the address of a kernel parameter would spill the whole PassArgs to local memory
+#pragma unroll
+      for (int i = 0; i < 6; ++i) xl[i] = a.x.v[i];
+      p2p_fused_set0(a.cost, xl, s_set0);
+    }
+    __syncthreads();
+  }
   CT R[9], t[3];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = CT(a.pb->sets[0][i]);
+  for (int i = 0; i < 9; ++i) R[i] = CT(set0[i]);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) t[i] = CT(a.pb->sets[0][9 + i]);
+  for (int i = 0; i < 3; ++i) t[i] = CT(set0[9 + i]);
   const CT lossp = CT(a.cost->loss_param);
   const bool masked = a.masked != 0;
 
@@ -418,7 +471,22 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
       a.out->v[e] = a.accumulate ? a.out->v[e] + s_tot[22] : s_tot[22];
     }
   } else {
-    p2p_assemble(s_tot, a.pb, a.cost, a.out, a.accumulate, threadIdx.x, THREADS);
+    __shared__ double s_jl[FUSED ? 9 : 1];
+    __shared__ double s_jaff[FUSED ? 4 : 1][18];
+    const double(*jaff)[18] = FUSED ? s_jaff : a.pb->jaff;
+    if constexpr (FUSED) {
+      // the affine pieces of J, entry by entry (same sums, same order as setup_p2p_affine)
+      if (threadIdx.x == 0) {
+        double xl[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xl[i] = a.x.v[i];
+        p2p_fused_left_jacobian(a.cost, xl, s_jl);
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < 4 * 18; i += THREADS) s_jaff[i / 18][i % 18] = p2p_affine_entry(a.cost->variant, s_jl, i / 18, i % 18);
+      __syncthreads();
+    }
+    p2p_assemble(s_tot, jaff, a.cost, a.out, a.accumulate, threadIdx.x, THREADS);
   }
   peer_push(a, packed_size(6));
 }

@@ -32,15 +32,21 @@ struct ShapeF64 {
   static constexpr int THREADS = 256, MINB = 2, UNROLL = 2, FLUSH = 8;
 };
 
-template <typename ST, typename CT, int LOSS, bool QROT, class S>
-int launch_one(const PassLaunch& L, const PassArgs& a) {
-  auto kern = p2p_moment_kernel<ST, CT, LOSS, QROT, S::THREADS, S::MINB, S::UNROLL, S::FLUSH>;
+template <typename ST, typename CT, int LOSS, bool QROT, class S, bool FUSED>
+int launch_fused(const PassLaunch& L, const PassArgs& a) {
+  auto kern = p2p_moment_kernel<ST, CT, LOSS, QROT, S::THREADS, S::MINB, S::UNROLL, S::FLUSH, 0, false, FUSED>;
   const int64_t groups = a.n / VecOf<ST>::N;
   // small problems: keep CTAs at 256 threads' worth of work granularity by capping the grid, never below 1
   const int grid = pick_grid(reinterpret_cast<const void*>(kern), S::THREADS, L, groups);
   kern<<<grid, S::THREADS, 0, L.stream>>>(a);
   MOPT_CUDA_TRY(cudaGetLastError());
   return MOPT_OK;
+}
+
+// PassArgs::fused_setup (host-driven analytical passes): the instantiation that runs model->setup(x) itself
+template <typename ST, typename CT, int LOSS, bool QROT, class S>
+int launch_one(const PassLaunch& L, const PassArgs& a) {
+  return a.fused_setup ? launch_fused<ST, CT, LOSS, QROT, S, true>(L, a) : launch_fused<ST, CT, LOSS, QROT, S, false>(L, a);
 }
 
 template <typename ST, typename CT, class S>
