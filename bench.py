@@ -427,12 +427,12 @@ def run_ours(args):
                          "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                          "achieved_from": "24 B x n_per_gpu / (CUDA-event time of the K timed steps / K) on the "
-                                          "context's stream; a step = setup kernel (~3 us) + this kernel",
-                         "kernel": "p2p_moment_kernel<float,float,HUBER,QROT>",
+                                          "context's stream; a step = this kernel alone (model->setup(x) runs inside it)",
+                         "kernel": "p2p_moment_kernel<float,float,HUBER,QROT,...,FUSED>",
                          "algorithmic_bytes_per_launch": BYTES_PER_RES * n},
             "clocks": sampler.summary(),
-            # per step: setup kernel + pass kernel (+ NCCL's kernel or the separate consumer kernel when selected)
-            "gpu_launches": (2 + (1 if world > 1 and (collective == "nccl" or os.environ.get("MOPT_PEER_CONSUMER") == "kernel") else 0)) * args.steps,
+            # per step: the pass kernel (setup fused in) (+ NCCL's kernel or the separate consumer kernel when selected)
+            "gpu_launches": (1 + (1 if world > 1 and (collective == "nccl" or os.environ.get("MOPT_PEER_CONSUMER") == "kernel") else 0)) * args.steps,
             "check": {"sum_rtr": s, "H00": float(H[0, 0]), "b0": float(b[0])},
         }
         if local_ms is not None:
