@@ -427,12 +427,14 @@ def run_ours(args):
                          "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                          "achieved_from": "24 B x n_per_gpu / (CUDA-event time of the K timed steps / K) on the "
-                                          "context's stream; a step = this kernel alone (model->setup(x) runs inside it)",
+                                          "context's stream; a step = this kernel alone (model->setup(x) runs inside it; sharded contexts "
+                                          "launch the one-warp setup kernel before it)",
                          "kernel": "p2p_moment_kernel<float,float,HUBER,QROT,...,FUSED>",
                          "algorithmic_bytes_per_launch": BYTES_PER_RES * n},
             "clocks": sampler.summary(),
-            # per step: the pass kernel (setup fused in) (+ NCCL's kernel or the separate consumer kernel when selected)
-            "gpu_launches": (1 + (1 if world > 1 and (collective == "nccl" or os.environ.get("MOPT_PEER_CONSUMER") == "kernel") else 0)) * args.steps,
+            # per step: the pass kernel with setup fused in (single GPU) or setup kernel + pass kernel (sharded contexts)
+            # (+ NCCL's kernel or the separate consumer kernel when selected)
+            "gpu_launches": ((1 if world == 1 or os.environ.get("MOPT_FUSED_SETUP") == "1" else 2) + (1 if world > 1 and (collective == "nccl" or os.environ.get("MOPT_PEER_CONSUMER") == "kernel") else 0)) * args.steps,
             "check": {"sum_rtr": s, "H00": float(H[0, 0]), "b0": float(b[0])},
         }
         if local_ms is not None:

@@ -268,7 +268,17 @@ PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate
 // result to every peer when the NVLink exchange is open.
 // Host-driven passes of the analytical point2point model carry x into the kernel, which runs setup(x) itself
 // (PassArgs::fused_setup): the step is one kernel instead of setup kernel + pass kernel.
-bool can_fuse_setup(const mopt_problem* p) {
+// Single-GPU contexts only by default: with the peer exchange in the same kernel the first 2-GPU measurement of the
+// fused form came out slower in lock step (0.403 vs 0.382 ms per step on another box, rank-local time unchanged),
+// so sharded contexts keep the measured two-kernel sequence unless MOPT_FUSED_SETUP=1 asks for the A/B
+// (MOPT_FUSED_SETUP=0 switches the fusion off everywhere).
+bool can_fuse_setup(const mopt_ctx* ctx, const mopt_problem* p) {
+  static const int env = [] {
+    const char* e = getenv("MOPT_FUSED_SETUP");
+    return e ? (e[0] == '0' ? 0 : 1) : -1;
+  }();
+  if (env == 0) return false;
+  if (ctx->world > 1 && env != 1) return false;
   return p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL &&
          p->manifold == MOPT_MANIFOLD_ADDITIVE;
 }
@@ -348,7 +358,7 @@ int enqueue_pass(mopt_ctx* ctx, mopt_store* st, const mopt_problem* p, const dou
     MOPT_REQUIRE(x != nullptr, "null parameter vector");
     for (int i = 0; i < P; ++i) xa.v[i] = x[i];
   }
-  if (can_fuse_setup(p)) {
+  if (can_fuse_setup(ctx, p)) {
     MOPT_TRY(launch_pass(ctx, st, p, 0, 0, mode, true, &xa));
   } else {
     setup_kernel<<<1, 32, 0, ctx->stream>>>(&ctx->d_slots[0], xa);
