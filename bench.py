@@ -434,7 +434,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             # per step: the pass kernel with setup fused in (single GPU) or setup kernel + pass kernel (sharded contexts)
             # (+ NCCL's kernel or the separate consumer kernel when selected)
-            "gpu_launches": ((1 if world == 1 or os.environ.get("MOPT_FUSED_SETUP") == "1" else 2) + (1 if world > 1 and (collective == "nccl" or os.environ.get("MOPT_PEER_CONSUMER") == "kernel") else 0)) * args.steps,
+            "gpu_launches": ((1 if world == 1 or os.environ.get("MOPT_FUSED_SETUP", "")[:1] not in ("", "0") else 2) + (1 if world > 1 and (collective == "nccl" or os.environ.get("MOPT_PEER_CONSUMER") == "kernel") else 0)) * args.steps,
             "check": {"sum_rtr": s, "H00": float(H[0, 0]), "b0": float(b[0])},
         }
         if local_ms is not None:

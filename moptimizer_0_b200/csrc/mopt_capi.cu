@@ -275,7 +275,7 @@ PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate
 bool can_fuse_setup(const mopt_ctx* ctx, const mopt_problem* p) {
   static const int env = [] {
     const char* e = getenv("MOPT_FUSED_SETUP");
-    return e ? (e[0] == '0' ? 0 : 1) : -1;
+    return (e && e[0]) ? (e[0] == '0' ? 0 : 1) : -1;
   }();
   if (env == 0) return false;
   if (ctx->world > 1 && env != 1) return false;
