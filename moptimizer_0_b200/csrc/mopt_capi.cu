@@ -268,10 +268,10 @@ PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate
 // result to every peer when the NVLink exchange is open.
 // Host-driven passes of the analytical point2point model carry x into the kernel, which runs setup(x) itself
 // (PassArgs::fused_setup): the step is one kernel instead of setup kernel + pass kernel.
-// Single-GPU contexts only by default: with the peer exchange in the same kernel the first 2-GPU measurement of the
-// fused form came out slower in lock step (0.403 vs 0.382 ms per step on another box, rank-local time unchanged),
-// so sharded contexts keep the measured two-kernel sequence unless MOPT_FUSED_SETUP=1 asks for the A/B
-// (MOPT_FUSED_SETUP=0 switches the fusion off everywhere).
+// Single-GPU contexts only by default: at 2 GPUs in lock step the A/B (scripts/fused_setup_ab.sh,
+// profiles/r1_fused_setup_ab_n2.txt: fused 0.390 / 0.384 ms, two kernels 0.385 / 0.395 ms per step) shows no
+// difference beyond that box's run-to-run spread, so sharded contexts keep the two-kernel sequence the 4- and
+// 8-GPU numbers were measured with.  MOPT_FUSED_SETUP=1 fuses there too, MOPT_FUSED_SETUP=0 never fuses.
 bool can_fuse_setup(const mopt_ctx* ctx, const mopt_problem* p) {
   static const int env = [] {
     const char* e = getenv("MOPT_FUSED_SETUP");
