@@ -1,5 +1,6 @@
-// moptimizer::Exception — what the reference throws for API misuse (include/moptimizer/exception.h:7-19).  Here it
-// also carries the C-ABI status of the call that failed, so a caller can tell a bad argument from a CUDA failure.
+// moptimizer::Exception — what the reference throws for API misuse (include/moptimizer/exception.h:7-19: a
+// std::exception constructible from a C string or a std::string whose what() returns that text).  Here it also
+// carries the C-ABI status of the call that failed, so a caller can tell a bad argument from a CUDA failure.
 #pragma once
 
 #include <exception>
@@ -9,16 +10,15 @@
 namespace moptimizer {
 
 class Exception : public std::exception {
- public:
-  explicit Exception(std::string message, int status = 0) : msg_(std::move(message)), status_(status) {}
-  explicit Exception(const char* message, int status = 0) : msg_(message ? message : ""), status_(status) {}
-  const char* what() const noexcept override { return msg_.c_str(); }
-  /// mopt_status of the C-ABI call behind this exception, 0 when it was raised by the C++ layer itself.
-  int status() const noexcept { return status_; }
+  std::string text_;  // returned by what()
+  int code_ = 0;      // mopt_status of the C-ABI call behind this exception; 0: raised by the C++ layer itself
 
- protected:
-  std::string msg_;
-  int status_;
+ public:
+  explicit Exception(std::string message, int status = 0) : text_(std::move(message)), code_(status) {}
+  explicit Exception(const char* message, int status = 0) : Exception(std::string(message ? message : ""), status) {}
+
+  const char* what() const noexcept override { return text_.c_str(); }
+  int status() const noexcept { return code_; }
 };
 
 }  // namespace moptimizer

@@ -6,25 +6,23 @@
 
 namespace moptimizer::loss {
 
-template <typename T>
-class GemmanMCClure : public ILossFunction<T> {
- public:
-  using Ptr = std::shared_ptr<GemmanMCClure>;
-  explicit GemmanMCClure(T threshold) : threshold_(threshold) {}
+template <typename T> struct GemmanMCClure : ILossFunction<T> {
+  typedef std::shared_ptr<GemmanMCClure> Ptr;
+
+  explicit GemmanMCClure(T threshold) : th_(threshold) {}
+  T threshold() const { return th_; }
 
   T weight(T errorSquaredNorm) override {
-    const T shifted = errorSquaredNorm + threshold_;
-    return (threshold_ * threshold_) / (shifted * shifted);
+    const T shifted = errorSquaredNorm + th_;
+    return (th_ * th_) / (shifted * shifted);
   }
   bool deviceLoss(int* kind, double* parameter) const override {
-    *kind = MOPT_LOSS_GEMAN_MCCLURE;
-    *parameter = double(threshold_);
+    *kind = MOPT_LOSS_GEMAN_MCCLURE, *parameter = double(th_);
     return true;
   }
-  T threshold() const { return threshold_; }
 
  private:
-  T threshold_;
+  T th_;
 };
 
 }  // namespace moptimizer::loss

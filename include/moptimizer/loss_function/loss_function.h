@@ -10,34 +10,27 @@
 
 namespace moptimizer::loss {
 
-template <typename T>
-class ILossFunction {
- public:
-  using Ptr = std::shared_ptr<ILossFunction>;
-  using ConstPtr = std::shared_ptr<const ILossFunction>;
-
-  ILossFunction() = default;
-  virtual ~ILossFunction() = default;
+template <typename T> struct ILossFunction {
+  typedef std::shared_ptr<ILossFunction> Ptr;
+  typedef std::shared_ptr<const ILossFunction> ConstPtr;
 
   /// w(e2) applied to J^T C J and J^T C r (linearization.h:112-115,149-152); host copy kept for API parity.
   virtual T weight(T errorSquaredNorm) = 0;
 
   /// Kernel-side kind and parameter of this loss; false = not implemented on the device.
-  virtual bool deviceLoss(int* kind, double* parameter) const {
-    (void)kind;
-    (void)parameter;
-    return false;
-  }
+  virtual bool deviceLoss(int* /*kind*/, double* /*parameter*/) const { return false; }
+
+  virtual ~ILossFunction() {}
+
+ protected:
+  ILossFunction() {}
 };
 
 /// w = 1 (loss_function.h:20-23).
-template <typename T>
-class NoLoss : public ILossFunction<T> {
- public:
+template <typename T> struct NoLoss final : ILossFunction<T> {
   T weight(T) override { return T(1); }
   bool deviceLoss(int* kind, double* parameter) const override {
-    *kind = MOPT_LOSS_NONE;
-    *parameter = 0.0;
+    *kind = MOPT_LOSS_NONE, *parameter = 0.0;
     return true;
   }
 };
