@@ -9,6 +9,7 @@
 #pragma once
 
 #include <cstring>
+#include <stdexcept>
 #include <vector>
 
 #include "moptimizer/device/context.h"

@@ -58,3 +58,45 @@ def test_affine_fd_model_hooks_host_only(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     print(r.stdout)
     assert r.returncode == 0, r.stdout
+
+
+def _build_example(tmp_path):
+    exe = str(tmp_path / "p2p_example")
+    src = os.path.join(ROOT, "examples", "point2point_registration.cpp")
+    pkg = os.path.join(ROOT, "moptimizer_0_b200")
+    build_cpp_tests()  # makes sure libmopt_b200.so exists
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-L", pkg,
+                    "-lmopt_b200", "-Wl,-rpath," + pkg, "-o", exe], check=True)
+    return exe
+
+
+def test_public_headers_are_self_contained(tmp_path):
+    """Every header under include/ compiles on its own (-Wall -Werror): a user of the reference includes them one by one."""
+    inc = os.path.join(ROOT, "include")
+    for d, _, files in os.walk(inc):
+        for f in files:
+            if f.endswith(".h"):
+                rel = os.path.relpath(os.path.join(d, f), inc)
+                tu = tmp_path / "hdr.cpp"
+                tu.write_text("#include <%s>\nint main() { return 0; }\n" % rel)
+                r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(tu)],
+                                   capture_output=True, text=True)
+                assert r.returncode == 0, rel + "\n" + r.stderr[:2000]
+
+
+def test_integration_example_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """examples/point2point_registration.cpp is the INTEGRATION.md snippet as a program."""
+    import torch
+    exe = _build_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked test")
+    r = subprocess.run([exe, "1000"], capture_output=True, text=True)
+    assert r.returncode == 77 and "moptimizer::Exception" in r.stdout
+
+
+@pytest.mark.gpu
+def test_integration_example_runs_on_gpu(tmp_path):
+    exe = _build_example(tmp_path)
+    r = subprocess.run([exe, "200000"], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
