@@ -57,6 +57,28 @@ int main(void) { printf("%zu %zu %zu %zu %zu\n", sizeof(mopt_problem), sizeof(mo
                      ctypes.sizeof(capi.LmReport), ctypes.sizeof(capi.Synth)]
 
 
+def test_header_is_plain_c99_and_enums_match_the_python_binding(tmp_path):
+    """The boundary is a C ABI: the header must compile as strict C99, and the enum values the ctypes binding
+    hard-codes must be the header's."""
+    import subprocess
+    from moptimizer_0_b200 import capi
+    names = ["MOPT_F32", "MOPT_F64", "MOPT_MODEL_POINT2POINT", "MOPT_MODEL_PINHOLE_DISTORT", "MOPT_JAC_CENTRAL",
+             "MOPT_P2P_LEFT", "MOPT_MANIFOLD_SO3_LEFT", "MOPT_LOSS_HUBER", "MOPT_FLAG_GENERIC_KERNEL",
+             "MOPT_FLAG_STABLE_FD", "MOPT_MAX_PARAMETERS", "MOPT_MAX_OUTPUTS", "MOPT_MAX_COSTS", "MOPT_MAX_TRACE",
+             "MOPT_NCCL_ID_BYTES"]
+    c = tmp_path / "e.c"
+    c.write_text('#include <stdio.h>\n#include "mopt_capi.h"\nint main(void) { printf("' + " ".join(["%d"] * len(names)) +
+                 '\\n", ' + ", ".join("(int)" + n for n in names) + "); return 0; }\n")
+    exe = str(tmp_path / "e")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(c), "-o", exe], check=True)
+    vals = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert vals == [capi.F32, capi.F64, capi.MODEL_POINT2POINT, capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL,
+                    capi.P2P_LEFT, capi.MANIFOLD_SO3_LEFT, capi.LOSS_HUBER, capi.FLAG_GENERIC_KERNEL,
+                    capi.FLAG_STABLE_FD, capi.MAX_PARAMETERS, capi.MAX_OUTPUTS, capi.MAX_COSTS, capi.MAX_TRACE,
+                    capi.NCCL_ID_BYTES]
+
+
 def test_no_cuda_device_is_a_loud_error(libpath):
     from moptimizer_0_b200 import capi
     import torch
