@@ -444,13 +444,14 @@ extern "C" {
 const char* mopt_last_error(void) { return g_last_error.c_str(); }
 const char* mopt_version(void) { return "moptimizer_0_b200 0.1 (sm_100a)"; }
 
-int mopt_device_count(int* count) {
+int mopt_device_count(int* count) try {
   MOPT_REQUIRE(count, "null count");
   MOPT_CUDA_TRY(cudaGetDeviceCount(count));
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_ctx_create(int device, mopt_ctx** out) {
+int mopt_ctx_create(int device, mopt_ctx** out) try {
   MOPT_REQUIRE(out, "null out");
   mopt_ctx* ctx = new mopt_ctx();
   ctx->device = device;
@@ -462,8 +463,9 @@ int mopt_ctx_create(int device, mopt_ctx** out) {
   *out = ctx;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_comm_unique_id(void* out_id) {
+int mopt_comm_unique_id(void* out_id) try {
   MOPT_REQUIRE(out_id, "null out_id");
   if (!nccl().ok) {
     set_last_error(nccl().why);
@@ -474,8 +476,9 @@ int mopt_comm_unique_id(void* out_id) {
   std::memcpy(out_id, &id, MOPT_NCCL_ID_BYTES);
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_ctx_create_sharded(int device, int rank, int world_size, const void* nccl_unique_id, mopt_ctx** out) {
+int mopt_ctx_create_sharded(int device, int rank, int world_size, const void* nccl_unique_id, mopt_ctx** out) try {
   MOPT_REQUIRE(out, "null out");
   MOPT_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "bad rank/world_size");
   MOPT_REQUIRE(world_size <= kMaxWorld, "at most 8 ranks (one box) are supported");
@@ -504,8 +507,9 @@ int mopt_ctx_create_sharded(int device, int rank, int world_size, const void* nc
   }
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_ctx_destroy(mopt_ctx* ctx) {
+int mopt_ctx_destroy(mopt_ctx* ctx) try {
   if (!ctx) return MOPT_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -534,8 +538,9 @@ int mopt_ctx_destroy(mopt_ctx* ctx) {
                              // the next launch check of another context
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_ctx_peer_handle(mopt_ctx* ctx, void* out_handle) {
+int mopt_ctx_peer_handle(mopt_ctx* ctx, void* out_handle) try {
   MOPT_REQUIRE(ctx && out_handle, "null argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == MOPT_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t size");
   MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -544,8 +549,9 @@ int mopt_ctx_peer_handle(mopt_ctx* ctx, void* out_handle) {
   std::memcpy(out_handle, &h, sizeof(h));
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_ctx_open_peers(mopt_ctx* ctx, const void* handles) {
+int mopt_ctx_open_peers(mopt_ctx* ctx, const void* handles) try {
   MOPT_REQUIRE(ctx && handles, "null argument");
   MOPT_REQUIRE(ctx->world > 1, "not a sharded context");
   MOPT_REQUIRE(!ctx->peers_open, "peers already open");
@@ -566,65 +572,74 @@ int mopt_ctx_open_peers(mopt_ctx* ctx, const void* handles) {
   ctx->fused_consumer = !(mode && std::string(mode) == "kernel");
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_ctx_set_exchange_enabled(mopt_ctx* ctx, int enabled) {
+int mopt_ctx_set_exchange_enabled(mopt_ctx* ctx, int enabled) try {
   MOPT_REQUIRE(ctx, "null ctx");
   ctx->exchange_enabled = enabled != 0;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_ctx_synchronize(mopt_ctx* ctx) {
+int mopt_ctx_synchronize(mopt_ctx* ctx) try {
   MOPT_REQUIRE(ctx, "null ctx");
   MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
   MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_ctx_stream(mopt_ctx* ctx, uint64_t* out_stream) {
+int mopt_ctx_stream(mopt_ctx* ctx, uint64_t* out_stream) try {
   MOPT_REQUIRE(ctx && out_stream, "null ctx/out");
   *out_stream = reinterpret_cast<uint64_t>(ctx->stream);
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_ctx_set_launch(mopt_ctx* ctx, int ctas_per_sm, int threads) {
+int mopt_ctx_set_launch(mopt_ctx* ctx, int ctas_per_sm, int threads) try {
   MOPT_REQUIRE(ctx, "null ctx");
   MOPT_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 8, "ctas_per_sm must be in [0, 8]");
   ctx->ctas_per_sm = ctas_per_sm;
   ctx->threads = threads;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
 int mopt_linearize(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x, double* H, double* b,
-                   double* sum) {
+                   double* sum) try {
   MOPT_REQUIRE(ctx && store && store->ctx == ctx, "store does not belong to this context");
   MOPT_TRY(validate_problem(store, problem, true));
   MOPT_TRY(enqueue_pass(ctx, store, problem, x, PASS_LINEARIZE));
   return fetch_result(ctx, problem->num_parameters, H, b, sum);
 }
+MOPT_ABI_CATCH
 
-int mopt_compute_cost(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x, double* sum) {
+int mopt_compute_cost(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x, double* sum) try {
   MOPT_REQUIRE(ctx && store && store->ctx == ctx, "store does not belong to this context");
   MOPT_TRY(validate_problem(store, problem, false));
   MOPT_TRY(enqueue_pass(ctx, store, problem, x, PASS_COST));
   return fetch_result(ctx, problem->num_parameters, nullptr, nullptr, sum);
 }
+MOPT_ABI_CATCH
 
-int mopt_linearize_async(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x) {
+int mopt_linearize_async(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const double* x) try {
   MOPT_REQUIRE(ctx && store && store->ctx == ctx, "store does not belong to this context");
   MOPT_TRY(validate_problem(store, problem, true));
   return enqueue_pass(ctx, store, problem, x, PASS_LINEARIZE);
 }
+MOPT_ABI_CATCH
 
-int mopt_ctx_result(mopt_ctx* ctx, int num_parameters, double* H, double* b, double* sum) {
+int mopt_ctx_result(mopt_ctx* ctx, int num_parameters, double* H, double* b, double* sum) try {
   MOPT_REQUIRE(ctx, "null ctx");
   MOPT_REQUIRE(num_parameters >= 0 && num_parameters <= kMaxP, "bad num_parameters");
   MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
   return fetch_result(ctx, num_parameters, H, b, sum);
 }
+MOPT_ABI_CATCH
 
 int mopt_upload_and_linearize(mopt_ctx* ctx, mopt_store* store, const mopt_problem* problem, const void* host_a,
                               const void* host_b, int host_dtype, int64_t count, const double* x, double* H, double* b,
-                              double* sum) {
+                              double* sum) try {
   MOPT_REQUIRE(ctx && store && store->ctx == ctx, "store does not belong to this context");
   MOPT_TRY(validate_problem(store, problem, true));
   MOPT_REQUIRE(count == store->n, "count must equal the store size");
@@ -634,6 +649,7 @@ int mopt_upload_and_linearize(mopt_ctx* ctx, mopt_store* store, const mopt_probl
   MOPT_TRY(enqueue_pass(ctx, store, problem, x, PASS_LINEARIZE));
   return fetch_result(ctx, problem->num_parameters, H, b, sum);
 }
+MOPT_ABI_CATCH
 
 void mopt_lm_default_options(mopt_lm_options* o) {
   if (!o) return;
@@ -645,7 +661,7 @@ void mopt_lm_default_options(mopt_lm_options* o) {
 }
 
 int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, const mopt_problem* problems,
-                     const mopt_lm_options* options, double* x, mopt_lm_report* report) {
+                     const mopt_lm_options* options, double* x, mopt_lm_report* report) try {
   MOPT_REQUIRE(ctx && stores && problems && x && report, "null argument");
   if (n_costs <= 0) {
     // Optimizer::checkCosts, optimizer.h:48-54
@@ -756,8 +772,9 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
   std::memcpy(report->trials, hs->trials, sizeof(mopt_lm_trial) * size_t(report->num_trials));
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_so3_convert6dof(const double* x, double* T) {
+int mopt_so3_convert6dof(const double* x, double* T) try {
   MOPT_REQUIRE(x && T, "null argument");
   // src/so3.cpp:7-19,43-57 (host-side helper kept for API parity; the device copy is so3_exp_dev)
   const double w[3] = {x[3], x[4], x[5]};
@@ -782,9 +799,10 @@ int mopt_so3_convert6dof(const double* x, double* T) {
   T[15] = 1.0;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
 // Runs the DEVICE LDL^T (the one the LM step kernel uses) on one thread; for tests.
-int mopt_ldlt_solve(int n, const double* A, const double* rhs, double* out) {
+int mopt_ldlt_solve(int n, const double* A, const double* rhs, double* out) try {
   MOPT_REQUIRE(n >= 1 && n <= kMaxP && A && rhs && out, "bad argument");
   double *dA = nullptr, *dr = nullptr, *dout = nullptr;
   MOPT_CUDA_TRY(cudaMalloc(&dA, sizeof(double) * n * n));
@@ -810,16 +828,19 @@ int mopt_ldlt_solve(int n, const double* A, const double* rhs, double* out) {
   }
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_host_alloc(void** ptr, uint64_t bytes) {
+int mopt_host_alloc(void** ptr, uint64_t bytes) try {
   MOPT_REQUIRE(ptr, "null ptr");
   MOPT_CUDA_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_host_free(void* ptr) {
+int mopt_host_free(void* ptr) try {
   if (ptr) MOPT_CUDA_TRY(cudaFreeHost(ptr));
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
 }  // extern "C"

@@ -8,6 +8,8 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <exception>
+#include <new>
 #include <string>
 #else
 typedef int int32_t;
@@ -42,6 +44,21 @@ void set_last_error(const std::string& msg);
       return MOPT_ERR_INVALID_ARGUMENT;                                          \
     }                                                                            \
   } while (0)
+
+// No C++ exception may cross the C ABI: every `int mopt_*` entry point is a function-try-block closed by this.
+#define MOPT_ABI_CATCH                                                        \
+  catch (const std::bad_alloc&) {                                             \
+    ::mopt::set_last_error("out of host memory");                             \
+    return MOPT_ERR_OUT_OF_MEMORY;                                            \
+  }                                                                           \
+  catch (const std::exception& e) {                                           \
+    ::mopt::set_last_error(std::string("internal error: ") + e.what());       \
+    return MOPT_ERR_INVALID_ARGUMENT;                                         \
+  }                                                                           \
+  catch (...) {                                                               \
+    ::mopt::set_last_error("internal error: unknown exception");              \
+    return MOPT_ERR_INVALID_ARGUMENT;                                         \
+  }
 
 #define MOPT_TRY(expr)              \
   do {                              \

@@ -246,12 +246,15 @@ int build_index(mopt_nn_index* ix, const void* host, int host_dtype) {
   // cell edge: the search radius, grown until the grid has at most 2^24 cells
   double cell = ix->max_dist;
   for (;;) {
-    double total = 1.0;
-    for (int k = 0; k < 3; ++k) {
-      ix->dims[k] = int(std::floor((hi[k] - lo[k]) / cell)) + 1;
-      total *= double(ix->dims[k]);
+    double dims[3], total = 1.0;  // in double until the total is known to be small: a tiny radius over a wide
+    for (int k = 0; k < 3; ++k) {  // cloud gives per-axis counts far beyond INT_MAX
+      dims[k] = std::floor((hi[k] - lo[k]) / cell) + 1.0;
+      total *= dims[k];
     }
-    if (total <= double(1 << 24)) break;
+    if (total <= double(1 << 24)) {
+      for (int k = 0; k < 3; ++k) ix->dims[k] = int(dims[k]);
+      break;
+    }
     cell *= 1.26;
   }
   ix->cell = cell;
@@ -327,7 +330,7 @@ int enqueue_reassociate(mopt_store* st, const ParamBlock* pb, const LmState* gat
 extern "C" {
 
 int mopt_nn_index_create(mopt_ctx* ctx, const void* host_xyz, int host_dtype, int index_dtype, int64_t m,
-                         double max_distance, mopt_nn_index** out) {
+                         double max_distance, mopt_nn_index** out) try {
   MOPT_REQUIRE(ctx && out && (host_xyz || m == 0), "null argument");
   MOPT_REQUIRE(m >= 0 && m < (int64_t(1) << 31), "target cloud size must be below 2^31");
   MOPT_REQUIRE(max_distance > 0.0 && std::isfinite(max_distance), "max_distance must be positive");
@@ -347,8 +350,9 @@ int mopt_nn_index_create(mopt_ctx* ctx, const void* host_xyz, int host_dtype, in
   *out = ix;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_nn_index_destroy(mopt_nn_index* ix) {
+int mopt_nn_index_destroy(mopt_nn_index* ix) try {
   if (!ix) return MOPT_OK;
   cudaSetDevice(ix->ctx->device);
   cudaStreamSynchronize(ix->ctx->stream);
@@ -356,16 +360,18 @@ int mopt_nn_index_destroy(mopt_nn_index* ix) {
   delete ix;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_store_set_target(mopt_store* store, mopt_nn_index* index) {
+int mopt_store_set_target(mopt_store* store, mopt_nn_index* index) try {
   MOPT_REQUIRE(store, "null store");
   MOPT_REQUIRE(store->model == MOPT_MODEL_POINT2POINT, "correspondence re-association is defined for point2point stores");
   MOPT_REQUIRE(!index || index->ctx == store->ctx, "index and store live on different contexts");
   store->index = index;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_store_reassociate(mopt_store* store, const double* x, int64_t* matched) {
+int mopt_store_reassociate(mopt_store* store, const double* x, int64_t* matched) try {
   MOPT_REQUIRE(store && x, "null argument");
   MOPT_REQUIRE(store->index, "no target index attached (mopt_store_set_target)");
   mopt_ctx* ctx = store->ctx;
@@ -382,5 +388,6 @@ int mopt_store_reassociate(mopt_store* store, const double* x, int64_t* matched)
   if (matched) *matched = int64_t(h);
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
 }  // extern "C"

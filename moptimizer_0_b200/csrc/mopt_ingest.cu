@@ -3,10 +3,13 @@
 // fixture tst/data/fachada.txt).  This is a multi-threaded restatement of that loader that parses straight
 // into (optionally pinned) host memory ready for mopt_store_upload, plus a raw binary cache format.
 // Host-side code: it feeds the device path, it is not a substitute for it.
+#include <sys/stat.h>
+
 #include <charconv>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -83,7 +86,7 @@ int alloc_host(void** out, size_t bytes, int pinned) {
 
 extern "C" {
 
-int mopt_cloud_read_text(const char* path, int columns, int keep, int host_dtype, int pinned, void** out, int64_t* n) {
+int mopt_cloud_read_text(const char* path, int columns, int keep, int host_dtype, int pinned, void** out, int64_t* n) try {
   MOPT_REQUIRE(path && out && n, "null argument");
   MOPT_REQUIRE(columns >= 1 && columns <= 16 && keep >= 1 && keep <= columns, "bad columns/keep");
   MOPT_REQUIRE(host_dtype == MOPT_F32 || host_dtype == MOPT_F64, "bad host dtype");
@@ -92,11 +95,22 @@ int mopt_cloud_read_text(const char* path, int columns, int keep, int host_dtype
     set_last_error(std::string("not a file! ") + path);  // tst/point2point.cpp:127
     return MOPT_ERR_INVALID_ARGUMENT;
   }
-  std::fseek(f, 0, SEEK_END);
-  const long bytes = std::ftell(f);
-  std::fseek(f, 0, SEEK_SET);
-  std::vector<char> buf(size_t(bytes) + 1);
-  const size_t rd = std::fread(buf.data(), 1, size_t(bytes), f);
+  struct stat sb;
+  if (fstat(fileno(f), &sb) != 0 || !S_ISREG(sb.st_mode)) {  // a directory opens fine with "rb" and then lies about its size
+    std::fclose(f);
+    set_last_error(std::string("not a file! ") + path);
+    return MOPT_ERR_INVALID_ARGUMENT;
+  }
+  const size_t bytes = size_t(sb.st_size);
+  std::vector<char> buf;
+  try {
+    buf.resize(bytes + 1);
+  } catch (const std::bad_alloc&) {  // no exception may cross the C ABI
+    std::fclose(f);
+    set_last_error("out of host memory reading " + std::string(path));
+    return MOPT_ERR_OUT_OF_MEMORY;
+  }
+  const size_t rd = std::fread(buf.data(), 1, bytes, f);
   std::fclose(f);
   buf[rd] = '\n';
   const char* b = buf.data();
@@ -116,9 +130,21 @@ int mopt_cloud_read_text(const char* path, int columns, int keep, int host_dtype
     cur = stop;
   }
   std::vector<std::thread> th;
-  for (unsigned t = 1; t < nt; ++t) th.emplace_back(parse_chunk, std::ref(chunks[t]), columns, keep);
-  parse_chunk(chunks[0], columns, keep);
+  bool oom = false;
+  auto guarded = [&oom, columns, keep](Chunk& c) {
+    try {
+      parse_chunk(c, columns, keep);
+    } catch (const std::bad_alloc&) {
+      oom = true;  // only ever set, never cleared: a plain bool is enough
+    }
+  };
+  for (unsigned t = 1; t < nt; ++t) th.emplace_back(guarded, std::ref(chunks[t]));
+  guarded(chunks[0]);
   for (auto& x : th) x.join();
+  if (oom) {
+    set_last_error("out of host memory parsing " + std::string(path));
+    return MOPT_ERR_OUT_OF_MEMORY;
+  }
   size_t total = 0;
   for (unsigned t = 0; t < nt; ++t) {
     total += chunks[t].vals.size();
@@ -143,8 +169,9 @@ int mopt_cloud_read_text(const char* path, int columns, int keep, int host_dtype
   *n = int64_t(total / size_t(keep));
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_cloud_write_binary(const char* path, const void* data, int host_dtype, int keep, int64_t n) {
+int mopt_cloud_write_binary(const char* path, const void* data, int host_dtype, int keep, int64_t n) try {
   MOPT_REQUIRE(path && (data || n == 0) && n >= 0 && keep >= 1, "bad argument");
   MOPT_REQUIRE(host_dtype == MOPT_F32 || host_dtype == MOPT_F64, "bad host dtype");
   FILE* f = std::fopen(path, "wb");
@@ -167,8 +194,9 @@ int mopt_cloud_write_binary(const char* path, const void* data, int host_dtype, 
   }
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_cloud_read_binary(const char* path, int pinned, int* host_dtype, int* keep, void** out, int64_t* n) {
+int mopt_cloud_read_binary(const char* path, int pinned, int* host_dtype, int* keep, void** out, int64_t* n) try {
   MOPT_REQUIRE(path && host_dtype && keep && out && n, "null argument");
   FILE* f = std::fopen(path, "rb");
   if (!f) {
@@ -202,11 +230,13 @@ int mopt_cloud_read_binary(const char* path, int pinned, int* host_dtype, int* k
   *n = h.n;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_cloud_free(void* p, int pinned) {
+int mopt_cloud_free(void* p, int pinned) try {
   if (!p) return MOPT_OK;
   if (pinned) MOPT_CUDA_TRY(cudaFreeHost(p)); else std::free(p);
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
 }  // extern "C"

@@ -228,7 +228,7 @@ int store_upload_async(mopt_store* st, int group, const void* host, int host_dty
 
 extern "C" {
 
-int mopt_store_create(mopt_ctx* ctx, int model, int dtype, int64_t n, mopt_store** out) {
+int mopt_store_create(mopt_ctx* ctx, int model, int dtype, int64_t n, mopt_store** out) try {
   MOPT_REQUIRE(ctx && out, "null ctx/out");
   const ModelShape sh = model_shape(model);
   MOPT_REQUIRE(sh.P >= 0, "unknown model kind");
@@ -255,8 +255,9 @@ int mopt_store_create(mopt_ctx* ctx, int model, int dtype, int64_t n, mopt_store
   *out = st;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_store_destroy(mopt_store* st) {
+int mopt_store_destroy(mopt_store* st) try {
   if (!st) return MOPT_OK;
   cudaSetDevice(st->ctx->device);
   cudaStreamSynchronize(st->ctx->stream);
@@ -264,23 +265,26 @@ int mopt_store_destroy(mopt_store* st) {
   delete st;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_store_size(const mopt_store* st, int64_t* n) {
+int mopt_store_size(const mopt_store* st, int64_t* n) try {
   MOPT_REQUIRE(st && n, "null store/n");
   *n = st->n;
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
 int mopt_store_upload(mopt_store* st, int group, const void* host, int host_dtype, int64_t host_stride, int64_t first,
-                      int64_t count) {
+                      int64_t count) try {
   MOPT_REQUIRE(st, "null store");
   MOPT_CUDA_TRY(cudaSetDevice(st->ctx->device));
   MOPT_TRY(store_upload_async(st, group, host, host_dtype, host_stride, first, count));
   MOPT_CUDA_TRY(cudaStreamSynchronize(st->ctx->stream));
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_store_download(mopt_store* st, int group, void* host, int host_dtype, int64_t first, int64_t count) {
+int mopt_store_download(mopt_store* st, int group, void* host, int host_dtype, int64_t first, int64_t count) try {
   MOPT_REQUIRE(st && host, "null store/host");
   mopt_ctx* ctx = st->ctx;
   MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -312,8 +316,9 @@ int mopt_store_download(mopt_store* st, int group, void* host, int host_dtype, i
   }
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
-int mopt_store_generate(mopt_store* st, const mopt_synth* desc) {
+int mopt_store_generate(mopt_store* st, const mopt_synth* desc) try {
   MOPT_REQUIRE(st && desc, "null store/desc");
   mopt_ctx* ctx = st->ctx;
   MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -398,5 +403,6 @@ int mopt_store_generate(mopt_store* st, const mopt_synth* desc) {
   MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return MOPT_OK;
 }
+MOPT_ABI_CATCH
 
 }  // extern "C"

@@ -62,6 +62,8 @@ def test_ragged_and_malformed_input_matches_stream_semantics(capi, tmp_path):
     assert capi.cloud_read_text(p).shape == (0, 3)
     with pytest.raises(capi.MoptError, match="not a file"):
         capi.cloud_read_text(str(tmp_path / "missing.txt"))
+    with pytest.raises(capi.MoptError, match="not a file"):  # a directory opens with "rb": it must not be sized and read
+        capi.cloud_read_text(str(tmp_path))
 
 
 def test_binary_cache_roundtrip(capi, tmp_path):
