@@ -257,3 +257,19 @@ def test_pinhole_distort_reduces_to_reference_camera_model():
     assert s15 == pytest.approx(s6, rel=1e-12)
     assert rel_err(H15[:6, :6], H6) < 1e-6 and rel_err(b15[:6], b6) < 1e-6
     assert np.allclose(H15, H15.T)
+
+
+# ---- a property of the reference's float instantiation that the device path deliberately does not share ----
+def test_float_rodrigues_guard_zeroes_the_rotation_columns_inside_its_ball():
+    """so3::Exp returns R = I while |omega| <= 10 eps (src/so3.cpp:47).  With Scalar = float that is a ball of radius
+    1.2e-6: there x and every finite-difference perturbation of it (h_j = sqrt(eps) |x_j|, linearization.h:85-87)
+    give the same R, so the rotation block of J, H and b is exactly zero and LM can never move omega again.  The
+    restated oracle reproduces this; the device `setup` computes in fp64 for either Scalar and always uses the fp64
+    guard (found with LM on 50 M observations), so its float-Scalar results differ from the oracle's
+    only inside that ball."""
+    x = [-0.0066, -0.0365, -0.0597, 5e-7, -8e-8, 8e-7]
+    H32, b32, _ = orc.linearize(camera_cost(jac_mode=orc.JAC_FORWARD), x, orc.F32)
+    H64, b64, _ = orc.linearize(camera_cost(jac_mode=orc.JAC_FORWARD), x, orc.F64)
+    assert not H32[3:, :].any() and not H32[:, 3:].any() and not b32[3:].any()
+    assert np.abs(H32[:3, :3]).max() > 1e5                       # the translation block is alive
+    assert np.abs(np.diag(H64)[3:]).min() > 1e5 and np.abs(b64[3:]).max() > 1e3   # fp64: the rotation block too
