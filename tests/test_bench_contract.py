@@ -1,0 +1,60 @@
+"""CPU-only checks of bench.py's output contract: the reference arm runs here (oracle on the host cores) and its JSON
+line carries every key the driver reads; the CUDA arm must refuse to run without a GPU (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_bench(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          cwd=ROOT, env=e, timeout=600)
+
+
+def test_reference_arm_json_line():
+    r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-sample", "50000")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1  # ONE JSON line
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "point2point_linearized_residuals_per_sec" and d["unit"] == "Gres/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] == 2 and d["n_gpus"] == 1
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "Gres/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "20000", "--gpus", "2",
+                  env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_cuda_arm_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = run_bench("--steps", "1")
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The round's recorded N = 1 line (profiles/) has the roofline / cpu_baseline / e2e / clocks objects."""
+    path = os.path.join(ROOT, "profiles", "r1_bench_n1_final.json")
+    d = json.loads(open(path).read().strip().splitlines()[-1])
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["roofline"]["bound"] == "hbm"
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-12
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert d["e2e"]["h2d_bytes_per_step"] == 24 * d["config"]["n_per_gpu"] and d["e2e"]["matches_resident"] is True
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"} and d["gpu_launches"] == d["steps"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["dtype"] == "f32" and d["scaling"] == "weak"
+    # algorithmic bytes vs measured DRAM traffic of the same launch: no wasted re-reads
+    assert 1.0 <= d["roofline"]["traffic"] / d["roofline"]["algorithmic_bytes_per_launch"] < 1.01
