@@ -50,6 +50,7 @@ struct PassArgs {
   // every CTA derives (R, t) from x itself and the last CTA derives the affine Jacobian pieces — instead of in a
   // one-warp kernel launched before it (6.8 us + a dependent-launch gap per step).  `pb` is then not read.
   int fused_setup;
+  int no_ring;               // second-generation point2point kernel: 1 = no TMA ring (unaligned streams), direct loads only
   XArg x;
 };
 
@@ -291,6 +292,38 @@ __device__ inline void p2p_assemble(const double* tot, const double (*jaff)[18],
   }
 }
 
+// Everything after a point2point streaming loop: CTA + grid reduction of the 23 moment sums (dacc[0]: the lane's
+// fp64 total of moment `lane`), then, in the last CTA, assembly of the packed (H, b, sum) and the peer exchange.
+template <bool FUSED, int THREADS>
+__device__ __forceinline__ void p2p_finish(const PassArgs& a, int mode, const double (&dacc)[1], double* s_tot,
+                                           double* s_warp) {
+  if (!grid_reduce<kP2PRaw, 32, 1, THREADS>(dacc, a, s_tot, s_warp)) return;
+  if (mode == PASS_COST) {
+    if (threadIdx.x == 0) {
+      const int e = packed_size(6) - 1;
+      a.out->v[e] = a.accumulate ? a.out->v[e] + s_tot[22] : s_tot[22];
+    }
+  } else {
+    __shared__ double s_jl[FUSED ? 9 : 1];
+    __shared__ double s_jaff[FUSED ? 4 : 1][18];
+    const double(*jaff)[18] = FUSED ? s_jaff : a.pb->jaff;
+    if constexpr (FUSED) {
+      // the affine pieces of J, entry by entry (same sums, same order as setup_p2p_affine)
+      if (threadIdx.x == 0) {
+        double xl[6];  // a copy: taking the address of a kernel parameter would spill the whole PassArgs to local memory
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xl[i] = a.x.v[i];
+        p2p_fused_left_jacobian(a.cost, xl, s_jl);
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < 4 * 18; i += THREADS) s_jaff[i / 18][i % 18] = p2p_affine_entry(a.cost->variant, s_jl, i / 18, i % 18);
+      __syncthreads();
+    }
+    p2p_assemble(s_tot, jaff, a.cost, a.out, a.accumulate, threadIdx.x, THREADS);
+  }
+  peer_push(a, packed_size(6));
+}
+
 // FUSED: model->setup(x) runs inside the kernel (PassArgs::x; host-driven analytical passes), `pb` is not read.
 template <typename ST, typename CT, int LOSS, bool QROT, int THREADS, int MINB, int UNROLL = 2, int FLUSH_ROUNDS = 8,
           int PF = 0, bool SWP = false, bool FUSED = false>
@@ -464,31 +497,7 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
   }
   flush();
 
-  if (!grid_reduce<kP2PRaw, 32, 1, THREADS>(dacc, a, s_tot, s_warp)) return;
-  if (mode == PASS_COST) {
-    if (threadIdx.x == 0) {
-      const int e = packed_size(6) - 1;
-      a.out->v[e] = a.accumulate ? a.out->v[e] + s_tot[22] : s_tot[22];
-    }
-  } else {
-    __shared__ double s_jl[FUSED ? 9 : 1];
-    __shared__ double s_jaff[FUSED ? 4 : 1][18];
-    const double(*jaff)[18] = FUSED ? s_jaff : a.pb->jaff;
-    if constexpr (FUSED) {
-      // the affine pieces of J, entry by entry (same sums, same order as setup_p2p_affine)
-      if (threadIdx.x == 0) {
-        double xl[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) xl[i] = a.x.v[i];
-        p2p_fused_left_jacobian(a.cost, xl, s_jl);
-      }
-      __syncthreads();
-      for (int i = threadIdx.x; i < 4 * 18; i += THREADS) s_jaff[i / 18][i % 18] = p2p_affine_entry(a.cost->variant, s_jl, i / 18, i % 18);
-      __syncthreads();
-    }
-    p2p_assemble(s_tot, jaff, a.cost, a.out, a.accumulate, threadIdx.x, THREADS);
-  }
-  peer_push(a, packed_size(6));
+  p2p_finish<FUSED, THREADS>(a, mode, dacc, s_tot, s_warp);
 }
 
 // =============================================================================================

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "mopt_pass.cuh"
+#include "mopt_pass_p2p2.cuh"
 
 namespace mopt {
 void set_last_error(const std::string&) {}
@@ -103,6 +104,22 @@ float time_launch(Env& E, F launch, int reps = 15) {
   return ms[ms.size() / 2];
 }
 
+// Sustained rate: `warm` untimed launches, then `reps` back-to-back launches between one pair of events (what a
+// long-running job sees under the power cap), in ms per launch.
+static int g_sustained_reps = 0;
+template <class F>
+float time_sustained(Env& E, F launch) {
+  if (g_sustained_reps <= 0) return 0.f;
+  for (int i = 0; i < g_sustained_reps / 4; ++i) launch();
+  CK(cudaEventRecord(E.e0, E.stream));
+  for (int i = 0; i < g_sustained_reps; ++i) launch();
+  CK(cudaEventRecord(E.e1, E.stream));
+  CK(cudaEventSynchronize(E.e1));
+  float t;
+  CK(cudaEventElapsedTime(&t, E.e0, E.e1));
+  return t / g_sustained_reps;
+}
+
 template <int THREADS, int MINB, int UNROLL, int FLUSH, int PF = 0, bool SWP = false, int LOSS = MOPT_LOSS_HUBER>
 void run_variant(Env& E, int ctas_per_sm, int mode = PASS_LINEARIZE) {
   auto kern = p2p_moment_kernel<float, float, LOSS, true, THREADS, MINB, UNROLL, FLUSH, PF, SWP>;
@@ -117,10 +134,50 @@ void run_variant(Env& E, int ctas_per_sm, int mode = PASS_LINEARIZE) {
   a.mode_override = mode;
   if (mode != PASS_LINEARIZE || LOSS != MOPT_LOSS_HUBER) std::printf("[mode=%d loss=%d] ", mode, LOSS);
   const float ms = time_launch(E, [&] { kern<<<grid, THREADS, 0, E.stream>>>(a); });
+  const float sus = time_sustained(E, [&] { kern<<<grid, THREADS, 0, E.stream>>>(a); });
   const double gbs = 24.0 * double(a.n) / (ms * 1e-3) / 1e9;
-  std::printf("moment%s threads=%3d minb=%d unroll=%d flush=%2d pf=%2d ctas/sm=%d regs=%3d occ=%d  %8.1f us  %7.1f GB/s  %6.1f Gres/s\n",
+  std::printf("moment%s threads=%3d minb=%d unroll=%d flush=%2d pf=%2d ctas/sm=%d regs=%3d occ=%d  %8.1f us  %7.1f GB/s  %6.1f Gres/s",
               SWP ? "/swp" : "    ", THREADS, MINB, UNROLL, FLUSH, PF, per_sm, fa.numRegs, occ, ms * 1e3, gbs, gbs / 24.0);
+  if (sus > 0.f) std::printf("   sustained %8.1f us %6.1f Gres/s", sus * 1e3, double(a.n) / (sus * 1e-3) / 1e9);
+  std::printf("\n");
   std::fflush(stdout);
+}
+
+
+// second-generation kernel (mopt_pass_p2p2.cuh): packed fp32 + TMA bulk-copy ring (STAGES > 0) or direct loads
+template <int THREADS, int MINB, int STAGES, int U, int FLUSH, int PF = 0, int LOSS = MOPT_LOSS_HUBER, bool FUSED = false>
+void run_variant2(Env& E, int ctas_per_sm, int mode = PASS_LINEARIZE) {
+  auto kern = p2p_moment2_kernel<LOSS, true, false, FUSED, THREADS, MINB, STAGES, U, FLUSH, PF>;
+  const size_t smem = p2p2_ring_bytes(THREADS, STAGES, U);
+  if (smem > 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  const int per_sm = std::min(occ, ctas_per_sm);
+  if (per_sm < ctas_per_sm) {
+    std::printf("moment2 threads=%d stages=%d u=%d: only %d CTAs/SM reachable (regs=%d smem=%zu), skipped\n", THREADS, STAGES, U, occ, fa.numRegs, smem);
+    return;
+  }
+  const int grid = per_sm * E.num_sms;
+  PassArgs a = E.a;
+  a.mode_override = mode;
+  if (mode != PASS_LINEARIZE || LOSS != MOPT_LOSS_HUBER) std::printf("[mode=%d loss=%d] ", mode, LOSS);
+  const float ms = time_launch(E, [&] { kern<<<grid, THREADS, smem, E.stream>>>(a); });
+  const float sus = time_sustained(E, [&] { kern<<<grid, THREADS, smem, E.stream>>>(a); });
+  const double gbs = 24.0 * double(a.n) / (ms * 1e-3) / 1e9;
+  std::printf("moment2 threads=%4d minb=%d stages=%d u=%d flush=%2d pf=%2d ctas/sm=%d regs=%3d smem=%6zu  %8.1f us  %7.1f GB/s  %6.1f Gres/s",
+              THREADS, MINB, STAGES, U, FLUSH, PF, per_sm, fa.numRegs, smem, ms * 1e3, gbs, gbs / 24.0);
+  if (sus > 0.f) std::printf("   sustained %8.1f us %6.1f Gres/s", sus * 1e3, double(a.n) / (sus * 1e-3) / 1e9);
+  std::printf("\n");
+  std::fflush(stdout);
+}
+
+// result of the last launch: the packed (H, b, sum) — to compare kernel generations on the same data
+void print_result(Env& E, const char* tag) {
+  PassResult h;
+  CK(cudaMemcpy(&h, E.a.out, sizeof(h), cudaMemcpyDeviceToHost));
+  std::printf("%s: H00=%.9e H05=%.9e H55=%.9e b0=%.9e b5=%.9e sum=%.9e\n", tag, h.v[0], h.v[5], h.v[20], h.v[21], h.v[26], h.v[27]);
 }
 
 // fp64-compute variants (the reference's default Scalar is double): ST = float or double streams
@@ -160,8 +217,11 @@ void run_ceiling(Env& E, int ctas_per_sm) {
   const int per_sm = std::min(occ, ctas_per_sm);
   const int grid = per_sm * E.num_sms;
   const float ms = time_launch(E, [&] { kern<<<grid, THREADS, 0, E.stream>>>(E.a.streams, E.a.n, E.d_out); });
+  const float sus = time_sustained(E, [&] { kern<<<grid, THREADS, 0, E.stream>>>(E.a.streams, E.a.n, E.d_out); });
   const double gbs = 24.0 * double(E.a.n) / (ms * 1e-3) / 1e9;
-  std::printf("ceiling threads=%3d unroll=%d ctas/sm=%d occ=%d  %8.1f us  %7.1f GB/s\n", THREADS, UNROLL, per_sm, occ, ms * 1e3, gbs);
+  std::printf("ceiling threads=%3d unroll=%d ctas/sm=%d occ=%d  %8.1f us  %7.1f GB/s", THREADS, UNROLL, per_sm, occ, ms * 1e3, gbs);
+  if (sus > 0.f) std::printf("   sustained %8.1f us %7.1f GB/s", sus * 1e3, 24.0 * double(E.a.n) / (sus * 1e-3) / 1e9);
+  std::printf("\n");
   std::fflush(stdout);
 }
 
@@ -205,6 +265,72 @@ int main(int argc, char** argv) {
   CK(cudaStreamSynchronize(E.stream));
   std::printf("%s, %d SMs, n = %lld, data = %s\n", prop.name, E.num_sms, (long long)n, argc > 2 ? argv[2] : "random");
 
+  if (argc > 2 && std::string(argv[2]) == "gen2ncu") {  // a few launches of the candidates, for an ncu capture
+    make_targets_kernel<<<148 * 8, 256, 0, E.stream>>>((const float*)E.a.streams.p[0], (const float*)E.a.streams.p[1],
+                                                       (const float*)E.a.streams.p[2], (float*)E.a.streams.p[3],
+                                                       (float*)E.a.streams.p[4], (float*)E.a.streams.p[5], n);
+    CK(cudaStreamSynchronize(E.stream));
+    PassArgs a = E.a;
+    auto k1 = p2p_moment_kernel<float, float, MOPT_LOSS_HUBER, true, 1024, 1, 1, 16>;
+    auto k2 = p2p_moment2_kernel<MOPT_LOSS_HUBER, true, false, false, 512, 1, 2, 2, 16, 0>;
+    auto k3 = p2p_moment2_kernel<MOPT_LOSS_HUBER, true, false, false, 384, 1, 2, 2, 16, 0>;
+    auto k4 = p2p_moment2_kernel<MOPT_LOSS_HUBER, true, false, false, 512, 1, 4, 1, 32, 0>;
+    const size_t s2 = p2p2_ring_bytes(512, 2, 2), s3 = p2p2_ring_bytes(384, 2, 2), s4 = p2p2_ring_bytes(512, 4, 1);
+    CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2)));
+    CK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s3)));
+    CK(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s4)));
+    for (int i = 0; i < 2; ++i) {
+      k1<<<148, 1024, 0, E.stream>>>(a);
+      k2<<<148, 512, s2, E.stream>>>(a);
+      k3<<<148, 384, s3, E.stream>>>(a);
+      k4<<<148, 512, s4, E.stream>>>(a);
+    }
+    CK(cudaStreamSynchronize(E.stream));
+    std::printf("gen2ncu done\n");
+    return 0;
+  }
+  if (argc > 2 && std::string(argv[2]) == "gen2") {  // packed-fp32 / TMA-ring kernel against the shipped one, realistic data
+    make_targets_kernel<<<148 * 8, 256, 0, E.stream>>>((const float*)E.a.streams.p[0], (const float*)E.a.streams.p[1],
+                                                       (const float*)E.a.streams.p[2], (float*)E.a.streams.p[3],
+                                                       (float*)E.a.streams.p[4], (float*)E.a.streams.p[5], n);
+    CK(cudaStreamSynchronize(E.stream));
+    const int prewarm = argc > 3 ? std::atoi(argv[3]) : 0;
+    {
+      auto kern = p2p_moment_kernel<float, float, MOPT_LOSS_HUBER, true, 1024, 1, 1, 16>;
+      PassArgs a = E.a;
+      for (int i = 0; i < prewarm; ++i) kern<<<148, 1024, 0, E.stream>>>(a);
+      CK(cudaStreamSynchronize(E.stream));
+    }
+    g_sustained_reps = argc > 4 ? std::atoi(argv[4]) : 0;
+    for (int rep = 0; rep < 2; ++rep) {
+      run_ceiling<256, 4>(E, 3);
+      run_variant<1024, 1, 1, 16>(E, 1);  // shipped in round 1
+      if (rep == 0) print_result(E, "gen1");
+      run_variant2<512, 1, 4, 1, 32>(E, 1);
+      if (rep == 0) print_result(E, "gen2");
+      run_variant2<512, 1, 3, 1, 32>(E, 1);
+      run_variant2<512, 1, 2, 1, 32>(E, 1);
+      run_variant2<512, 1, 2, 2, 16>(E, 1);
+      run_variant2<512, 1, 2, 2, 8>(E, 1);
+      run_variant2<384, 1, 3, 1, 32>(E, 1);
+      run_variant2<384, 1, 4, 1, 32>(E, 1);
+      run_variant2<384, 1, 2, 2, 16>(E, 1);
+      run_variant2<384, 1, 3, 2, 16>(E, 1);
+      run_variant2<384, 1, 2, 3, 8>(E, 1);
+      run_variant2<448, 1, 2, 2, 16>(E, 1);
+      run_variant2<320, 1, 2, 2, 16>(E, 1);
+      run_variant2<320, 1, 3, 2, 16>(E, 1);
+      run_variant2<256, 1, 2, 4, 8>(E, 1);
+      run_variant2<256, 2, 2, 1, 32>(E, 2);
+      run_variant2<256, 2, 2, 2, 16>(E, 2);
+      run_variant2<192, 2, 2, 2, 16>(E, 2);
+      run_variant2<512, 1, 0, 1, 32, 1>(E, 1);    // direct loads + L2 bulk prefetch
+      run_variant2<512, 1, 2, 2, 16>(E, 1, PASS_COST);
+      run_variant2<384, 1, 2, 2, 16>(E, 1, PASS_COST);
+      run_variant2<512, 1, 2, 2, 16, 0, MOPT_LOSS_NONE>(E, 1);
+    }
+    return 0;
+  }
   if (argc > 2 && std::string(argv[2]) == "f64") {  // fp64-compute launch shapes
     make_targets_kernel<<<148 * 8, 256, 0, E.stream>>>((const float*)E.a.streams.p[0], (const float*)E.a.streams.p[1],
                                                        (const float*)E.a.streams.p[2], (float*)E.a.streams.p[3],
