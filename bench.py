@@ -1,15 +1,22 @@
 #!/usr/bin/env python
 """bench.py — point2point linearization throughput (Gres/s) on B200, the BASELINE.json metric.
 
-Workload (BASELINE.json configs[2]): point-to-point rigid registration,
+Headline workload (BASELINE.json configs[2]): point-to-point rigid registration,
 100 M correspondences per GPU, analytical Jacobian + Huber loss, fp32 planar streams resident in
 HBM (24 B per correspondence), fp32 residual math with fp64 accumulation.  A "step" is one
 linearization pass (H, b, sum r^T r) over every rank's shard plus, for N > 1, the exchange of the 28
 packed fp64 values (NVLink peer exchange fused into the pass kernel; `--collective nccl` for the
 NCCL all-reduce baseline).  Weak scaling: every rank holds `--n` correspondences.
 
+The same JSON line also carries (under "configs") the other BASELINE.json configurations, each with its own
+roofline: curve fitting 10 M (central differences), camera calibration 50 M with 6 and 15 parameters, the
+small-problem LM (tst/point2point's 29 310-point cloud) and, for N > 1, the 1 B-correspondence strong-scaling split
+of configs[3]; "peaks" holds the fp32 FMA / issue / HBM-read / host-to-device ceilings measured in this run with
+the library's micro-kernels; for N > 1 "check.vs_single_gpu" compares the exchanged result with the sum of every
+shard's result recomputed on rank 0's GPU alone.
+
   python bench.py [--gpus N] [--steps K] [--warmup W]          # our CUDA path
-  python bench.py --impl reference ...                         # CPU restatement of the reference
+  python bench.py --impl reference ...                         # CPU restatement of the reference, same workload
 Multi-GPU: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 Prints ONE JSON line on rank 0.
 """
@@ -32,7 +39,11 @@ UNIT = "Gres/s"
 BYTES_PER_RES = 24  # src xyz + tgt xyz, fp32
 X_GT = [0.5, -0.3, 0.2, 0.10, -0.05, 0.08]
 HUBER_K = 0.05
+SEED = 2
 NOISE_SIGMA, OUTLIER_FRACTION, OUTLIER_RANGE = 0.01, 0.05, 1.0
+GEN = dict(lo=(0, 0, 0), hi=(10, 10, 10), noise_sigma=NOISE_SIGMA, outlier_fraction=OUTLIER_FRACTION,
+           outlier_range=OUTLIER_RANGE)
+INST_COUNTS = os.path.join(ROOT, "profiles", "kernel_inst_counts.json")
 
 
 def parse():
@@ -43,22 +54,38 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", "--per-gpu", dest="n", type=int, default=100_000_000, help="correspondences per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample", type=int, default=20_000_000, help="correspondences in the CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000,
+                    help="correspondences in the cpu_baseline sample of the GPU arm (the reference arm uses --n)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-budget-s", type=float, default=240.0,
+                    help="--impl reference: shrink the per-step sample only if (W + K) steps of --n would exceed this")
     ap.add_argument("--prewarm-steps", type=int, default=2000, help="untimed steps before the W warm-up steps")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
-    ap.add_argument("--threads", type=int, default=0, help="launch-shape override (0 = default, 256 = small CTAs)")
+    ap.add_argument("--threads", type=int, default=0,
+                    help="launch-shape override (0 = default; 512 = second ring shape; 1024 = first-generation kernel)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations")
+    ap.add_argument("--no-check", action="store_true", help="N>1: skip the comparison with the single-GPU sums")
+    ap.add_argument("--no-peaks", action="store_true")
     ap.add_argument("--lm", dest="lm", action="store_true", default=True,
                     help="also time a device-resident LM solve (LM iters/s, the second half of BASELINE.json's metric)")
     ap.add_argument("--no-lm", dest="lm", action="store_false")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: how the 28 packed doubles are combined per step")
-    ap.add_argument("--strong-total", type=int, default=0,
-                    help="strong scaling: this many correspondences in total, sharded contiguously over the ranks "
-                         "(BASELINE configs[3] uses 1e9); default is weak scaling with --n per GPU")
+    ap.add_argument("--strong-total", type=int, default=-1,
+                    help="N>1: second timed region, this many correspondences in total sharded contiguously over the "
+                         "ranks (BASELINE configs[3]); default 1e9 when N>1, 0 disables")
     return ap.parse_args()
+
+
+def workload_config(n_per_gpu: int, n_total: int) -> dict:
+    """The keys that define the workload: identical in the GPU arm and in `--impl reference`."""
+    return {"workload": f"point2point {n_per_gpu / 1e6:.0f}M correspondences/GPU, analytical Jacobian + Huber(k=0.05), x0=0",
+            "n_per_gpu": n_per_gpu, "n_total": n_total,
+            "generator": f"counter-based (splitmix64), seed {SEED}, src uniform in [0,10]^3, tgt = T_gt src + N(0,0.01^2), "
+                         "5% outliers U(-1,1); identical rows on the device and on the host (tests/test_gpu_generator.py)",
+            "l2": "inputs per step (2.4 GB fp32 / 4.8 GB fp64 per 100M) exceed every cache: no flush needed"}
 
 
 def peaks():
@@ -71,23 +98,13 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def ncu_traffic_bytes(n: int):
-    """DRAM bytes per launch of the moment kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
-    `ncu --set full` capture of this workload (profiles/); only meaningful for the size that capture was taken at."""
-    if n != 100_000_000:
-        return None, None
-    path = os.path.join(ROOT, "profiles", "r1_p2p_moment_kernel_ncu_full.csv")
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+def inst_counts() -> dict:
+    """Warp instructions per residual of each kernel, from the committed ncu captures (profiles/kernel_inst_counts.json,
+    written by scripts/ncu_inst_counts.py): a property of the binary, used for the issue-slot rooflines."""
     try:
-        tot = 0.0
-        for line in open(path):
-            f = line.strip().split(",")
-            if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                vals = [float(v) for v in f[2:]]
-                tot += scale[f[1]] * sum(vals) / len(vals)
-        return (tot or None), os.path.relpath(path, ROOT)
+        return json.load(open(INST_COUNTS))
     except Exception:
-        return None, None
+        return {}
 
 
 # ------------------------------------------------------------------------- clocks ----
@@ -129,7 +146,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def start(self):
         if self.nv is not None:
@@ -165,40 +182,35 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(vals), "window": where}
 
 
-def bind_host_thread_to_gpu_numa(index: int):
-    """Pin this process to the CPUs NVML reports as local to GPU `index` BEFORE any pinned host buffer is allocated,
-    so the e2e leg's H2D copies read first-touched local memory instead of crossing the socket interconnect
-    (matters once several ranks stream from the host at the same time).  Returns a short note for the JSON line."""
+def bind_host_thread(index: int, local_rank: int, local_world: int):
+    """Pin this process BEFORE any pinned host buffer is allocated: to the CPUs NVML reports as local to GPU `index`
+    and, when several ranks share that set (a single-NUMA box reports every CPU for every GPU), to this rank's own
+    contiguous 1/local_world slice of it, so the ranks' staging copies and first-touched pages do not compete for the
+    same cores.  Returns a short note for the JSON line."""
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        ncpu = os.cpu_count() or 1
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
-        cpus = [w * 64 + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1 and w * 64 + b < ncpu]
-        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
-        if not allowed:
-            return "no local CPUs in this cpuset"
-        os.sched_setaffinity(0, allowed)
-        return f"{len(allowed)} CPUs local to GPU {index}"
-    except Exception as e:  # NVML without topology info, containers without the syscall, ...
+        allowed = sorted(os.sched_getaffinity(0))
+        local = allowed
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cpus = [w * 64 + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1 and w * 64 + b < ncpu]
+            local = sorted(set(cpus) & set(allowed)) or allowed
+        except Exception:
+            pass
+        mine = local
+        if local_world > 1 and len(local) >= local_world:
+            per = len(local) // local_world
+            mine = local[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return f"{len(mine)} of {len(local)} CPUs local to GPU {index} (CPUs {mine[0]}-{mine[-1]})"
+    except Exception as e:  # containers without the syscall, ...
         return f"unavailable ({type(e).__name__})"
 
 
 # ------------------------------------------------------------------ CPU (oracle) arm ----
-def host_workload(n: int, seed: int = 2):
-    """Same distribution as the device generator (not bit-identical): box [0,10]^3, tgt = T_gt src +
-    N(0, 0.01^2), 5 % outliers U(-1,1).  fp64 AoS, the layout the reference models read."""
-    from scipy.spatial.transform import Rotation
-    rng = np.random.default_rng(seed)
-    src = rng.uniform(0.0, 10.0, (n, 3))
-    R = Rotation.from_rotvec(X_GT[3:]).as_matrix()
-    tgt = src @ R.T + np.array(X_GT[:3]) + rng.normal(0.0, NOISE_SIGMA, (n, 3))
-    out = rng.uniform(size=n) < OUTLIER_FRACTION
-    tgt[out] += rng.uniform(-OUTLIER_RANGE, OUTLIER_RANGE, (int(out.sum()), 3))
-    return np.ascontiguousarray(src), np.ascontiguousarray(tgt)
-
-
 def oracle_cost(src, tgt):
     from oracle import oracle_py as orc
     return orc.Cost(orc.P2P, 6, 3, src.shape[0], a=src, b=tgt, jac_mode=orc.JAC_ANALYTICAL, variant=orc.P2P_EXACT,
@@ -218,39 +230,205 @@ def time_oracle(src, tgt, nthreads: int, budget_s: float):
 
 
 def run_reference(args):
-    """`--impl reference`: the CPU restatement of the reference path (oracle port; the reference itself
-    cannot be built in this image — no Eigen3/oneTBB), all host threads, bounded sample per step."""
+    """`--impl reference`: the CPU restatement of the reference path (oracle port; the reference itself cannot be
+    built in this image — no Eigen3/oneTBB) on all host threads, on the SAME workload as the GPU arm: the rows of
+    rank 0's shard come from the host restatement of the device generator (bit-identical, tests/test_gpu_generator.py),
+    W warm-up and K timed steps of one full linearization each.  Only if (W + K) full steps would not fit
+    --ref-budget-s is the per-step sample shrunk, and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle_py as orc
     orc.build()
     cores = orc.hardware_concurrency() or (os.cpu_count() or 1)
-    n = args.cpu_sample
-    src, tgt = host_workload(n)
+    n_full = args.n
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # a quick probe decides whether the full per-GPU workload fits the time budget
+    probe_n = min(n_full, 2_000_000)
+    ps, pt = orc.generate_p2p(SEED, probe_n, X_GT, **GEN)
+    t_probe, _, _, _ = orc.time_linearize(oracle_cost(ps, pt), [0.0] * 6, nthreads=cores, reps=1)
+    est_step = t_probe * n_full / probe_n
+    n = n_full
+    if est_step * (steps + warmup) > args.ref_budget_s:
+        n = max(probe_n, int(n_full * args.ref_budget_s / (est_step * (steps + warmup))))
+    del ps, pt
+    src, tgt = orc.generate_p2p(SEED, n, X_GT, **GEN)
     cost = oracle_cost(src, tgt)
     x0 = [0.0] * 6
-    for _ in range(min(args.warmup, 2)):
-        orc.time_linearize(cost, x0, nthreads=cores, reps=1)
-    steps = max(1, min(args.steps, 50))
-    t, _, _, _ = orc.time_linearize(cost, x0, nthreads=cores, reps=steps)
+    if warmup:
+        orc.time_linearize(cost, x0, nthreads=cores, reps=warmup)
+    t, H, b, s = orc.time_linearize(cost, x0, nthreads=cores, reps=steps)
     ms = t / steps * 1e3
     value = n / (t / steps) / 1e9
-    sample = f"{n} correspondences per step (fp64 AoS), threaded linearization with thread-local H/b"
+    sample = (f"{n} correspondences per step (fp64 AoS, the first rows of rank 0's shard"
+              + ("" if n == n_full else f"; shrunk from {n_full} to fit --ref-budget-s {args.ref_budget_s:.0f}")
+              + "), threaded linearization with thread-local H/b on all host threads (the reference's own loop is "
+                "serial, linearization.h:142)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "point2point 100M correspondences/GPU, analytical Jacobian + Huber(k=0.05), x0=0",
-                   "cpu_sample_per_step": n},
+        "config": workload_config(n_full, n_full * max(1, args.gpus)),
+        "cpu_sample_per_step": n,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "check": {"sum_rtr": s, "H00": float(H[0, 0]), "b0": float(b[0]), "rows": n},
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------- GPU arm ----
+class Timer:
+    """CUDA-event timing of back-to-back asynchronous passes on the context's stream."""
+
+    def __init__(self, torch, ctx, stream):
+        self.torch, self.ctx, self.stream = torch, ctx, stream
+
+    def ms_per_pass(self, store, prob, x, steps, warm):
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+        for _ in range(warm):
+            self.ctx.linearize_async(store, prob, x)
+        self.ctx.synchronize()
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            self.ctx.linearize_async(store, prob, x)
+        e1.record(self.stream)
+        self.ctx.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+
+def alu_roofline(key, n, ms, bytes_per, pk, counts, hbm_peak):
+    """Roofline of an ALU-bound pass: warp instructions issued per second against the measured issue peak
+    (one instruction per clock per scheduler = the FFMA-only rate of csrc/mopt_peaks.cu), next to the HBM fraction."""
+    out = {"bound": "fp32_issue", "hbm_gbs": n * bytes_per / (ms * 1e-3) / 1e9,
+           "hbm_frac": n * bytes_per / (ms * 1e-3) / 1e9 / hbm_peak}
+    c = counts.get(key)
+    if c and pk:
+        issue_peak = pk["fp32_fma_tflops"] * 1e12 / 64.0 / 1e9  # G warp-instructions/s: one FFMA = 64 flop per warp
+        ach = c["warp_inst_per_residual"] * n / (ms * 1e-3) / 1e9
+        out.update({"achieved": ach, "peak": issue_peak, "unit": "G warp-inst/s", "frac": ach / issue_peak,
+                    "warp_inst_per_residual": c["warp_inst_per_residual"], "inst_source": c.get("source"),
+                    "peak_source": "FFMA-only issue rate measured in this run (mopt_measure_peaks)"})
+        if c.get("fma_pipe_inst_per_residual"):
+            f = c["fma_pipe_inst_per_residual"] * n / (ms * 1e-3) / 1e9
+            out["fma_pipe"] = {"achieved": f, "peak": issue_peak, "frac": f / issue_peak,
+                               "note": "FMA-pipe warp instructions per second (FFMA2 counted twice) against the same peak"}
+    else:
+        out.update({"achieved": None, "peak": None, "unit": "G warp-inst/s", "frac": None})
+    return out
+
+
+def camera_consts():
+    """K (3x4 row-major) ++ C (4x4 row-major) of tst/camera_calibration.cpp:22-30 (K from the golden fixtures)."""
+    fx = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_fixtures.json")))
+    K = np.array(fx["camera"]["K"], dtype=np.float64)
+    c, s = np.cos(np.pi / 2), np.sin(np.pi / 2)
+    rx = np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+    rz = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+    Cm = np.eye(4)
+    Cm[:3, :3] = rx @ rz
+    return np.concatenate([K, Cm.reshape(-1)])
+
+
+def run_other_configs(capi, ctx, timer, pk, hbm_peak):
+    """BASELINE.json configs[1], configs[4] (6 and 15 parameters) and configs[0]-sized LM, on this GPU."""
+    counts = inst_counts()
+    out = {}
+    # configs[1]: curve fitting, 10 M samples, central differences, fp32 compute
+    n = 10_000_000
+    st = capi.Store(ctx, capi.MODEL_EXP_CURVE, n, capi.F32)
+    st.generate(seed=1, gt=[0.3, 0.1], lo=(0, 0, 0), hi=(5, 0, 0), n_total=n, noise_sigma=0.2)
+    prob = capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_CENTRAL, capi.F32)
+    ms = timer.ms_per_pass(st, prob, [0.25, 0.15], steps=200, warm=200)
+    out["curve_10M_central"] = {
+        "workload": "exp curve y = exp(m t + c), 10M samples, numerical central-difference Jacobian, fp32 (BASELINE configs[1])",
+        "n": n, "ms": ms, "Gres_per_s": n / ms / 1e6, "l2": "80 MB of streams: L2-resident between passes (126 MB L2)",
+        "roofline": alu_roofline("curve_central_f32", n, ms, 8, pk, counts, hbm_peak)}
+    r64 = capi.make_problem(capi.MODEL_EXP_CURVE, capi.JAC_CENTRAL, capi.F64)
+    t0 = time.perf_counter()
+    r = ctx.lm_minimize([st], [r64], [0.0, 0.0], max_iterations=50)
+    dt = time.perf_counter() - t0
+    out["curve_10M_central"]["lm_f64"] = {"status": r.status, "iterations": r.executed_iterations, "passes": r.num_passes,
+                                          "seconds": dt, "x": [float(v) for v in r.x]}
+    st.close()
+    # configs[4]: camera calibration, 50 M observations, numerical Jacobian; 6 extrinsics, then the n x n case (P = 15)
+    n = 50_000_000
+    consts = camera_consts()
+    x6 = np.array([-0.01, 0.02, -0.06, 0.018, -0.0013, 0.027])
+    T = capi.so3_convert6dof(x6)
+    M = consts[:12].reshape(3, 4) @ T @ consts[12:].reshape(4, 4)
+    st = capi.Store(ctx, capi.MODEL_PINHOLE, n, capi.F32)
+    st.generate(seed=3, gt=M.reshape(-1), lo=(2.0, -1.0, -0.5), hi=(5.0, 1.0, 1.0), noise_sigma=0.5)
+    prob = capi.make_problem(capi.MODEL_PINHOLE, capi.JAC_CENTRAL, capi.F32, consts=consts)
+    ms = timer.ms_per_pass(st, prob, [0.0] * 6, steps=30, warm=30)
+    out["camera_50M_P6_central"] = {
+        "workload": "pinhole reprojection, 50M observations, 6 extrinsics, numerical central differences, fp32 (BASELINE configs[4], the reference's own test model)",
+        "n": n, "ms": ms, "Gres_per_s": n / ms / 1e6,
+        "roofline": alu_roofline("camera6_central_f32", n, ms, 20, pk, counts, hbm_peak)}
+    st.close()
+    x15 = np.concatenate([x6, [600.0, 600.0, 320.0, 240.0, 0.05, -0.02, 0.001, -0.001, 0.005]])
+    C44 = consts[12:]
+    st = capi.Store(ctx, capi.MODEL_PINHOLE_DISTORT, n, capi.F32)
+    st.generate(seed=3, gt=x15, lo=(2.0, -1.0, -0.5), hi=(5.0, 1.0, 1.0), noise_sigma=0.5, consts=C44)
+    prob = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL, capi.F32, consts=C44)
+    ms = timer.ms_per_pass(st, prob, x15 * 0.999, steps=15, warm=15)
+    entry = {
+        "workload": "pinhole + distortion, 50M observations, 15 parameters (n x n device solve), numerical central differences, fp32 (BASELINE configs[4])",
+        "n": n, "ms": ms, "Gres_per_s": n / ms / 1e6,
+        "roofline": alu_roofline("camera15_central_f32", n, ms, 20, pk, counts, hbm_peak)}
+    p64 = capi.make_problem(capi.MODEL_PINHOLE_DISTORT, capi.JAC_CENTRAL, capi.F64, consts=C44)
+    x0 = x15.copy()
+    x0[:6] = 0.0
+    x0[6:10] *= 1.02
+    x0[10:] = 0.0
+    t0 = time.perf_counter()
+    r = ctx.lm_minimize([st], [p64], x0, max_iterations=50)
+    dt = time.perf_counter() - t0
+    entry["lm_f64"] = {"status": r.status, "iterations": r.executed_iterations, "passes": r.num_passes, "seconds": dt,
+                       "x_err_extrinsics": float(np.max(np.abs(r.x[:6] - x15[:6]))),
+                       "x_err_focal_rel": float(np.max(np.abs(r.x[6:10] / x15[6:10] - 1.0)))}
+    out["camera_50M_P15_central"] = entry
+    st.close()
+    # configs[0]: the small-problem LM — tst/point2point's cloud (29 310 points), fp64 Scalar, LM iterations per second
+    try:
+        src = np.fromfile(os.path.join(ROOT, "tests", "golden", "fachada_xyz.f64"), dtype="<f8").reshape(-1, 3)
+        fx = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_fixtures.json")))["fachada"]
+        ex, ey, ez = fx["gt_euler_xyz"]
+
+        def rot(axis, a):
+            c, s = np.cos(a), np.sin(a)
+            return {"x": np.array([[1, 0, 0], [0, c, -s], [0, s, c]]), "y": np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]]),
+                    "z": np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])}[axis]
+        R = rot("x", ex) @ rot("y", ey) @ rot("z", ez)
+        tgt = src @ R.T + np.array(fx["gt_translation"])
+        n = src.shape[0]
+        st = capi.Store(ctx, capi.MODEL_POINT2POINT, n, capi.F64)
+        st.upload(0, src)
+        st.upload(1, tgt)
+        prob = capi.make_problem(capi.MODEL_POINT2POINT, capi.JAC_ANALYTICAL, capi.F64, variant=capi.P2P_EXACT)
+        ctx.lm_minimize([st], [prob], [0.0] * 6, max_iterations=50)
+        times, r = [], None
+        for _ in range(30):
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            r = ctx.lm_minimize([st], [prob], [0.0] * 6, max_iterations=50)
+            times.append(time.perf_counter() - t0)
+        dt = float(np.median(times))
+        out["fachada_lm"] = {
+            "workload": "tst/point2point cloud (29 310 correspondences), analytical Jacobian, fp64, LM from x0 = 0 "
+                        "(BASELINE configs[0]); wall clock of mopt_lm_minimize, median of 30 solves",
+            "n": n, "status": r.status, "iterations": r.executed_iterations, "passes": r.num_passes, "sequence": r.sequence,
+            "seconds": dt, "lm_iters_per_s": r.executed_iterations / dt, "us_per_pass": dt / max(r.num_passes, 1) * 1e6,
+            "roofline": {"bound": "latency", "note": "launch- and dependency-bound: a pass over 0.7 MB takes microseconds; "
+                                                     "the figure of merit is microseconds per pass + optimizer step"}}
+        st.close()
+    except Exception as e:  # the fixture travels with the repo; never fail the headline line over it
+        out["fachada_lm"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -259,10 +437,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the CUDA path is the only implementation (no CPU fallback)")
     torch.cuda.set_device(local)
-    numa_note = bind_host_thread_to_gpu_numa(local) if world > 1 else "not bound (single rank)"
+    numa_note = bind_host_thread(local, local, local_world) if world > 1 else "not bound (single rank)"
     from moptimizer_0_b200 import sharding
     collective, collective_note = "none", ""
     if world > 1:
@@ -273,14 +452,9 @@ def run_ours(args):
         ctx = capi.Context(local)
     if args.ctas_per_sm or args.threads:
         ctx.set_launch(args.ctas_per_sm, args.threads)
-    if args.strong_total:
-        first, last = sharding.shard_range(args.strong_total, rank, world)
-        n, n_total = last - first, args.strong_total
-    else:
-        n, first, n_total = args.n, rank * args.n, args.n * world
+    n, first, n_total = args.n, rank * args.n, args.n * world
     store = capi.Store(ctx, capi.MODEL_POINT2POINT, n, capi.F32)
-    store.generate(seed=2, gt=X_GT, lo=(0, 0, 0), hi=(10, 10, 10), first_index=first,
-                   noise_sigma=NOISE_SIGMA, outlier_fraction=OUTLIER_FRACTION, outlier_range=OUTLIER_RANGE)
+    store.generate(seed=SEED, gt=X_GT, first_index=first, **GEN)
     prob = capi.make_problem(capi.MODEL_POINT2POINT, capi.JAC_ANALYTICAL, capi.F32, loss=capi.LOSS_HUBER,
                              loss_param=HUBER_K, variant=capi.P2P_EXACT)
     x0 = np.zeros(6, dtype=np.float64)
@@ -292,6 +466,21 @@ def run_ours(args):
         torch.cuda.synchronize()
         ctx.synchronize()
 
+    def timed_steps(st, steps):
+        """K lock-step passes between two events on the context's stream; max over ranks, ms per step."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            ctx.linearize_async(st, prob, x0)
+        e1.record(stream)
+        barrier()
+        mine = e0.elapsed_time(e1)
+        t = torch.tensor([mine], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, mine / steps
+
     # Untimed pre-warm: the B200's clocks/power state take a few hundred ms of load to settle (measured:
     # the same kernel moves between 347 and 380 us during the first ~0.3 s), so a 20 ms timed region right
     # after an idle GPU does not measure the sustained rate.  Fixed step count => identical on every rank.
@@ -302,41 +491,70 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         ctx.linearize_async(store, prob, x0)
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        ctx.linearize_async(store, prob, x0)
-    ev1.record(stream)
-    barrier()
+    ms_step, ms_mine = timed_steps(store, args.steps)
     sampler.mark()
     sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
     H, b, s = ctx.result(6)
     # diagnostics for N > 1: every rank's own pass time with the exchange switched off (no lock-step coupling);
     # the gap between max(local) and the coupled step is what the collective + straggling cost
     local_ms = None
     if world > 1:
         ctx.set_exchange_enabled(False)
-        barrier()
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record(stream)
-        for _ in range(args.steps):
-            ctx.linearize_async(store, prob, x0)
-        l1.record(stream)
-        barrier()
+        _, mine = timed_steps(store, args.steps)
         ctx.set_exchange_enabled(True)
-        mine = torch.tensor([l0.elapsed_time(l1) / args.steps], dtype=torch.float64, device="cuda")
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
+        mt = torch.tensor([mine], dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(mt) for _ in range(world)]
+        dist.all_gather(allv, mt)
         local_ms = [float(v.item()) for v in allv]
     value = n_total / (ms_step * 1e-3) / 1e9
     peak, peak_kind = peaks()
-    achieved = BYTES_PER_RES * n / (ms_total / args.steps * 1e-3) / 1e9  # this rank's kernel, GB/s
+    achieved = BYTES_PER_RES * n / (ms_mine * 1e-3) / 1e9  # this rank's kernel, GB/s
+
+    # ---- N > 1: the exchanged result against every shard recomputed on ONE GPU (rank 0's) -------------------
+    vs_single = None
+    if world > 1 and not args.no_check:
+        barrier()
+        if rank == 0:
+            solo = capi.Context(local)  # a plain single-GPU context: no exchange, no peers
+            if args.ctas_per_sm or args.threads:
+                solo.set_launch(args.ctas_per_sm, args.threads)
+            tmp = capi.Store(solo, capi.MODEL_POINT2POINT, n, capi.F32)
+            tot = np.zeros(28)
+            for r_ in range(world):  # the exchange sums the ranks' slots in rank order, starting from 0.0
+                tmp.generate(seed=SEED, gt=X_GT, first_index=r_ * n, **GEN)
+                Hr, br, sr = solo.linearize(tmp, prob, x0)
+                tot = tot + sharding.pack(Hr, br, sr)
+            got = sharding.pack(H, b, s)
+            Hs, bs, ss = sharding.unpack(tot, 6)
+            vs_single = {"H_rel": float(np.max(np.abs(H - Hs)) / np.max(np.abs(Hs))),
+                         "b_rel": float(np.max(np.abs(b - bs)) / np.max(np.abs(bs))),
+                         "sum_rel": float(abs(s - ss) / abs(ss)), "bit_identical": bool(np.array_equal(got, tot)),
+                         "how": f"rank 0 regenerated all {world} shards on its own GPU with a single-GPU context, "
+                                "linearized each and added the packed results in rank order"}
+            tmp.close()
+            solo.close()
+        barrier()
+
+    # ---- measured ceilings of this box ----------------------------------------------------------------------
+    pk = None
+    if not args.no_peaks:
+        pk = ctx.measure_peaks() if rank == 0 else None
+        barrier()
+        h2d = ctx.measure_h2d(1 << 30, 1.0)  # every rank at the same time: the N-way concurrent ceiling
+        ht = torch.tensor([h2d], dtype=torch.float64, device="cuda")
+        if world > 1:
+            allh = [torch.zeros_like(ht) for _ in range(world)]
+            dist.all_gather(allh, ht)
+            h2d_all = [float(v.item()) for v in allh]
+        else:
+            h2d_all = [h2d]
+        if rank == 0:
+            pk["h2d_pinned_gbs_per_rank"] = h2d_all
+            pk["h2d_pinned_gbs_total"] = float(sum(h2d_all))
+            pk["how"] = ("csrc/mopt_peaks.cu micro-kernels on rank 0's GPU: 8 independent FFMA / FFMA2 chains per thread, "
+                         "2048 threads per SM; 2 GiB read-only stream; pinned host->device copies of 1 GiB in 64 MB "
+                         "cudaMemcpyAsync chunks for >= 1 s on all ranks at once")
 
     # ---- e2e: host (pinned) AoS buffers -> upload -> linearize -> H, b back, every step -------------
     e2e = None
@@ -360,7 +578,11 @@ def run_ours(args):
         e2e = {"host_affinity": numa_note, "value": n_total * args.e2e_steps / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(BYTES_PER_RES * n), "d2h_bytes_per_step": 8 * 28,
                "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "h2d_gbs_total": BYTES_PER_RES * n_total * args.e2e_steps / dt / 1e9,
                "matches_resident": bool(np.array_equal(He, H) and np.array_equal(be, b) and se == s)}
+        if pk is not None:
+            e2e["h2d_ceiling_gbs_total"] = pk["h2d_pinned_gbs_total"]
+            e2e["frac_of_h2d_ceiling"] = e2e["h2d_gbs_total"] / pk["h2d_pinned_gbs_total"]
         e_store.close()
         del ha, hb
 
@@ -376,6 +598,46 @@ def run_ours(args):
         lm = {"status": r.status, "executed_iterations": r.executed_iterations, "passes": r.num_passes,
               "seconds": dt, "lm_iters_per_s": (r.executed_iterations or 1) / dt, "sequence": r.sequence,
               "x_err_inf": float(np.max(np.abs(r.x - np.array(X_GT))))}
+
+    # ---- N > 1: BASELINE configs[3] as stated — 1 B correspondences in total, strong split ------------------
+    strong = None
+    strong_total = args.strong_total if args.strong_total >= 0 else (1_000_000_000 if world > 1 else 0)
+    if world > 1 and strong_total > 0:
+        store.close()
+        store = None
+        f0, f1 = sharding.shard_range(strong_total, rank, world)
+        sst = capi.Store(ctx, capi.MODEL_POINT2POINT, f1 - f0, capi.F32)
+        sst.generate(seed=SEED, gt=X_GT, first_index=f0, **GEN)
+        for _ in range(max(args.warmup, 3) + 200):
+            ctx.linearize_async(sst, prob, x0)
+        sms, _ = timed_steps(sst, args.steps)
+        Hs_, bs_, ss_ = ctx.result(6)
+        ctx.lm_minimize([sst], [prob], x0, max_iterations=2)
+        barrier()
+        t0 = time.perf_counter()
+        r = ctx.lm_minimize([sst], [prob], x0, max_iterations=50)
+        barrier()
+        dt = time.perf_counter() - t0
+        ach = BYTES_PER_RES * strong_total / (sms * 1e-3) / 1e9
+        strong = {"workload": f"point2point {strong_total / 1e9:.0f}B correspondences in total, contiguous shards over {world} GPUs, "
+                              "one exchange of 28 packed doubles per step (BASELINE configs[3])",
+                  "n_total": strong_total, "n_per_gpu": f1 - f0, "scaling": "strong", "ms_per_step": sms,
+                  "Gres_per_s": strong_total / (sms * 1e-3) / 1e9,
+                  "roofline": {"bound": "hbm", "achieved": ach, "peak": peak * world, "unit": "GB/s",
+                               "frac": ach / (peak * world), "note": "aggregate over all ranks against N x the measured copy peak"},
+                  "check": {"sum_rtr": ss_, "H00": float(Hs_[0, 0])},
+                  "lm": {"status": r.status, "executed_iterations": r.executed_iterations, "passes": r.num_passes,
+                         "seconds": dt, "lm_iters_per_s": (r.executed_iterations or 1) / dt, "sequence": r.sequence,
+                         "x_err_inf": float(np.max(np.abs(r.x - np.array(X_GT))))}}
+        sst.close()
+
+    # ---- the other BASELINE configurations (single-GPU workloads: rank 0 of an N = 1 run) ------------------------
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = run_other_configs(capi, ctx, Timer(torch, ctx, stream), pk, peak)
+    if strong is not None:
+        configs = configs or {}
+        configs["p2p_1B_strong"] = strong
 
     # ---- CPU baseline: oracle port on a bounded sample of the same data (rank 0, N=1 only) ----------
     cpu = None
@@ -407,29 +669,36 @@ def run_ours(args):
                                          "(tst/parallel.cpp) restated with std::thread"}}
 
     if rank == 0:
-        traffic, traffic_src = ncu_traffic_bytes(n)
+        counts = inst_counts()
+        tr = counts.get("p2p_gen2_f32", {})
+        traffic = tr.get("dram_bytes_per_launch") if n == 100_000_000 else None
+        gen1 = args.threads == 1024
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong" if args.strong_total else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"point2point {n / 1e6:.0f}M correspondences/GPU, analytical Jacobian + Huber(k=0.05), x0=0",
-                       "n_per_gpu": n, "n_total": n_total, "store": "fp32 planar (SoA) streams, 24 B/correspondence",
-                       "accumulate": "fp32 partials folded into fp64 every 64 residuals/thread",
-                       "prewarm_steps": args.prewarm_steps,
-                       "l2": f"inputs {BYTES_PER_RES * n / 1e6:.0f} MB per GPU >> 126 MB L2, no flush needed",
-                       "collective": {"none": "none",
-                                      "p2p": "NVLink peer exchange of 28 x f64, pushed and reduced by the pass kernel's last CTA"
-                                             + (" (separate consumer kernel)" if os.environ.get("MOPT_PEER_CONSUMER") == "kernel" else ""),
-                                      "nccl": "ncclAllReduce(28 x f64) per step"}[collective]
-                                     + (f" (p2p unavailable: {collective_note})" if collective_note else "")},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(n, n_total),
+            "impl_detail": {"store": "fp32 planar (SoA) streams, 24 B/correspondence",
+                            "kernel": "first generation (register-direct loads, scalar fp32)" if gen1 else
+                                      "TMA bulk-copy ring (cp.async.bulk + mbarrier) + packed fp32 (FFMA2), one CTA per SM",
+                            "accumulate": "fp32 partials folded into fp64 every 64 residuals per accumulator lane",
+                            "prewarm_steps": args.prewarm_steps,
+                            "collective": {"none": "none",
+                                           "p2p": "NVLink peer exchange of 28 x f64, pushed and reduced by the pass kernel's last CTA"
+                                                  + (" (separate consumer kernel)" if os.environ.get("MOPT_PEER_CONSUMER") == "kernel" else ""),
+                                           "nccl": "ncclAllReduce(28 x f64) per step"}[collective]
+                                          + (f" (p2p unavailable: {collective_note})" if collective_note else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src,
+                         "traffic": traffic,
+                         "traffic_source": (tr.get("source", "") + " — ncu --set full capture of this kernel on this workload, "
+                                            "committed; not re-measured in this run") if traffic else None,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+                         "frac_of_read_stream": (achieved / pk["hbm_read_gbs"]) if pk else None,
                          "achieved_from": "24 B x n_per_gpu / (CUDA-event time of the K timed steps / K) on the "
                                           "context's stream; a step = this kernel alone (model->setup(x) runs inside it; sharded contexts "
                                           "launch the one-warp setup kernel before it)",
-                         "kernel": "p2p_moment_kernel<float,float,HUBER,QROT,...,FUSED>",
+                         "kernel": "p2p_moment_kernel<float,float,HUBER,QROT,...,FUSED>" if gen1 else
+                                   "p2p_moment2_kernel<HUBER,QROT,...> (csrc/mopt_pass_p2p2.cuh)",
                          "algorithmic_bytes_per_launch": BYTES_PER_RES * n},
             "clocks": sampler.summary(),
             # per step: the pass kernel with setup fused in (single GPU) or setup kernel + pass kernel (sharded contexts)
@@ -437,16 +706,23 @@ def run_ours(args):
             "gpu_launches": ((1 if world == 1 or os.environ.get("MOPT_FUSED_SETUP", "")[:1] not in ("", "0") else 2) + (1 if world > 1 and (collective == "nccl" or os.environ.get("MOPT_PEER_CONSUMER") == "kernel") else 0)) * args.steps,
             "check": {"sum_rtr": s, "H00": float(H[0, 0]), "b0": float(b[0])},
         }
+        if vs_single is not None:
+            line["check"]["vs_single_gpu"] = vs_single
         if local_ms is not None:
             line["per_rank_uncoupled_ms_per_step"] = local_ms
+        if pk is not None:
+            line["peaks"] = pk
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if lm is not None:
             line["lm"] = lm
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
-    store.close()
+    if store is not None:
+        store.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -157,7 +157,17 @@ typedef struct mopt_lm_options {
   int32_t scalar_dtype;      /* mopt_dtype of the LM arithmetic (lambda, rho, solve): the reference's Scalar */
   int32_t speculative;       /* 1: every trial pass evaluates cost AND H,b at x+delta so an accepted step needs
                                 no second pass (valid while model->update(x) is a no-op); 0: reference pass order */
+  int32_t flags;             /* mopt_lm_flags; mopt_lm_default_options sets MOPT_LM_STAGNATION_STOP */
+  int32_t reserved;
 } mopt_lm_options;
+/* MOPT_LM_STAGNATION_STOP: end with SMALL_DELTA (CONVERGED if the cost is small) when an accepted step is below
+ * isDeltaSmall's threshold (delta.h:11-16) AND left sum r^T r bit-for-bit unchanged.  The reference accepts such a
+ * step (rho = 0 is not < 0, levenberg_marquadt_dyn.cpp:97), doubles lambda (:113) and carries on; it leaves that
+ * state only because its y0 (serial loop, linearization.h:142-154) and y_i (TBB parallel_reduce, :52-62) are summed
+ * in different orders, so that the sign of rho is rounding noise and the next negative one returns SMALL_DELTA
+ * (:98-101).  On the device both sums come from the same deterministic kernel and the noise never arrives: without
+ * this flag such a run spends every remaining iteration on rho = 0 steps (DESIGN.md "LM tail").  0 = literal. */
+typedef enum mopt_lm_flags { MOPT_LM_STAGNATION_STOP = 1 } mopt_lm_flags;
 
 typedef struct mopt_lm_trial {
   int32_t outer_iteration, k, accepted, reserved;
@@ -329,6 +339,22 @@ MOPT_API int mopt_user_model_compile(const char* cuda_source, const mopt_user_mo
 MOPT_API int mopt_user_model_release(int model_id);
 /* Compiler log of the most recent NVRTC compilation of this model (warnings included), "" if none. */
 MOPT_API const char* mopt_user_model_log(int model_id);
+
+/* ---- measured ceilings of this box (roofline denominators) --------------------------- */
+/* MEASURED_PEAKS.json holds an HBM copy and a bf16 GEMM figure only.  The ALU-bound paths (finite differences of
+ * the curve and camera models, computeHessianNumerical, linearization.h:65-124) are judged against an fp32 rate
+ * measured here with committed micro-kernels (csrc/mopt_peaks.cu). */
+typedef struct mopt_peaks {
+  double fp32_fma_tflops;         /* scalar FFMA, 8 independent chains per thread, 2048 threads per SM */
+  double fp32_fma2_tflops;        /* packed FFMA2 (fma.rn.f32x2), same shape */
+  double issue_gwarp_inst_per_s;  /* warp instructions issued per second, in 1e9: the FFMA-only rate (1 per clock per scheduler) */
+  double hbm_read_gbs;            /* read-only stream of 2 GiB, 16-byte loads */
+  double reserved[4];
+} mopt_peaks;
+MOPT_API int mopt_measure_peaks(mopt_ctx* ctx, mopt_peaks* out);
+/* Pinned host -> device copy rate of this process over at least `seconds` (concurrent callers on other GPUs
+ * overlap): the ceiling of the end-to-end path that starts from host buffers (mopt_upload_and_linearize). */
+MOPT_API int mopt_measure_h2d(mopt_ctx* ctx, uint64_t bytes, double seconds, double* gbs);
 
 /* Pinned host memory for callers that want full-speed uploads. */
 MOPT_API int mopt_host_alloc(void** ptr, uint64_t bytes);

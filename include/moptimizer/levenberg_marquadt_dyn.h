@@ -38,6 +38,7 @@ class LevenbergMarquadtDynamic : public Optimizer<Scalar> {
     opt.lambda_factor = double(lm_init_lambda_factor_);
     opt.scalar_dtype = device::dtypeOf<Scalar>();
     opt.speculative = speculative_ ? 1 : 0;
+    opt.flags = stagnation_stop_ ? MOPT_LM_STAGNATION_STOP : 0;
     double xd[MOPT_MAX_PARAMETERS] = {0};
     for (int i = 0; i < num_parameters_; ++i) xd[i] = double(x0[i]);
     report_.reset(new mopt_lm_report());
@@ -62,6 +63,10 @@ class LevenbergMarquadtDynamic : public Optimizer<Scalar> {
   /// New: 1 (default) fuses cost and linearization of every trial point into one pass; 0 keeps the reference's
   /// pass order (linearize at x, then cost at each trial).  Same results either way.
   inline void setSpeculativeLinearization(bool on) { speculative_ = on; }
+  /// New: on (default) ends with SMALL_DELTA once an accepted step is below isDeltaSmall's threshold and leaves the
+  /// cost bit-for-bit unchanged; off is the literal loop (rho = 0 steps until the iterations run out, see
+  /// MOPT_LM_STAGNATION_STOP in mopt_capi.h).
+  inline void setStagnationStop(bool on) { stagnation_stop_ = on; }
   /// New: the device iteration trace of the last minimize() (nullptr before the first call).
   const mopt_lm_report* report() const { return report_.get(); }
 
@@ -82,6 +87,7 @@ class LevenbergMarquadtDynamic : public Optimizer<Scalar> {
   Scalar lm_lambda_;
   unsigned int lm_max_iterations_;
   bool speculative_ = true;
+  bool stagnation_stop_ = true;
   std::unique_ptr<mopt_lm_report> report_;
 };
 

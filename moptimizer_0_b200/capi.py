@@ -25,6 +25,7 @@ P2P_EXACT, P2P_REFTEST, P2P_REFTEST_COLMAJOR, P2P_LEFT = range(4)
 MANIFOLD_ADDITIVE, MANIFOLD_SO3_LEFT = 0, 1
 FLAG_GENERIC_KERNEL = 1
 FLAG_STABLE_FD = 2
+LM_STAGNATION_STOP = 1
 LOSS_NONE, LOSS_GEMAN_MCCLURE, LOSS_HUBER = range(3)
 STATUS = ["CONVERGED", "MAXIMUM_ITERATIONS_REACHED", "SMALL_DELTA", "NUMERIC_ERROR", "FATAL_ERROR"]
 MODEL_SHAPE = {  # model -> (P, O, ncomp_a, ncomp_b)
@@ -44,6 +45,7 @@ EXPORTS = [
     "mopt_nn_index_create", "mopt_nn_index_destroy", "mopt_store_set_target", "mopt_store_reassociate",
     "mopt_ctx_peer_handle", "mopt_ctx_open_peers", "mopt_ctx_set_exchange_enabled",
     "mopt_user_model_compile", "mopt_user_model_release", "mopt_user_model_log",
+    "mopt_measure_peaks", "mopt_measure_h2d",
 ]
 MODEL_USER_BASE = 1000
 PEER_HANDLE_BYTES = 64
@@ -59,7 +61,8 @@ class Problem(C.Structure):
 
 class LmOptions(C.Structure):
     _fields_ = [("max_iterations", C.c_int32), ("lm_max_iterations", C.c_int32), ("lambda_factor", C.c_double),
-                ("scalar_dtype", C.c_int32), ("speculative", C.c_int32)]
+                ("scalar_dtype", C.c_int32), ("speculative", C.c_int32), ("flags", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class LmTrial(C.Structure):
@@ -84,6 +87,11 @@ class UserModelDesc(C.Structure):
     _fields_ = [("num_parameters", C.c_int32), ("num_outputs", C.c_int32), ("ncomp_a", C.c_int32),
                 ("ncomp_b", C.c_int32), ("has_jacobian", C.c_int32), ("set_size", C.c_int32),
                 ("rot_offset", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Peaks(C.Structure):
+    _fields_ = [("fp32_fma_tflops", C.c_double), ("fp32_fma2_tflops", C.c_double),
+                ("issue_gwarp_inst_per_s", C.c_double), ("hbm_read_gbs", C.c_double), ("reserved", C.c_double * 4)]
 
 
 class MoptError(RuntimeError):
@@ -123,6 +131,8 @@ def lib():
         L.mopt_compute_cost.argtypes = [vp, vp, C.POINTER(Problem), dp, dp]
         L.mopt_linearize_async.argtypes = [vp, vp, C.POINTER(Problem), dp]
         L.mopt_ctx_result.argtypes = [vp, C.c_int, dp, dp, dp]
+        L.mopt_measure_peaks.argtypes = [vp, C.POINTER(Peaks)]
+        L.mopt_measure_h2d.argtypes = [vp, C.c_uint64, C.c_double, dp]
         L.mopt_upload_and_linearize.argtypes = [vp, vp, C.POINTER(Problem), vp, vp, C.c_int, i64, dp, dp, dp, dp]
         L.mopt_lm_minimize.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(Problem), C.POINTER(LmOptions), dp,
                                        C.POINTER(LmReport)]
@@ -253,6 +263,19 @@ class Context:
         check(lib().mopt_ctx_stream(self._h, C.byref(s)))
         return s.value
 
+    def measure_peaks(self) -> dict:
+        """Measured ceilings of this GPU (fp32 FMA / packed FMA TFLOP/s, warp-instruction issue rate, HBM read)."""
+        p = Peaks()
+        check(lib().mopt_measure_peaks(self._h, C.byref(p)))
+        return {"fp32_fma_tflops": p.fp32_fma_tflops, "fp32_fma2_tflops": p.fp32_fma2_tflops,
+                "issue_gwarp_inst_per_s": p.issue_gwarp_inst_per_s, "hbm_read_gbs": p.hbm_read_gbs}
+
+    def measure_h2d(self, nbytes: int = 1 << 30, seconds: float = 1.0) -> float:
+        """Pinned host -> device GB/s of this process over at least `seconds` (ranks overlap when called together)."""
+        g = C.c_double(0)
+        check(lib().mopt_measure_h2d(self._h, int(nbytes), float(seconds), C.byref(g)))
+        return g.value
+
     def set_launch(self, ctas_per_sm: int = 0, threads: int = 0):
         check(lib().mopt_ctx_set_launch(self._h, ctas_per_sm, threads))
 
@@ -300,7 +323,8 @@ class Context:
         return H, b, s.value
 
     def lm_minimize(self, stores: Sequence["Store"], problems: Sequence[Problem], x0, max_iterations: int = 15,
-                    lm_iterations: int = 3, scalar_dtype: int = F64, speculative: bool = True) -> "LmResult":
+                    lm_iterations: int = 3, scalar_dtype: int = F64, speculative: bool = True,
+                    stagnation_stop: bool = True) -> "LmResult":
         n = len(stores)
         hs = (C.c_void_p * n)(*[s.handle for s in stores])
         ps = (Problem * n)(*problems)
@@ -308,6 +332,7 @@ class Context:
         lib().mopt_lm_default_options(C.byref(opt))
         opt.max_iterations, opt.lm_max_iterations = max_iterations, lm_iterations
         opt.scalar_dtype, opt.speculative = scalar_dtype, 1 if speculative else 0
+        opt.flags = LM_STAGNATION_STOP if stagnation_stop else 0
         x = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).copy())
         rep = LmReport()
         check(lib().mopt_lm_minimize(self._h, n, hs, ps, C.byref(opt), _dp(x), C.byref(rep)))

@@ -84,6 +84,7 @@ __global__ void setup_kernel(CostSlot* slot, XArg x) { setup_cost(slot->cost, x.
 struct LmInit {
   int P, n_costs, max_it, lm_max_it, speculative, scalar_f32;
   double lambda_factor;
+  int flags;
   double x0[kMaxP];
 };
 
@@ -92,6 +93,7 @@ __global__ void lm_init_kernel(LmState* st, CostSlot* slots, LmInit in) {
   if (threadIdx.x == 0) {
     st->P = in.P; st->n_costs = in.n_costs; st->max_it = in.max_it; st->lm_max_it = in.lm_max_it;
     st->speculative = in.speculative; st->scalar_f32 = in.scalar_f32; st->lambda_factor = in.lambda_factor;
+    st->flags = in.flags;
     for (int i = 0; i < kMaxP; ++i) {
       const double v = i < in.P ? (in.scalar_f32 ? double(float(in.x0[i])) : in.x0[i]) : 0.0;
       st->x[i] = v; st->xi[i] = v; st->x_eval[i] = v; st->delta[i] = 0.0;
@@ -107,10 +109,17 @@ __global__ void lm_init_kernel(LmState* st, CostSlot* slots, LmInit in) {
 }
 
 // One optimizer transition between passes; also publishes the done flag of this slot to the host.
-__global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* slots, int* flag) {
+__global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* slots, int* flag, const int* xerr) {
   __shared__ int s_act;
   __shared__ LmSolveScratch s_scratch;
   const int lane = threadIdx.x;
+  if (*reinterpret_cast<const volatile int*>(xerr)) {  // a peer exchange timed out: `trial` is not a total
+    if (lane == 0) {
+      if (!st->done) lm_finish(st, MOPT_FATAL_ERROR);
+      *flag = 1;
+    }
+    return;
+  }
   if (lane == 0) s_act = st->scalar_f32 ? lm_step_thread<float>(st, trial, slots[0].cost) : lm_step_thread<double>(st, trial, slots[0].cost);
   __syncthreads();  // lane 0's state writes are visible to the warp below
   if (s_act == 2) {  // damped solve + proposal, the lanes sharing the factorization
@@ -139,9 +148,10 @@ __global__ void ldlt_warp_test_kernel(int n, const double* A, const double* rhs,
 // Consumer side of the NVLink peer exchange (mopt_pass.cuh peer_push): acquire every rank's sequence flag for
 // this exchange, then sum the slots in rank order into `out` — identical bits on every rank.
 __global__ void peer_reduce_kernel(XSlot* local, int world, unsigned long long seq, PassResult* out, int npk,
-                                   const int* mode_ptr, int mode_override, int* err) {
+                                   const int* mode_ptr, int mode_override, int* err, int* err_dev) {
   const int mode = mode_override >= 0 ? mode_override : *mode_ptr;
   if (mode == PASS_SKIP) return;  // the optimizer finished: no rank pushed, nothing to wait for
+  if (*reinterpret_cast<const volatile int*>(err_dev)) return;  // an earlier exchange already failed
   const int base = int(seq & 1ull) * kMaxWorld;
   __shared__ int s_ok;
   if (threadIdx.x == 0) {
@@ -160,7 +170,10 @@ __global__ void peer_reduce_kernel(XSlot* local, int world, unsigned long long s
         __nanosleep(64);
       }
     }
-    if (!ok) *err = 1;
+    if (!ok) {
+      *err = 1;
+      *err_dev = 1;
+    }
     s_ok = ok ? 1 : 0;
     __threadfence_system();
   }
@@ -297,6 +310,7 @@ int launch_pass(mopt_ctx* ctx, const mopt_store* st, const mopt_problem* p, int 
     a.peer.push = 1;
     a.peer.fused = ctx->fused_consumer ? 1 : 0;
     a.peer.err = ctx->d_xerr;
+    a.peer.err_dev = ctx->d_xerr_dev;
     a.peer.seq = ++ctx->xseq;
   }
   PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
@@ -322,7 +336,7 @@ int allreduce_trial(mopt_ctx* ctx, int P, int mode_override) {
   if (ctx->peers_open) {
     if (ctx->fused_consumer) return MOPT_OK;  // the pass kernel's last CTA already wrote the totals (peer_push)
     peer_reduce_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_xbuf, ctx->world, ctx->xseq, ctx->d_trial, packed_size(P),
-                                                  &ctx->d_lm->pass_mode, mode_override, ctx->d_xerr);
+                                                  &ctx->d_lm->pass_mode, mode_override, ctx->d_xerr, ctx->d_xerr_dev);
     MOPT_CUDA_TRY(cudaGetLastError());
     return MOPT_OK;
   }
@@ -348,7 +362,17 @@ void unpack_result(const PassResult& r, int P, double* H, double* b, double* sum
   if (sum) *sum = r.v[packed_size(P) - 1];
 }
 
+// After a peer-exchange timeout the sequence numbers of the ranks no longer agree: the context is unusable.
+int check_exchange_alive(const mopt_ctx* ctx) {
+  if (ctx->h_xerr && *reinterpret_cast<volatile int*>(ctx->h_xerr)) {
+    set_last_error("an earlier peer exchange on this context timed out (a rank died); destroy the context");
+    return MOPT_ERR_COMM;
+  }
+  return MOPT_OK;
+}
+
 int enqueue_pass(mopt_ctx* ctx, mopt_store* st, const mopt_problem* p, const double* x, int mode) {
+  MOPT_TRY(check_exchange_alive(ctx));
   MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
   MOPT_TRY(stage_cost(ctx, 0, p));
   const int P = p->num_parameters;
@@ -425,6 +449,8 @@ int ctx_alloc(mopt_ctx* ctx) {
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_xerr, sizeof(int), cudaHostAllocMapped));
   *ctx->h_xerr = 0;
   MOPT_CUDA_TRY(cudaHostGetDevicePointer(&ctx->d_xerr, ctx->h_xerr, 0));
+  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_xerr_dev, sizeof(int)));
+  MOPT_CUDA_TRY(cudaMemset(ctx->d_xerr_dev, 0, sizeof(int)));
   ctx->flags_capacity = 4096;
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_flags, sizeof(int) * ctx->flags_capacity, cudaHostAllocMapped));
   MOPT_CUDA_TRY(cudaHostGetDevicePointer(&ctx->d_flags, ctx->h_flags, 0));
@@ -518,6 +544,7 @@ int mopt_ctx_destroy(mopt_ctx* ctx) try {
     for (int r = 0; r < ctx->world; ++r)
       if (r != ctx->rank && ctx->peer_base[r]) cudaIpcCloseMemHandle(ctx->peer_base[r]);
   cudaFree(ctx->d_xbuf);
+  cudaFree(ctx->d_xerr_dev);
   if (ctx->h_xerr) cudaFreeHost(ctx->h_xerr);
   cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trial);
   cudaFree(ctx->d_slots); cudaFree(ctx->d_lm);
@@ -658,6 +685,7 @@ void mopt_lm_default_options(mopt_lm_options* o) {
   o->lambda_factor = 1e-9;      // levenberg_marquadt_dyn.cpp:16
   o->scalar_dtype = MOPT_F64;
   o->speculative = 1;
+  o->flags = MOPT_LM_STAGNATION_STOP;
 }
 
 int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, const mopt_problem* problems,
@@ -681,6 +709,7 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
     MOPT_REQUIRE(problems[c].num_parameters == P, "all cost terms must share the parameter vector");
     MOPT_REQUIRE(problems[c].manifold == problems[0].manifold, "all cost terms must use the same manifold");
   }
+  MOPT_TRY(check_exchange_alive(ctx));
   MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
   std::memset(report, 0, sizeof(*report));
   if (opt.max_iterations == 0) {
@@ -699,6 +728,7 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
   for (int c = 0; c < n_costs; ++c) has_update = has_update || (stores[c]->index != nullptr);
   if (has_update) in.speculative = 0;
   in.lambda_factor = opt.lambda_factor;
+  in.flags = opt.flags;
   for (int i = 0; i < P; ++i) in.x0[i] = x[i];
   lm_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_slots, in);
   MOPT_CUDA_TRY(cudaGetLastError());
@@ -719,20 +749,23 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
   // Passes are enqueued in batches, always one batch ahead of the one whose done flag is being
   // awaited, so the device never idles on the host; every rank reads the flag of the same slot,
   // so all ranks stop after the same number of (collective-bearing) slots.
-  const int64_t max_slots64 = int64_t(opt.max_iterations) * (int64_t(opt.lm_max_iterations) + 1) + 2;
-  const int max_slots = int(max_slots64 < ctx->flags_capacity ? max_slots64 : ctx->flags_capacity);
+  // The per-slot done flags live in a ring of flags_capacity mapped words: at most two batches are ever in flight
+  // and a slot's word is free again once its batch event has completed, so any slot budget fits.
+  const int64_t max_slots = int64_t(opt.max_iterations) * (int64_t(opt.lm_max_iterations) + 1) + 2;
   const int kBatch = 2;
-  int enq = 0;
-  auto enqueue_batch = [&](int par, int* last_slot) -> int {
+  int64_t enq = 0;
+  auto slot_index = [&](int64_t slot) { return int(slot % ctx->flags_capacity); };
+  auto enqueue_batch = [&](int par, int64_t* last_slot) -> int {
     *last_slot = -1;
     for (int s = 0; s < kBatch && enq < max_slots; ++s, ++enq) {
-      ctx->h_flags[enq] = 0;
+      ctx->h_flags[slot_index(enq)] = 0;
       // cost->update(x0): re-associate correspondences; the kernel gates itself on "start of an outer iteration"
       for (int c = 0; c < n_costs; ++c) MOPT_TRY(enqueue_reassociate(stores[c], &ctx->d_slots[c].pb, ctx->d_lm));
       for (int c = 0; c < n_costs; ++c)
         MOPT_TRY(launch_pass(ctx, stores[c], &problems[c], c, c > 0 ? 1 : 0, -1, c == n_costs - 1));
       MOPT_TRY(allreduce_trial(ctx, P, -1));
-      lm_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_trial, ctx->d_slots, ctx->d_flags + enq);
+      lm_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_trial, ctx->d_slots, ctx->d_flags + slot_index(enq),
+                                                ctx->d_xerr_dev);
       MOPT_CUDA_TRY(cudaGetLastError());
       MOPT_TRY(user_setups());
       *last_slot = enq;
@@ -740,12 +773,14 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
     if (*last_slot >= 0) MOPT_CUDA_TRY(cudaEventRecord(ctx->ev_batch[par], ctx->stream));
     return MOPT_OK;
   };
-  int par = 0, cur_last = -1, next_last = -1;
+  int par = 0;
+  int64_t cur_last = -1, next_last = -1;
   MOPT_TRY(enqueue_batch(par, &cur_last));
   while (cur_last >= 0) {
     MOPT_TRY(enqueue_batch(par ^ 1, &next_last));  // keep one batch in flight behind the awaited one
     MOPT_CUDA_TRY(cudaEventSynchronize(ctx->ev_batch[par]));
-    if (reinterpret_cast<volatile int*>(ctx->h_flags)[cur_last] != 0) break;
+    if (reinterpret_cast<volatile int*>(ctx->h_flags)[slot_index(cur_last)] != 0) break;
+    if (ctx->h_xerr && *reinterpret_cast<volatile int*>(ctx->h_xerr)) break;  // a peer died: stop enqueuing
     par ^= 1;
     cur_last = next_last;
   }
@@ -756,7 +791,7 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
   MOPT_CUDA_TRY(cudaMemcpyAsync(hs, ctx->d_lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
   MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if (ctx->h_xerr && *reinterpret_cast<volatile int*>(ctx->h_xerr)) {
-    set_last_error("peer exchange timed out waiting for another rank");
+    set_last_error("peer exchange timed out waiting for another rank; this context cannot be used any more");
     return MOPT_ERR_COMM;
   }
   if (!hs->done) {

@@ -211,6 +211,21 @@ int mopt_cloud_read_binary(const char* path, int pinned, int* host_dtype, int* k
     return MOPT_ERR_INVALID_ARGUMENT;
   }
   const size_t esz = h.dtype == MOPT_F32 ? 4 : 8;
+  // the header is untrusted: the payload it announces must be exactly what the file holds (this also rules out
+  // esz * keep * n wrapping around size_t and under-allocating the buffer fread then fills)
+  bool size_ok = std::fseek(f, 0, SEEK_END) == 0;
+  const long file_end = size_ok ? std::ftell(f) : -1L;
+  size_ok = size_ok && file_end >= long(sizeof(h)) && std::fseek(f, long(sizeof(h)), SEEK_SET) == 0;
+  if (size_ok) {
+    const unsigned long long payload = (unsigned long long)(file_end) - sizeof(h);
+    const unsigned long long rec = (unsigned long long)(esz) * (unsigned long long)(h.keep);
+    size_ok = h.keep <= 1024 && (h.n == 0 ? payload == 0 : (payload / rec == (unsigned long long)(h.n) && payload % rec == 0));
+  }
+  if (!size_ok) {
+    std::fclose(f);
+    set_last_error("cloud file header does not match the file size (truncated or corrupt)");
+    return MOPT_ERR_INVALID_ARGUMENT;
+  }
   void* dst = nullptr;
   const int s = alloc_host(&dst, esz * size_t(h.keep) * size_t(h.n), pinned);
   if (s != MOPT_OK) {

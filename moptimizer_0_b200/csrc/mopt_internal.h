@@ -49,6 +49,7 @@ struct mopt_ctx {
   unsigned long long xseq = 0;
   int* h_xerr = nullptr;                         // mapped: set by the consumer kernel on a wait timeout
   int* d_xerr = nullptr;
+  int* d_xerr_dev = nullptr;                     // device-resident copy, read by the kernels that follow a failed exchange
 };
 
 struct mopt_store {

@@ -17,6 +17,8 @@ struct LmState {
   // configuration (written by lm_init_kernel)
   int P, n_costs, max_it, lm_max_it, speculative, scalar_f32;
   double lambda_factor;
+  int flags;  // mopt_lm_flags
+  int pad0_;
   // optimizer state
   double x[kMaxP], xi[kMaxP], delta[kMaxP], x_eval[kMaxP];
   PassResult cur;  // accepted linearization at x
@@ -250,6 +252,19 @@ __device__ inline int lm_step_thread(LmState* st, const PassResult* trial, const
       }
     } else {  // :112-114
       for (int i = 0; i < P; ++i) st->x[i] = st->xi[i];
+      // MOPT_LM_STAGNATION_STOP (not in the reference): a step below isDeltaSmall's threshold that leaves the cost
+      // bit-for-bit unchanged is "accepted" with rho = 0 by :97 and doubles lambda (:113) for as long as iterations
+      // remain.  The reference leaves this state by chance: its y0 (serial loop, linearization.h:142-154) and yi
+      // (TBB parallel_reduce, :52-62) are summed in different orders, so rho's sign is rounding noise and the next
+      // negative one ends in SMALL_DELTA (:98-101).  Both sums come from the same deterministic kernel here.
+      if ((st->flags & MOPT_LM_STAGNATION_STOP) && yi == y0) {
+        S m = S(0);
+        for (int i = 0; i < P; ++i) m = fmax(m, fabs(S(st->delta[i])));
+        if (m < sqrt(scalar_eps<S>())) {
+          lm_finish(st, is_cost_small<S>(yi) ? MOPT_CONVERGED : MOPT_SMALL_DELTA);
+          return 0;
+        }
+      }
       // std::pow(2 rho - 1, 3) evaluated in double (:113); v*v*v is within 1 ulp of it and keeps the library pow
       // (hundreds of instructions of a kernel that is instruction-fetch bound) out of the step
       const double v = double(S(2) * rho - S(1));

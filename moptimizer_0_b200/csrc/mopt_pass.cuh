@@ -29,7 +29,8 @@ struct PeerArgs {
   int fused;               // 1: the pushing warp also waits for every rank's slot and writes the totals to `out`
                            //    (no separate consumer kernel); 0: peer_reduce_kernel does that
   unsigned long long seq;  // sequence number of this exchange (>= 1)
-  int* err;                // set to 1 when a peer's slot does not arrive in time (mapped host memory)
+  int* err;                // set to 1 when a peer's slot does not arrive in time (mapped host memory: the host polls it)
+  int* err_dev;            // device copy of the same word: later kernels of the stream read it and skip their work
 };
 
 struct PassArgs {
@@ -111,6 +112,12 @@ __device__ __forceinline__ bool grid_reduce(const double (&lane_val)[NCH], const
   return grid_reduce_shared<NRAW, NCH * V, THREADS>(a, s_tot, s_warp);
 }
 
+// A peer exchange earlier in this stream timed out (a rank died): the totals are meaningless from here on, so every
+// later pass returns at once instead of spinning ~10 s on the dead peer again; the host sees the mapped error word.
+__device__ __forceinline__ bool peer_failed(const PassArgs& a) {
+  return a.peer.push && *reinterpret_cast<const volatile int*>(a.peer.err_dev) != 0;
+}
+
 // Last CTA of a pass, after `out` is complete: push the packed result into this rank's slot on every rank.
 __device__ __forceinline__ void peer_push(const PassArgs& a, int npk) {
   if (!a.peer.push) return;
@@ -153,9 +160,14 @@ __device__ __forceinline__ void peer_push(const PassArgs& a, int npk) {
       __nanosleep(32);
     }
   }
-  ok = __all_sync(0xffffffffu, ok);  // also orders every lane's slot reads after the acquiring lanes' flag reads
+  ok = __all_sync(0xffffffffu, ok);
+  __syncwarp();  // memory ordering among the lanes: every lane's slot reads below come after the acquiring lanes' flag reads
   if (!ok) {
-    if (lane == 0) *a.peer.err = 1;
+    if (lane == 0) {
+      *a.peer.err = 1;
+      *a.peer.err_dev = 1;
+      __threadfence_system();
+    }
     return;
   }
   for (int k = lane; k < npk; k += 32) {
@@ -330,6 +342,7 @@ template <typename ST, typename CT, int LOSS, bool QROT, int THREADS, int MINB, 
 __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArgs a) {
   const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
   if (mode == PASS_SKIP) return;
+  if (peer_failed(a)) return;
   constexpr int VEC = VecOf<ST>::N;
   constexpr bool kFp32Acc = (sizeof(CT) == 4);
   // fp32 partials are folded into fp64 every FLUSH_ROUNDS*VEC residuals/thread
@@ -518,6 +531,7 @@ template <class M, typename ST, typename CT, bool NUMERIC, int THREADS, int MINB
 __global__ void __launch_bounds__(THREADS, MINB) dense_pass_kernel(const PassArgs a) {
   const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
   if (mode == PASS_SKIP) return;
+  if (peer_failed(a)) return;
   constexpr int P = M::P, O = M::O, NS = M::NS;
   constexpr int VEC = VecOf<ST>::N;
   constexpr int NRAW = P * (P + 1) / 2 + P + 1;
@@ -855,6 +869,7 @@ template <class M, typename ST, typename CT, int THREADS, bool NUMERIC = true, b
 __global__ void __launch_bounds__(THREADS, (sizeof(CT) == 4 ? 2 : 1)) wide_pass_kernel(const PassArgs a) {
   const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
   if (mode == PASS_SKIP) return;
+  if (peer_failed(a)) return;
   constexpr int P = M::P, O = M::O, NS = M::NS;
   constexpr int NRAW = P * (P + 1) / 2 + P + 1;
   constexpr int NCH = (NRAW + 31) / 32;

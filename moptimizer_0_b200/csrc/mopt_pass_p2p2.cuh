@@ -134,6 +134,7 @@ template <int LOSS, bool QROT, bool MASKED, bool FUSED, int THREADS, int MINB, i
 __global__ void __launch_bounds__(THREADS, MINB) p2p_moment2_kernel(const PassArgs a) {
   const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
   if (mode == PASS_SKIP) return;
+  if (peer_failed(a)) return;
   constexpr int NW = THREADS / 32;
   constexpr int CHUNK = THREADS * U;  // float4 groups per stream per CTA per round
 

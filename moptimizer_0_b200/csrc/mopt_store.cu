@@ -48,11 +48,13 @@ __device__ __forceinline__ float u01(uint64_t seed, int64_t index, int lane) {
   const uint64_t h = splitmix64(seed ^ splitmix64(uint64_t(index) * 16ull + uint64_t(lane)));
   return float(uint32_t(h >> 40)) * (1.0f / 16777216.0f);
 }
-// Irwin-Hall(4) approximation of N(0,1): (u1+u2+u3+u4 - 2) * sqrt(3)
+// Irwin-Hall(4) approximation of N(0,1): (u1+u2+u3+u4 - 2) * sqrt(3).  Every operation is an explicitly rounded
+// intrinsic (no compiler-chosen FMA contraction) so that a host restatement with fmaf() reproduces the generated
+// streams bit for bit (oracle/oracle_capi.cpp orc_generate_p2p: the CPU arm of bench.py times the same workload).
 __device__ __forceinline__ float approx_normal(uint64_t seed, int64_t index, int lane0) {
-  const float s = (u01(seed, index, lane0) + u01(seed, index, lane0 + 1)) +
-                  (u01(seed, index, lane0 + 2) + u01(seed, index, lane0 + 3));
-  return (s - 2.0f) * 1.7320508f;
+  const float s = __fadd_rn(__fadd_rn(u01(seed, index, lane0), u01(seed, index, lane0 + 1)),
+                            __fadd_rn(u01(seed, index, lane0 + 2), u01(seed, index, lane0 + 3)));
+  return __fmul_rn(__fadd_rn(s, -2.0f), 1.7320508f);
 }
 
 struct SynthDev {
@@ -69,12 +71,13 @@ __global__ void generate_p2p_kernel(SynthDev d, int64_t n, ST* sx, ST* sy, ST* s
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t gi = d.first_index + i;
     float p[3], q[3];
-    for (int k = 0; k < 3; ++k) p[k] = d.lo[k] + (d.hi[k] - d.lo[k]) * u01(d.seed, gi, k);
+    for (int k = 0; k < 3; ++k) p[k] = __fmaf_rn(__fadd_rn(d.hi[k], -d.lo[k]), u01(d.seed, gi, k), d.lo[k]);
     const bool outlier = u01(d.seed, gi, 15) < d.outlier_fraction;
     for (int k = 0; k < 3; ++k) {
-      float v = d.gt[k * 3 + 0] * p[0] + d.gt[k * 3 + 1] * p[1] + d.gt[k * 3 + 2] * p[2] + d.gt[9 + k];
-      if (d.sigma > 0.0f) v += d.sigma * approx_normal(d.seed, gi, 3 + 4 * k);  // lanes 3..14
-      if (outlier) v += d.outlier_range * (2.0f * u01(d.seed, gi ^ 0x5bd1e995, k) - 1.0f);
+      // tgt = R src + t (+ noise) (+ outlier offset), one fused multiply-add per term, in this order
+      float v = __fmaf_rn(d.gt[k * 3 + 2], p[2], __fmaf_rn(d.gt[k * 3 + 1], p[1], __fmaf_rn(d.gt[k * 3 + 0], p[0], d.gt[9 + k])));
+      if (d.sigma > 0.0f) v = __fmaf_rn(d.sigma, approx_normal(d.seed, gi, 3 + 4 * k), v);  // lanes 3..14
+      if (outlier) v = __fmaf_rn(d.outlier_range, __fmaf_rn(2.0f, u01(d.seed, gi ^ 0x5bd1e995, k), -1.0f), v);
       q[k] = v;
     }
     sx[i] = ST(p[0]); sy[i] = ST(p[1]); sz[i] = ST(p[2]);
@@ -293,6 +296,7 @@ int mopt_store_download(mopt_store* st, int group, void* host, int host_dtype, i
   const int ncomp = group == 0 ? sh.ncomp_a : sh.ncomp_b;
   MOPT_REQUIRE(ncomp > 0, "this model has no such data group");
   MOPT_REQUIRE(first >= 0 && count >= 0 && first + count <= st->n, "download range outside the store");
+  MOPT_REQUIRE(host_dtype == MOPT_F32 || host_dtype == MOPT_F64, "bad host dtype");
   void* const* streams = st->streams + (group == 0 ? 0 : sh.NA);
   const size_t hsz = dtype_size(host_dtype);
   const int64_t chunk_elems_max = int64_t((size_t(64) << 20) / (hsz * ncomp));

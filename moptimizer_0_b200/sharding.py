@@ -14,20 +14,29 @@ def make_sharded_context(local_device: int, rank: int, world: int, collective: s
     from . import capi
     note = ""
     if collective == "p2p":
-        ctx = capi.Context(local_device, sharded=(rank, world, None))
+        # Every rank runs the SAME sequence of collectives whatever fails locally: gather (ok, handle) first, open the
+        # peers only if every rank has a handle, then gather the outcome of the open.
+        ctx, mine, ok = None, None, True
         try:
+            ctx = capi.Context(local_device, sharded=(rank, world, None))
             mine = ctx.peer_handle()
-            handles = [None] * world
-            dist.all_gather_object(handles, mine)
-            ctx.open_peers(handles)
-            ok = True
-        except capi.MoptError as e:  # e.g. IPC not permitted in this container
+        except Exception as e:  # e.g. CUDA IPC not permitted in this container
             ok, note = False, str(e)
-        flags = [None] * world
-        dist.all_gather_object(flags, ok)
-        if all(flags):
+        got = [None] * world
+        dist.all_gather_object(got, (ok, mine))
+        if all(g[0] for g in got):
+            try:
+                ctx.open_peers([g[1] for g in got])
+            except Exception as e:
+                ok, note = False, str(e)
+        else:
+            ok = False
+        opened = [None] * world
+        dist.all_gather_object(opened, ok)
+        if all(opened):
             return ctx, "p2p", ""
-        ctx.close()
+        if ctx is not None:
+            ctx.close()
         note = note or "a peer could not open the exchange"
     uid = [capi.Context.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)

@@ -814,9 +814,12 @@ struct Cost {  // include/moptimizer/cost_function.h:15-59 + the *_dyn wrappers
   int cost_threads = 1;
   bool float_carry = false;
   int manifold = MANIFOLD_ADDITIVE;
+  int lin_threads = 1;  // > 1: thread-local H/b over fixed chunks (not in the reference; lets a 1e7-residual LM
+                        // comparison finish in seconds — the sums differ from the serial loop by rounding only)
   S linearize(const S* x, S* H, S* b) {
     CostComputation<S> cc(P, O);
     cc.manifold_ = manifold;
+    if (lin_threads > 1) return cc.parallelLinearize(x, C.data(), *loss, H, b, *model, n, jac_mode, lin_threads);
     if (jac_mode == JAC_ANALYTICAL) return cc.computeHessian(x, C.data(), *loss, H, b, *model, n);
     return cc.computeHessianNumerical(x, C.data(), *loss, H, b, *model, n, jac_mode);
   }
@@ -849,7 +852,7 @@ inline bool is_cost_small(S c) {
 template <class S>
 inline Status lm_minimize(std::vector<Cost<S>*>& costs, int P, int max_iterations,
                           int lm_max_iterations, S* x0, int* executed_iterations,
-                          std::vector<TraceEntry>* trace) {
+                          std::vector<TraceEntry>* trace, bool stagnation_stop = false) {
   S lambda = S(-1.0);
   const S lambda_factor = S(1e-9);
   std::vector<S> H(size_t(P) * P), Hc(size_t(P) * P), b(P), bc(P), A(size_t(P) * P), nb(P),
@@ -896,6 +899,12 @@ inline Status lm_minimize(std::vector<Cost<S>*>& costs, int P, int max_iteration
         continue;
       }
       for (int d = 0; d < P; ++d) x0[d] = xi[d];
+      // NOT in the reference (restates the product's MOPT_LM_STAGNATION_STOP, include/mopt_capi.h): an accepted
+      // step below isDeltaSmall's threshold that leaves the cost bit-for-bit unchanged ends the run
+      if (stagnation_stop && yi == y0 && is_delta_small(delta.data(), P)) {
+        *executed_iterations = it;
+        return is_cost_small(yi) ? CONVERGED : SMALL_DELTA;
+      }
       // std::max(1.0/3.0, 1 - std::pow(2*rho-1, 3)) is evaluated in double (:113)
       lambda = S(double(lambda) *
                  std::max(1.0 / 3.0, 1.0 - std::pow(double(2 * rho - 1), 3)));

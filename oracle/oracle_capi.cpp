@@ -2,7 +2,11 @@
 // C interface over the restated reference so that pytest (ctypes) and bench.py's
 // cpu_baseline / `--impl reference` legs can drive it.  Never loaded by the product.
 #include <chrono>
+#include <cmath>
+#include <cstdint>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "moptimizer_oracle.hpp"
 
@@ -34,6 +38,7 @@ struct orc_cost {
   double max_dist;       // ORC_P2P_ICP: maximum correspondence distance
   const double* update_x;  // ORC_P2P_ICP: parameters at which cost->update(x) ran before linearize / computeCost
                            // (NULL: at the evaluation point)
+  int lin_threads;         // threads for Cost::linearize inside orc_lm_minimize (<= 1: the reference's serial loop)
 };
 
 }  // extern "C"
@@ -119,6 +124,7 @@ std::unique_ptr<Holder<S>> build(const orc_cost& c) {
   k.cost_threads = c.cost_threads < 1 ? 1 : c.cost_threads;
   k.float_carry = c.float_carry != 0;
   k.manifold = c.manifold;
+  k.lin_threads = c.lin_threads < 1 ? 1 : c.lin_threads;
   k.C.assign(size_t(c.O) * c.O, S(0));
   for (int i = 0; i < c.O; ++i) k.C[i + size_t(i) * c.O] = S(1);
   if (c.cov)
@@ -178,7 +184,7 @@ int cost_t(const orc_cost* c, const double* x, double* sum, int parallel) {
 
 template <class S>
 int lm_t(const orc_cost* cs, int ncosts, int P, int max_it, int lm_it, double* x, int* status,
-         int* executed, double* trace, int max_trace, int* ntrace) {
+         int* executed, double* trace, int max_trace, int* ntrace, int stagnation_stop) {
   std::vector<std::unique_ptr<Holder<S>>> hs;
   std::vector<Cost<S>*> costs;
   for (int i = 0; i < ncosts; ++i) {
@@ -189,7 +195,7 @@ int lm_t(const orc_cost* cs, int ncosts, int P, int max_it, int lm_it, double* x
   std::vector<S> xs(P);
   for (int i = 0; i < P; ++i) xs[i] = S(x[i]);
   std::vector<TraceEntry> tr;
-  Status st = lm_minimize<S>(costs, P, max_it, lm_it, xs.data(), executed, &tr);
+  Status st = lm_minimize<S>(costs, P, max_it, lm_it, xs.data(), executed, &tr, stagnation_stop != 0);
   for (int i = 0; i < P; ++i) x[i] = double(xs[i]);
   *status = int(st);
   int nt = 0;
@@ -220,13 +226,14 @@ int orc_compute_cost(const orc_cost* c, int scalar, const double* x, double* sum
 }
 
 // trace: max_trace rows of 8 doubles {outer_it, k, y0, yi, rho, lambda, nu, accepted}.
+// stagnation_stop: 0 = the reference's loop, 1 = with the product's MOPT_LM_STAGNATION_STOP rule restated.
 int orc_lm_minimize(const orc_cost* costs, int ncosts, int scalar, int P, int max_it, int lm_it,
                     double* x, int* status, int* executed, double* trace, int max_trace,
-                    int* ntrace) {
+                    int* ntrace, int stagnation_stop) {
   return scalar ? lm_t<double>(costs, ncosts, P, max_it, lm_it, x, status, executed, trace,
-                               max_trace, ntrace)
+                               max_trace, ntrace, stagnation_stop)
                 : lm_t<float>(costs, ncosts, P, max_it, lm_it, x, status, executed, trace,
-                              max_trace, ntrace);
+                              max_trace, ntrace, stagnation_stop);
 }
 
 int orc_ldlt_solve(int n, const double* A, const double* rhs, double* out) {
@@ -273,5 +280,85 @@ double orc_time_linearize(const orc_cost* c, int scalar, const double* x, int nt
 }
 
 int orc_hardware_concurrency() { return int(std::thread::hardware_concurrency()); }
+
+// ---- the bench workload on the host ---------------------------------------------------------------------------
+// Host restatement of the product's counter-based synthetic generator for the point2point model
+// (moptimizer_0_b200/csrc/mopt_store.cu generate_p2p_kernel; same hash, same explicitly rounded operations in the
+// same order, fmaf where the device uses __fmaf_rn): element i of the output equals element i of a device store
+// generated with the same description, bit for bit (asserted on a GPU in tests/test_gpu_parity.py).  This is how
+// `bench.py --impl reference` times the CPU path on the SAME 100 M correspondences without touching a GPU.
+namespace {
+inline uint64_t gen_splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+inline float gen_u01(uint64_t seed, int64_t index, int lane) {
+  const uint64_t h = gen_splitmix64(seed ^ gen_splitmix64(uint64_t(index) * 16ull + uint64_t(lane)));
+  return float(uint32_t(h >> 40)) * (1.0f / 16777216.0f);
+}
+inline float gen_normal(uint64_t seed, int64_t index, int lane0) {
+  const float s = (gen_u01(seed, index, lane0) + gen_u01(seed, index, lane0 + 1)) +
+                  (gen_u01(seed, index, lane0 + 2) + gen_u01(seed, index, lane0 + 3));
+  return (s + -2.0f) * 1.7320508f;
+}
+}  // namespace
+
+// x_gt = [t, omega] (6), lo / hi = source box corners (3 each).  src_xyz / tgt_xyz: n x 3 AoS doubles (each value
+// is exactly the float the device store holds).  nthreads >= 1.
+int orc_generate_p2p(uint64_t seed, int64_t first_index, int64_t n, const double* x_gt, const double* lo,
+                     const double* hi, double sigma_d, double outlier_fraction_d, double outlier_range_d,
+                     double* src_xyz, double* tgt_xyz, int nthreads) {
+  if (!x_gt || !lo || !hi || !src_xyz || !tgt_xyz || n < 0) return 1;
+  // rodrigues_host of mopt_store.cu (guard n > 0), then rounded to float like SynthDev::gt
+  float gt[12], flo[3], fhi[3];
+  {
+    const double* w = x_gt + 3;
+    const double nn = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    double R[9];
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (nn > 0.0) {
+      const double a[3] = {w[0] / nn, w[1] / nn, w[2] / nn};
+      const double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+      const double sn = std::sin(nn), cs = std::cos(nn);
+      for (int r = 0; r < 3; ++r)
+        for (int col = 0; col < 3; ++col) {
+          double kk = 0;
+          for (int k = 0; k < 3; ++k) kk += K[r * 3 + k] * K[k * 3 + col];
+          R[r * 3 + col] += sn * K[r * 3 + col] + (1.0 - cs) * kk;
+        }
+    }
+    for (int i = 0; i < 9; ++i) gt[i] = float(R[i]);
+    for (int i = 0; i < 3; ++i) gt[9 + i] = float(x_gt[i]);
+    for (int k = 0; k < 3; ++k) { flo[k] = float(lo[k]); fhi[k] = float(hi[k]); }
+  }
+  const float sigma = float(sigma_d), ofrac = float(outlier_fraction_d), orange = float(outlier_range_d);
+  if (nthreads < 1) nthreads = 1;
+  auto body = [&](int t) {
+    const int64_t i0 = n * t / nthreads, i1 = n * (t + 1) / nthreads;
+    for (int64_t i = i0; i < i1; ++i) {
+      const int64_t gi = first_index + i;
+      float p[3];
+      for (int k = 0; k < 3; ++k) p[k] = std::fmaf(fhi[k] + -flo[k], gen_u01(seed, gi, k), flo[k]);
+      const bool outlier = gen_u01(seed, gi, 15) < ofrac;
+      for (int k = 0; k < 3; ++k) {
+        float v = std::fmaf(gt[k * 3 + 2], p[2], std::fmaf(gt[k * 3 + 1], p[1], std::fmaf(gt[k * 3 + 0], p[0], gt[9 + k])));
+        if (sigma > 0.0f) v = std::fmaf(sigma, gen_normal(seed, gi, 3 + 4 * k), v);
+        if (outlier) v = std::fmaf(orange, std::fmaf(2.0f, gen_u01(seed, gi ^ 0x5bd1e995, k), -1.0f), v);
+        tgt_xyz[i * 3 + k] = double(v);
+        src_xyz[i * 3 + k] = double(p[k]);
+      }
+    }
+  };
+  if (nthreads == 1) {
+    body(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(body, t);
+    for (auto& x : th) x.join();
+  }
+  return 0;
+}
 
 }  // extern "C"

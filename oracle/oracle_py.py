@@ -38,6 +38,7 @@ class _OrcCost(C.Structure):
         ("cost_threads", C.c_int), ("float_carry", C.c_int), ("manifold", C.c_int),
         ("target", C.c_void_p), ("target_m", C.c_int), ("max_dist", C.c_double),
         ("update_x", C.POINTER(C.c_double)),
+        ("lin_threads", C.c_int),
     ]
 
 
@@ -66,7 +67,7 @@ def lib():
         L.orc_linearize.argtypes = [C.POINTER(_OrcCost), C.c_int, dp, dp, dp, dp, C.c_int]
         L.orc_compute_cost.argtypes = [C.POINTER(_OrcCost), C.c_int, dp, dp, C.c_int]
         L.orc_lm_minimize.argtypes = [C.POINTER(_OrcCost), C.c_int, C.c_int, C.c_int, C.c_int,
-                                      C.c_int, dp, ip, ip, dp, C.c_int, ip]
+                                      C.c_int, dp, ip, ip, dp, C.c_int, ip, C.c_int]
         L.orc_ldlt_solve.argtypes = [C.c_int, dp, dp, dp]
         L.orc_so3_convert6dof.argtypes = [dp, dp]
         L.orc_so3_left_jacobian_full.argtypes = [dp, dp]
@@ -74,6 +75,8 @@ def lib():
                                          dp, dp]
         L.orc_time_linearize.restype = C.c_double
         L.orc_hardware_concurrency.restype = C.c_int
+        L.orc_generate_p2p.argtypes = [C.c_uint64, C.c_int64, C.c_int64, dp, dp, dp, C.c_double, C.c_double,
+                                       C.c_double, dp, dp, C.c_int]
         _lib = L
     return _lib
 
@@ -103,6 +106,7 @@ class Cost:
     target: Optional[np.ndarray] = None   # P2P_ICP: fixed target cloud (m, 3)
     max_dist: float = 0.0                 # P2P_ICP: maximum correspondence distance
     update_x: Optional[Sequence[float]] = None  # P2P_ICP: where cost->update(x) ran (default: evaluation point)
+    lin_threads: int = 1                  # lm_minimize: threads of the linearization (1 = the reference's serial loop)
     _keep: list = field(default_factory=list, repr=False)
 
     def c_struct(self) -> _OrcCost:
@@ -143,6 +147,7 @@ class Cost:
         s.cost_threads = int(self.cost_threads)
         s.float_carry = 1 if self.float_carry else 0
         s.manifold = int(self.manifold)
+        s.lin_threads = int(self.lin_threads)
         s.target, s.target_m, s.max_dist, s.update_x = None, 0, float(self.max_dist), None
         if self.target is not None:
             t = np.ascontiguousarray(np.asarray(self.target, dtype=np.float32 if f32 else np.float64))
@@ -192,7 +197,8 @@ class LmResult:
 
 
 def lm_minimize(costs: Sequence[Cost], x0: Sequence[float], max_iterations: int = 15,
-                lm_iterations: int = 3, scalar: int = F64) -> LmResult:
+                lm_iterations: int = 3, scalar: int = F64, stagnation_stop: bool = False) -> LmResult:
+    """The reference's LM loop; `stagnation_stop` restates the product's MOPT_LM_STAGNATION_STOP extension."""
     P = costs[0].P
     arr = (_OrcCost * len(costs))(*[c.c_struct() for c in costs])
     x = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).copy())
@@ -201,7 +207,7 @@ def lm_minimize(costs: Sequence[Cost], x0: Sequence[float], max_iterations: int 
     trace = np.zeros((max_trace, 8), dtype=np.float64)
     rc = lib().orc_lm_minimize(arr, len(costs), scalar, P, max_iterations, lm_iterations, _dp(x),
                                C.byref(status), C.byref(executed), _dp(trace), max_trace,
-                               C.byref(ntrace))
+                               C.byref(ntrace), 1 if stagnation_stop else 0)
     if rc:
         raise RuntimeError("oracle: unsupported cost description")
     return LmResult(x, STATUS[status.value], executed.value, trace[: ntrace.value].copy())
@@ -247,3 +253,21 @@ def time_linearize(cost: Cost, x, nthreads: int = 1, reps: int = 1):
 
 def hardware_concurrency() -> int:
     return int(lib().orc_hardware_concurrency())
+
+
+def generate_p2p(seed: int, n: int, x_gt, lo=(0, 0, 0), hi=(10, 10, 10), first_index: int = 0, noise_sigma: float = 0.0,
+                 outlier_fraction: float = 0.0, outlier_range: float = 0.0, nthreads: int = 0):
+    """Host restatement of the product's synthetic point2point generator (csrc/mopt_store.cu): returns (src, tgt) as
+    (n, 3) float64 arrays whose values are bit for bit the floats a device store generated with the same arguments
+    holds."""
+    src = np.empty((n, 3), dtype=np.float64)
+    tgt = np.empty((n, 3), dtype=np.float64)
+    g = np.ascontiguousarray(np.asarray(x_gt, dtype=np.float64))
+    l = np.ascontiguousarray(np.asarray(lo, dtype=np.float64))
+    h = np.ascontiguousarray(np.asarray(hi, dtype=np.float64))
+    rc = lib().orc_generate_p2p(int(seed), int(first_index), int(n), _dp(g), _dp(l), _dp(h), float(noise_sigma),
+                                float(outlier_fraction), float(outlier_range), _dp(src), _dp(tgt),
+                                int(nthreads) if nthreads > 0 else max(1, hardware_concurrency()))
+    if rc:
+        raise RuntimeError("oracle: bad generator arguments")
+    return src, tgt

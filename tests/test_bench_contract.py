@@ -18,7 +18,7 @@ def run_bench(*args, env=None):
 
 
 def test_reference_arm_json_line():
-    r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-sample", "50000")
+    r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--n", "50000")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1  # ONE JSON line
@@ -30,10 +30,14 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "Gres/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # same workload keys as the GPU arm prints, W warm-up and K timed steps as requested, the whole --n per step
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(50000, 50000) and d["warmup"] == 1 and d["cpu_sample_per_step"] == 50000
 
 
 def test_reference_arm_other_ranks_stay_silent():
-    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "20000", "--gpus", "2",
+    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--n", "20000", "--gpus", "2",
                   env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
 
