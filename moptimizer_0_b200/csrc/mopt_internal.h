@@ -72,6 +72,7 @@ struct PassLaunch {
   int threads;      // 0 = default launch shape
   bool affine_fd = true;  // finite differences over a common denominator where the model allows it
                           // (dense_pass_kernel AFFINE_FD); false with MOPT_FLAG_GENERIC_KERNEL
+  bool identity_cov = false;  // the problem has no setCovariance matrix (C = I): the tensor-core Gram kernel applies
 };
 
 // mopt_pass_p2p.cu

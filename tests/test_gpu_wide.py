@@ -103,7 +103,7 @@ def test_wide_fp32_common_denominator_differences(env, jac):
     eb = np.max(np.abs(b32 - b) / (d * np.sqrt(s)))
     eHg = np.max(np.abs(Hg - H) / np.outer(d, d))
     print("wide fp32 jac=%d: common-denominator H %.2e b %.2e | per-residual H %.2e" % (jac, eH, eb, eHg))
-    assert s32 == sg and abs(s32 - s) <= 1e-5 * s
+    assert abs(s32 - sg) <= 1e-6 * sg and abs(s32 - s) <= 1e-5 * s  # two kernels: same residuals, different summation order
     tol = 1e-5 if jac == 2 else 1e-4  # forward: first-order truncation with the float step on top
     assert eH < tol and eb < 2e-4, (eH, eb)
     assert eHg > 10 * eH, (eHg, eH)  # the noise floor the new form removes
