@@ -147,7 +147,16 @@ typedef struct mopt_problem {
  * form (by default fp64 compute is the literal per-residual restatement of linearization.h:97-111, the path compared
  * with the reference at 1e-10 / 1e-6).  Same quotient without the eps/h rounding of the subtraction, and 26 IEEE
  * divisions per observation fewer.  Ignored where no such form exists. */
-typedef enum mopt_problem_flags { MOPT_FLAG_GENERIC_KERNEL = 1, MOPT_FLAG_STABLE_FD = 2 } mopt_problem_flags;
+/* MOPT_FLAG_REFERENCE_FLOAT_GUARD: with compute_dtype MOPT_F32, so3::Exp returns the identity below |omega| = 10 eps_f32
+ * (1.2e-6) exactly as the reference's float instantiation does (src/so3.cpp:47).  By default the device derives the
+ * rotation in fp64 for either Scalar and uses the fp64 threshold: inside that ball every finite-difference column of
+ * the rotation block is exactly zero, and an LM run started at omega = 0 with a heavily damped first step can land in
+ * it and never leave. */
+typedef enum mopt_problem_flags {
+  MOPT_FLAG_GENERIC_KERNEL = 1,
+  MOPT_FLAG_STABLE_FD = 2,
+  MOPT_FLAG_REFERENCE_FLOAT_GUARD = 4
+} mopt_problem_flags;
 
 /* Optimizer knobs: optimizer.h:19,33-37, levenberg_marquadt_dyn.cpp:9,16, levenberg_marquadt_dyn.h:22-24. */
 typedef struct mopt_lm_options {

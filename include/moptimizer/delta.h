@@ -1,4 +1,6 @@
-// Mirrors include/moptimizer/delta.h:11-16 with a raw-pointer signature (no Eigen).
+// Mirrors include/moptimizer/delta.h:11-16.  The test itself takes a raw pointer (no dependency); with
+// MOPTIMIZER_USE_EIGEN defined and <Eigen/Dense> on the include path the reference's own signature
+// `isDeltaSmall(const Eigen::Matrix<Scalar, Dim, 1>&)` is declared as well and forwards to it.
 #pragma once
 
 #include <cmath>
@@ -15,3 +17,14 @@ inline bool isDeltaSmall(const Scalar* delta, int n) {
 }
 
 }  // namespace moptimizer
+
+#if defined(MOPTIMIZER_USE_EIGEN) && __has_include(<Eigen/Dense>)
+#include <Eigen/Dense>
+namespace moptimizer {
+/// include/moptimizer/delta.h:11-16
+template <class Scalar, int Dim>
+inline bool isDeltaSmall(const Eigen::Matrix<Scalar, Dim, 1>& delta) {
+  return isDeltaSmall<Scalar>(delta.data(), int(delta.size()));
+}
+}  // namespace moptimizer
+#endif

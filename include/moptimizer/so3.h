@@ -1,4 +1,7 @@
-// Mirrors include/moptimizer/so3.h + src/so3.cpp with raw-array signatures (3x3 / 4x4 row-major), no Eigen.
+// Mirrors include/moptimizer/so3.h + src/so3.cpp.  The arithmetic lives in raw-array functions (3x3 / 4x4 row-major,
+// no dependency); with MOPTIMIZER_USE_EIGEN defined and <Eigen/Dense> on the include path the reference's own
+// Eigen-typed signatures (include/moptimizer/so3.h:8-41) are declared as well and forward to them, so that reference
+// code such as tst/point2point.cpp:33 `so3::convert6DOFParameterToMatrix(x, transform_)` compiles unchanged.
 // convert6DOFParameterToMatrix and Exp are on the hot path (the device copies the kernels use live in
 // csrc/mopt_setup.cuh); the rest of src/so3.cpp:21-155 is the kept API surface around the manifold update, restated
 // with the reference's own thresholds and formulas — including its first-order right/left Jacobians.
@@ -145,3 +148,109 @@ inline void leftJacobian(const Scalar* r, Scalar* J) {
 }
 
 }  // namespace so3
+
+#if defined(MOPTIMIZER_USE_EIGEN) && __has_include(<Eigen/Dense>)
+#include <Eigen/Dense>
+
+#ifndef SKEW_SYMMETRIC_FROM  // include/moptimizer/so3.h:4
+#define SKEW_SYMMETRIC_FROM(v) 0.0, -v[2], v[1], v[2], 0.0, -v[0], -v[1], v[0], 0.0
+#endif
+
+namespace so3 {
+namespace detail {
+template <typename Scalar, typename M>
+inline void store3(const Scalar* R9, M&& out) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) out(r, c) = R9[r * 3 + c];
+}
+template <typename Scalar, typename M>
+inline void store4(const Scalar* T16, M&& out) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) out(r, c) = T16[r * 4 + c];
+}
+}  // namespace detail
+
+/// include/moptimizer/so3.h:8-9 (src/so3.cpp:7-19)
+template <typename Scalar>
+inline void convert6DOFParameterToMatrix(const Scalar* x, Eigen::Matrix<Scalar, 4, 4>& transform_matrix_) {
+  Scalar T[16];
+  convert6DOFParameterToMatrix<Scalar>(x, T);
+  detail::store4(T, transform_matrix_);
+}
+/// :11-12 (src/so3.cpp:21-31)
+template <typename Scalar>
+inline void convert3DOFParameterToMatrix(const Scalar* x, Eigen::Matrix<Scalar, 4, 4>& transform_matrix_) {
+  Scalar T[16];
+  convert3DOFParameterToMatrix<Scalar>(x, T);
+  detail::store4(T, transform_matrix_);
+}
+/// :14-15 (src/so3.cpp:33-40)
+template <typename Scalar>
+inline void convert3DOFParameterToMatrix3(const Scalar* x, Eigen::Matrix<Scalar, 3, 3>& transform_matrix_) {
+  Scalar R[9];
+  convert3DOFParameterToMatrix3<Scalar>(x, R);
+  detail::store3(R, transform_matrix_);
+}
+/// :18-20 (src/so3.cpp:43-57): R = exp(delta)
+template <typename Scalar>
+inline void Exp(const Eigen::Ref<const Eigen::Matrix<Scalar, 3, 1>>& delta, Eigen::Ref<Eigen::Matrix<Scalar, 3, 3>> R) {
+  const Scalar d[3] = {delta[0], delta[1], delta[2]};
+  Scalar R9[9];
+  Exp<Scalar>(d, R9);
+  detail::store3(R9, R);
+}
+/// :22-23 (src/so3.cpp:60-74)
+template <typename Scalar>
+inline Eigen::Matrix<Scalar, 3, 3> Exp(const Eigen::Matrix<Scalar, 3, 1>& ang) {
+  const Scalar d[3] = {ang[0], ang[1], ang[2]};
+  Scalar R9[9];
+  ExpAng<Scalar>(d, R9);
+  Eigen::Matrix<Scalar, 3, 3> R;
+  detail::store3(R9, R);
+  return R;
+}
+/// :25-26 (src/so3.cpp:76-94)
+template <typename Scalar>
+inline Eigen::Matrix<Scalar, 3, 3> Exp(const Eigen::Matrix<Scalar, 3, 1>& ang_vel, const Scalar& dt) {
+  const Scalar d[3] = {ang_vel[0], ang_vel[1], ang_vel[2]};
+  Scalar R9[9];
+  Exp<Scalar>(d, dt, R9);
+  Eigen::Matrix<Scalar, 3, 3> R;
+  detail::store3(R9, R);
+  return R;
+}
+/// :29-30 (src/so3.cpp:96-105): delta = Log(R)
+template <typename Scalar>
+inline void Log(const Eigen::Ref<Eigen::Matrix<Scalar, 3, 3>>& R, Eigen::Matrix<Scalar, 3, 1>& delta) {
+  Scalar R9[9], d[3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) R9[r * 3 + c] = R(r, c);
+  Log<Scalar>(R9, d);
+  for (int i = 0; i < 3; ++i) delta[i] = d[i];
+}
+/// :32-34 (src/so3.cpp:107-121)
+template <typename Scalar>
+inline void inverseRightJacobian(const Eigen::Matrix<Scalar, 3, 1>& r, Eigen::Ref<Eigen::Matrix<Scalar, 3, 3>> inv_jacobian) {
+  const Scalar v[3] = {r[0], r[1], r[2]};
+  Scalar J[9];
+  inverseRightJacobian<Scalar>(v, J);
+  detail::store3(J, inv_jacobian);
+}
+/// :36-38 (src/so3.cpp:123-139)
+template <typename Scalar>
+inline void rightJacobian(const Eigen::Ref<const Eigen::Matrix<Scalar, 3, 1>>& r, Eigen::Ref<Eigen::Matrix<Scalar, 3, 3>> jacobian) {
+  const Scalar v[3] = {r[0], r[1], r[2]};
+  Scalar J[9];
+  rightJacobian<Scalar>(v, J);
+  detail::store3(J, jacobian);
+}
+/// :40-42 (src/so3.cpp:141-155)
+template <typename Scalar>
+inline void leftJacobian(const Eigen::Ref<const Eigen::Matrix<Scalar, 3, 1>>& r, Eigen::Ref<Eigen::Matrix<Scalar, 3, 3>> left_jacobian) {
+  const Scalar v[3] = {r[0], r[1], r[2]};
+  Scalar J[9];
+  leftJacobian<Scalar>(v, J);
+  detail::store3(J, left_jacobian);
+}
+}  // namespace so3
+#endif  // MOPTIMIZER_USE_EIGEN

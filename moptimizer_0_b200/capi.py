@@ -25,6 +25,7 @@ P2P_EXACT, P2P_REFTEST, P2P_REFTEST_COLMAJOR, P2P_LEFT = range(4)
 MANIFOLD_ADDITIVE, MANIFOLD_SO3_LEFT = 0, 1
 FLAG_GENERIC_KERNEL = 1
 FLAG_STABLE_FD = 2
+FLAG_REFERENCE_FLOAT_GUARD = 4
 LM_STAGNATION_STOP = 1
 LOSS_NONE, LOSS_GEMAN_MCCLURE, LOSS_HUBER = range(3)
 STATUS = ["CONVERGED", "MAXIMUM_ITERATIONS_REACHED", "SMALL_DELTA", "NUMERIC_ERROR", "FATAL_ERROR"]

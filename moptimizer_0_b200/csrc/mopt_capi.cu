@@ -81,37 +81,17 @@ namespace {
 // kernel argument, so back-to-back asynchronous calls need no staging buffer.
 __global__ void setup_kernel(CostSlot* slot, XArg x) { setup_cost(slot->cost, x.v, &slot->pb, threadIdx.x, blockDim.x); }
 
-struct LmInit {
-  int P, n_costs, max_it, lm_max_it, speculative, scalar_f32;
-  double lambda_factor;
-  int flags;
-  double x0[kMaxP];
-};
-
 // levenberg_marquadt_dyn.cpp:15-26 (prepare) + the first setup(x0).
 __global__ void lm_init_kernel(LmState* st, CostSlot* slots, LmInit in) {
-  if (threadIdx.x == 0) {
-    st->P = in.P; st->n_costs = in.n_costs; st->max_it = in.max_it; st->lm_max_it = in.lm_max_it;
-    st->speculative = in.speculative; st->scalar_f32 = in.scalar_f32; st->lambda_factor = in.lambda_factor;
-    st->flags = in.flags;
-    for (int i = 0; i < kMaxP; ++i) {
-      const double v = i < in.P ? (in.scalar_f32 ? double(float(in.x0[i])) : in.x0[i]) : 0.0;
-      st->x[i] = v; st->xi[i] = v; st->x_eval[i] = v; st->delta[i] = 0.0;
-    }
-    st->lambda = -1.0; st->nu = 2.0;
-    st->it = 0; st->k = 0; st->phase = LM_PHASE_LIN; st->status = MOPT_MAXIMUM_ITERATIONS_REACHED;
-    st->done = 0; st->executed = 0; st->num_trials = 0; st->num_passes = 0;
-    st->pass_mode = PASS_LINEARIZE;
-    for (int i = 0; i < kPackedMax; ++i) st->cur.v[i] = 0.0;
-  }
-  __syncthreads();
-  for (int c = 0; c < in.n_costs; ++c) setup_cost(slots[c].cost, st->x_eval, &slots[c].pb, threadIdx.x, blockDim.x);
+  __shared__ LmStepShared s_sh;
+  lm_init_warp(st, slots, in, &s_sh, threadIdx.x);
 }
 
+__device__ long long g_step_prof[8];  // MOPT_LM_MONO_TRACE=1: clock64 stamps of the last solving lm_step_kernel
+
 // One optimizer transition between passes; also publishes the done flag of this slot to the host.
-__global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* slots, int* flag, const int* xerr) {
-  __shared__ int s_act;
-  __shared__ LmSolveScratch s_scratch;
+__global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* slots, int* flag, const int* xerr, int prof) {
+  __shared__ LmStepShared s_sh;
   const int lane = threadIdx.x;
   if (*reinterpret_cast<const volatile int*>(xerr)) {  // a peer exchange timed out: `trial` is not a total
     if (lane == 0) {
@@ -120,18 +100,13 @@ __global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* s
     }
     return;
   }
-  if (lane == 0) s_act = st->scalar_f32 ? lm_step_thread<float>(st, trial, slots[0].cost) : lm_step_thread<double>(st, trial, slots[0].cost);
-  __syncthreads();  // lane 0's state writes are visible to the warp below
-  if (s_act == 2) {  // damped solve + proposal, the lanes sharing the factorization
-    if (st->scalar_f32) lm_solve_propose_warp<float>(st, slots[0].cost, &s_scratch, lane);
-    else lm_solve_propose_warp<double>(st, slots[0].cost, &s_scratch, lane);
-    __threadfence_block();
+  long long stamps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int done = lm_step_warp(st, trial, slots, &s_sh, lane, prof ? stamps : nullptr);
+  if (lane == 0) {
+    *flag = done;
+    if (prof && stamps[3] - stamps[2] > 1000)  // a transition that solved
+      for (int i = 0; i < 6; ++i) g_step_prof[i] = stamps[i];
   }
-  if (s_act) {
-    const int nc = st->n_costs;
-    for (int c = 0; c < nc; ++c) setup_cost(slots[c].cost, st->x_eval, &slots[c].pb, lane, blockDim.x);
-  }
-  if (lane == 0) *flag = st->done;
 }
 
 // The same solve through the warp-cooperative LDL^T (mopt_ldlt_solve with cooperative = 1; for tests).
@@ -240,6 +215,7 @@ void fill_cost(const mopt_problem* p, CostDev* c) {
   c->rot_offset = (p->model == MOPT_MODEL_POINT2POINT || p->model == MOPT_MODEL_PINHOLE ||
                    p->model == MOPT_MODEL_PINHOLE_DISTORT) ? 3 : -1;
   if (p->model >= MOPT_MODEL_USER_BASE) c->rot_offset = user_model_rot_offset(p->model);
+  c->so3_guard = ((p->flags & MOPT_FLAG_REFERENCE_FLOAT_GUARD) && p->compute_dtype == MOPT_F32) ? kSo3GuardF32 : kSo3GuardF64;
   const int O = p->num_outputs;
   for (int i = 0; i < O * O; ++i) c->cov[i] = p->has_covariance ? p->covariance[i] : ((i % (O + 1) == 0) ? 1.0 : 0.0);
   std::memcpy(c->consts, p->consts, sizeof(c->consts));
@@ -426,6 +402,38 @@ int fetch_result(mopt_ctx* ctx, int P, double* H, double* b, double* sum) {
   return MOPT_OK;
 }
 
+// Copies the final optimizer state back: x, status, iteration count and trace (end of mopt_lm_minimize).
+int finish_lm(mopt_ctx* ctx, int P, double* x, mopt_lm_report* report) {
+  // the state is 57 KB with its 1024-entry trace: fetch the hot part and the first trials, the rest only if used
+  LmState* hs = ctx->h_lm;
+  constexpr int kFirstTrials = 48;
+  const size_t first = offsetof(LmState, trials) + sizeof(mopt_lm_trial) * kFirstTrials;
+  MOPT_CUDA_TRY(cudaMemcpyAsync(hs, ctx->d_lm, first, cudaMemcpyDeviceToHost, ctx->stream));
+  MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (hs->num_trials > kFirstTrials) {
+    const int more = (hs->num_trials < MOPT_MAX_TRACE ? hs->num_trials : MOPT_MAX_TRACE) - kFirstTrials;
+    MOPT_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(hs) + first, reinterpret_cast<const char*>(ctx->d_lm) + first,
+                                  sizeof(mopt_lm_trial) * size_t(more), cudaMemcpyDeviceToHost, ctx->stream));
+    MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  if (ctx->h_xerr && *reinterpret_cast<volatile int*>(ctx->h_xerr)) {
+    set_last_error("peer exchange timed out waiting for another rank; this context cannot be used any more");
+    return MOPT_ERR_COMM;
+  }
+  if (!hs->done) {
+    set_last_error("internal error: the LM state machine did not terminate within its slot budget");
+    return MOPT_ERR_CUDA;
+  }
+  for (int i = 0; i < P; ++i) x[i] = hs->x[i];
+  report->status = hs->status;
+  report->executed_iterations = hs->executed;
+  report->num_trials = hs->num_trials < MOPT_MAX_TRACE ? hs->num_trials : MOPT_MAX_TRACE;
+  report->num_passes = hs->num_passes;
+  report->final_cost = hs->cur.v[packed_size(P) - 1];
+  std::memcpy(report->trials, hs->trials, sizeof(mopt_lm_trial) * size_t(report->num_trials));
+  return MOPT_OK;
+}
+
 int ctx_alloc(mopt_ctx* ctx) {
   MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
   cudaDeviceProp prop;
@@ -450,6 +458,8 @@ int ctx_alloc(mopt_ctx* ctx) {
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_xerr, sizeof(int), cudaHostAllocMapped));
   *ctx->h_xerr = 0;
   MOPT_CUDA_TRY(cudaHostGetDevicePointer(&ctx->d_xerr, ctx->h_xerr, 0));
+  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_gen, sizeof(unsigned long long)));
+  MOPT_CUDA_TRY(cudaMemset(ctx->d_gen, 0, sizeof(unsigned long long)));
   MOPT_CUDA_TRY(cudaMalloc(&ctx->d_xerr_dev, sizeof(int)));
   MOPT_CUDA_TRY(cudaMemset(ctx->d_xerr_dev, 0, sizeof(int)));
   ctx->flags_capacity = 4096;
@@ -546,6 +556,7 @@ int mopt_ctx_destroy(mopt_ctx* ctx) try {
       if (r != ctx->rank && ctx->peer_base[r]) cudaIpcCloseMemHandle(ctx->peer_base[r]);
   cudaFree(ctx->d_xbuf);
   cudaFree(ctx->d_xerr_dev);
+  cudaFree(ctx->d_gen);
   if (ctx->h_xerr) cudaFreeHost(ctx->h_xerr);
   cudaFree(ctx->d_partials); cudaFree(ctx->d_ticket); cudaFree(ctx->d_trial);
   cudaFree(ctx->d_slots); cudaFree(ctx->d_lm);
@@ -712,7 +723,7 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
   }
   MOPT_TRY(check_exchange_alive(ctx));
   MOPT_CUDA_TRY(cudaSetDevice(ctx->device));
-  std::memset(report, 0, sizeof(*report));
+  std::memset(report, 0, offsetof(mopt_lm_report, trials));  // the trace entries are valid up to num_trials
   if (opt.max_iterations == 0) {
     report->status = MOPT_MAXIMUM_ITERATIONS_REACHED;
     return MOPT_OK;
@@ -731,8 +742,14 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
   in.lambda_factor = opt.lambda_factor;
   in.flags = opt.flags;
   for (int i = 0; i < P; ++i) in.x0[i] = x[i];
-  lm_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_slots, in);
-  MOPT_CUDA_TRY(cudaGetLastError());
+  bool init_launched = false;
+  auto launch_init = [&]() -> int {
+    if (init_launched) return MOPT_OK;
+    lm_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_slots, in);
+    MOPT_CUDA_TRY(cudaGetLastError());
+    init_launched = true;
+    return MOPT_OK;
+  };
   // user models with their own setup(x): the run-time compiled setup kernel re-derives their parameter sets from
   // the state's evaluation point after every optimizer transition (idempotent when x_eval did not move)
   bool any_user_setup = false;
@@ -745,8 +762,68 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
                                    nullptr, P));
     return MOPT_OK;
   };
-  MOPT_TRY(user_setups());
+  if (any_user_setup) {
+    MOPT_TRY(launch_init());
+    MOPT_TRY(user_setups());
+  }
 
+  // Small single-cost point2point problems on one GPU: the whole loop in ONE cooperative launch (mopt_lm_mono.cuh);
+  // MOPT_LM_MONO=0 in the environment keeps the launch-per-trial path (A/B), MOPT_LM_MONO_MAX overrides the size limit.
+  {
+    static const int64_t mono_max = [] {
+      const char* e = getenv("MOPT_LM_MONO");
+      if (e && e[0] == '0') return int64_t(0);
+      const char* m = getenv("MOPT_LM_MONO_MAX");
+      return (m && m[0]) ? int64_t(atoll(m)) : int64_t(1) << 18;
+    }();
+    const mopt_problem& p0 = problems[0];
+    const bool moment_path = p0.model == MOPT_MODEL_POINT2POINT &&
+                             (p0.jacobian == MOPT_JAC_ANALYTICAL ||
+                              (!(p0.flags & MOPT_FLAG_GENERIC_KERNEL) && !(stores[0]->dtype == MOPT_F64 && p0.compute_dtype == MOPT_F32)));
+    if (n_costs == 1 && ctx->world == 1 && !has_update && !any_user_setup && moment_path && stores[0]->n <= mono_max &&
+        !(stores[0]->dtype == MOPT_F64 && p0.compute_dtype == MOPT_F32)) {
+      PassArgs a = make_args(ctx, stores[0], 0, 0, -1);
+      PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
+      MonoArgs m;
+      m.st = ctx->d_lm;
+      m.slots = ctx->d_slots;
+      m.gen = ctx->d_gen;
+      const int64_t slots64 = int64_t(opt.max_iterations) * (int64_t(opt.lm_max_iterations) + 1) + 2;
+      m.max_slots = int(slots64 < INT32_MAX ? slots64 : INT32_MAX);
+      m.init = in;  // prepare() + the first setup(x0) run inside the kernel too (CTA 0, before the first pass)
+      m.gen_base = ctx->mono_gen;
+      ctx->mono_gen += (unsigned long long)(m.max_slots) + 2ull;
+      m.dbg = nullptr;
+      static const bool trace = [] { const char* e = getenv("MOPT_LM_MONO_TRACE"); return e && e[0] == '1'; }();
+      unsigned long long* d_dbg = nullptr;
+      if (trace) {  // diagnostics: where a trial's time goes inside the persistent kernel (printed to stderr)
+        MOPT_CUDA_TRY(cudaMalloc(&d_dbg, sizeof(unsigned long long) * 512));
+        MOPT_CUDA_TRY(cudaMemsetAsync(d_dbg, 0, sizeof(unsigned long long) * 512, ctx->stream));
+        m.dbg = d_dbg;
+      }
+      const bool qrot = p0.jacobian == MOPT_JAC_ANALYTICAL && (p0.variant == MOPT_P2P_EXACT || p0.variant == MOPT_P2P_LEFT);
+      MOPT_TRY(launch_p2p_lm_mono(L, stores[0]->dtype, p0.compute_dtype, p0.loss, qrot, a, m));
+      MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      if (d_dbg) {
+        unsigned long long h[512];
+        MOPT_CUDA_TRY(cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(d_dbg);
+        for (int s = 0; s < 64 && h[s * 4 + 3]; ++s)
+          std::fprintf(stderr, "mono trial %2d: pass %6.2f us  step %6.2f us  open %5.2f us  (next begins +%6.2f us)\n", s,
+                       (h[s * 4 + 1] - h[s * 4]) * 1e-3, (h[s * 4 + 2] - h[s * 4 + 1]) * 1e-3, (h[s * 4 + 3] - h[s * 4 + 2]) * 1e-3,
+                       h[(s + 1) * 4] ? (double(h[(s + 1) * 4]) - double(h[s * 4 + 3])) * 1e-3 : 0.0);
+        for (int s = 0; s < 24 && h[256 + s * 8 + 5]; ++s) {
+          const unsigned long long* q = h + 256 + s * 8;
+          std::fprintf(stderr, "mono step %2d (cycles): stage-in %llu  state machine %llu  solve+propose %llu  setup %llu  write-back %llu\n",
+                       s, q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4]);
+        }
+      }
+      return finish_lm(ctx, P, x, report);
+    }
+  }
+
+  MOPT_TRY(launch_init());
+  static const bool step_prof = [] { const char* e = getenv("MOPT_LM_MONO_TRACE"); return e && e[0] == '1'; }();
   // Passes are enqueued in batches, always one batch ahead of the one whose done flag is being
   // awaited, so the device never idles on the host; every rank reads the flag of the same slot,
   // so all ranks stop after the same number of (collective-bearing) slots.
@@ -766,7 +843,7 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
         MOPT_TRY(launch_pass(ctx, stores[c], &problems[c], c, c > 0 ? 1 : 0, -1, c == n_costs - 1));
       MOPT_TRY(allreduce_trial(ctx, P, -1));
       lm_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_trial, ctx->d_slots, ctx->d_flags + slot_index(enq),
-                                                ctx->d_xerr_dev);
+                                                ctx->d_xerr_dev, step_prof ? 1 : 0);
       MOPT_CUDA_TRY(cudaGetLastError());
       MOPT_TRY(user_setups());
       *last_slot = enq;
@@ -786,27 +863,14 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
     cur_last = next_last;
   }
   MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (step_prof) {
+    long long q[8];
+    MOPT_CUDA_TRY(cudaMemcpyFromSymbol(q, g_step_prof, sizeof(q)));
+    std::fprintf(stderr, "lm_step_kernel (cycles): stage-in %lld  state machine %lld  solve+propose %lld  setup %lld  write-back %lld\n",
+                 q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4]);
+  }
 
-  // fetch the final state
-  LmState* hs = ctx->h_lm;
-  MOPT_CUDA_TRY(cudaMemcpyAsync(hs, ctx->d_lm, sizeof(LmState), cudaMemcpyDeviceToHost, ctx->stream));
-  MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (ctx->h_xerr && *reinterpret_cast<volatile int*>(ctx->h_xerr)) {
-    set_last_error("peer exchange timed out waiting for another rank; this context cannot be used any more");
-    return MOPT_ERR_COMM;
-  }
-  if (!hs->done) {
-    set_last_error("internal error: the LM state machine did not terminate within its slot budget");
-    return MOPT_ERR_CUDA;
-  }
-  for (int i = 0; i < P; ++i) x[i] = hs->x[i];
-  report->status = hs->status;
-  report->executed_iterations = hs->executed;
-  report->num_trials = hs->num_trials < MOPT_MAX_TRACE ? hs->num_trials : MOPT_MAX_TRACE;
-  report->num_passes = hs->num_passes;
-  report->final_cost = hs->cur.v[packed_size(P) - 1];
-  std::memcpy(report->trials, hs->trials, sizeof(mopt_lm_trial) * size_t(report->num_trials));
-  return MOPT_OK;
+  return finish_lm(ctx, P, x, report);
 }
 MOPT_ABI_CATCH
 

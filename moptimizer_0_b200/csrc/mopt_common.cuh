@@ -105,6 +105,7 @@ struct CostDev {
   double consts[32];
   int manifold;    // mopt_manifold
   int rot_offset;  // index of the rotation-vector block of x, or -1
+  double so3_guard;  // so3::Exp returns I for |omega| <= so3_guard (src/so3.cpp:47: 10 eps of the Scalar; see mopt_setup.cuh)
 };
 
 // One cost term on the device: its constants and the result of setup(x).

@@ -5,6 +5,7 @@
 
 #include "mopt_common.cuh"
 #include "mopt_lm.cuh"
+#include "mopt_lm_mono.cuh"
 #include "mopt_models.cuh"
 #include "mopt_pass.cuh"
 
@@ -49,6 +50,8 @@ struct mopt_ctx {
   unsigned long long xseq = 0;
   int* h_xerr = nullptr;                         // mapped: set by the consumer kernel on a wait timeout
   int* d_xerr = nullptr;
+  unsigned long long* d_gen = nullptr;           // grid-barrier generation counter of the persistent LM kernel (never reset)
+  unsigned long long mono_gen = 0;               // its value after the launches so far
   int* d_xerr_dev = nullptr;                     // device-resident copy, read by the kernels that follow a failed exchange
 };
 
@@ -77,6 +80,9 @@ struct PassLaunch {
 
 // mopt_pass_p2p.cu
 int launch_p2p_moment(const PassLaunch& L, int store_dtype, int compute_dtype, int loss, bool qrot, const PassArgs& a);
+// mopt_pass_p2p.cu: the whole LM loop of a small single-cost point2point problem in one cooperative launch
+int launch_p2p_lm_mono(const PassLaunch& L, int store_dtype, int compute_dtype, int loss, bool qrot, const PassArgs& a,
+                       const MonoArgs& m);
 // mopt_pass_dense.cu
 int launch_dense(const PassLaunch& L, int model, bool numeric, int store_dtype, int compute_dtype, const PassArgs& a);
 

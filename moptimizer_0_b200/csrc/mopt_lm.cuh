@@ -6,6 +6,8 @@
 // sets the control word the next pass kernel obeys.  No host round trip per iteration.
 #pragma once
 
+#include <cstddef>
+
 #include "mopt_common.cuh"
 #include "mopt_setup.cuh"
 
@@ -27,6 +29,18 @@ struct LmState {
   int pass_mode;  // PassMode control word read by the pass kernels
   int pad_;
   mopt_lm_trial trials[MOPT_MAX_TRACE];
+};
+
+// Everything of LmState before the trace: what an optimizer transition reads and writes (staged in shared memory).
+constexpr int kLmHotWords = int(offsetof(LmState, trials) / 8);
+static_assert(offsetof(LmState, trials) % 8 == 0, "LmState hot part is copied in 8-byte words");
+
+// Arguments of levenberg_marquadt_dyn.cpp:15-26 (prepare), passed by value to the kernel that initialises the state.
+struct LmInit {
+  int P, n_costs, max_it, lm_max_it, speculative, scalar_f32;
+  double lambda_factor;
+  int flags;
+  double x0[kMaxP];
 };
 
 #ifdef __CUDACC__
@@ -106,8 +120,10 @@ __device__ inline void lm_finish(LmState* st, int status) {
 // row's dot product keeps the serial summation order, so the factors are bit-identical to the serial code);
 // the O(n^2) substitutions stay on lane 0 in the serial order.  A (n x n, column-major), tmp, y and tr live in
 // shared memory.  The serial version cost ~2 500 of the step kernel's 5 300 dependent instructions.
-template <typename S>
-__device__ inline void ldlt_solve_warp(int n, S* A, const S* rhs, S* out, S* tmp, S* y, int* tr, int lane) {
+// NC > 0: the size is known at compile time (the loops unroll: the 6 x 6 point2point case runs ~3x fewer instructions).
+template <typename S, int NC = 0>
+__device__ inline void ldlt_solve_warp(int n_rt, S* A, const S* rhs, S* out, S* tmp, S* y, int* tr, int lane) {
+  const int n = NC > 0 ? NC : n_rt;
 #define MOPT_A(r, c) A[(r) + (c) * n]
   bool zero_matrix = false;
   for (int k = 0; k < n && !zero_matrix; ++k) {
@@ -171,9 +187,9 @@ struct LmSolveScratch {
 
 // Solve (H + lambda diag(H)) delta = -b (levenberg_marquadt_dyn.cpp:65,78-80), xi = x (+) delta (:83), executed by
 // one full warp: the lanes build the damped matrix and factor it together.
-template <typename S>
+template <typename S, int PC = 0>
 __device__ inline void lm_solve_propose_warp(LmState* st, const CostDev& cost0, LmSolveScratch* sc, int lane) {
-  const int P = st->P;
+  const int P = PC > 0 ? PC : st->P;
   S* A = reinterpret_cast<S*>(sc->A);
   S* nb = reinterpret_cast<S*>(sc->nb);
   S* d = reinterpret_cast<S*>(sc->d);
@@ -185,7 +201,7 @@ __device__ inline void lm_solve_propose_warp(LmState* st, const CostDev& cost0, 
   }
   if (lane < P) nb[lane] = -S(st->cur.v[P * (P + 1) / 2 + lane]);
   __syncwarp();
-  ldlt_solve_warp<S>(P, A, nb, d, reinterpret_cast<S*>(sc->tmp), reinterpret_cast<S*>(sc->y), sc->tr, lane);
+  ldlt_solve_warp<S, PC>(P, A, nb, d, reinterpret_cast<S*>(sc->tmp), reinterpret_cast<S*>(sc->y), sc->tr, lane);
   if (lane == 0) {
     for (int i = 0; i < P; ++i) st->delta[i] = double(d[i]);
     if (cost0.manifold == MOPT_MANIFOLD_SO3_LEFT) {
@@ -203,10 +219,12 @@ __device__ inline void lm_solve_propose_warp(LmState* st, const CostDev& cost0, 
 // One transition of the optimizer, run by ONE thread.  Returns 0 if the optimization ended, 1 if a new evaluation
 // point x_eval was set (the caller then runs model setup for every cost), 2 if the damped system has to be solved
 // and a step proposed first (lm_solve_propose_warp, by the whole warp), followed by the same setup.
-template <typename S>
-__device__ inline int lm_step_thread(LmState* st, const PassResult* trial, const CostDev& cost0) {
+// `st` may be a shared-memory copy of the hot part of the state (everything before `trials`): the trace is written
+// through `trials` (the array of the state in global memory), never through st->trials.
+template <typename S, int PC = 0>
+__device__ inline int lm_step_thread(LmState* st, const PassResult* trial, const CostDev& cost0, mopt_lm_trial* trials) {
   if (st->done) return 0;
-  const int P = st->P;
+  const int P = PC > 0 ? PC : st->P;
   const int npk = packed_size(P);
   st->num_passes += 1;
   if (st->phase == LM_PHASE_LIN) {
@@ -226,7 +244,7 @@ __device__ inline int lm_step_thread(LmState* st, const PassResult* trial, const
     }
     const S rho = (y0 - yi) / den;  // :93
     if (st->num_trials < MOPT_MAX_TRACE) {
-      mopt_lm_trial& t = st->trials[st->num_trials];
+      mopt_lm_trial& t = trials[st->num_trials];
       t.outer_iteration = st->it; t.k = st->k; t.accepted = !(rho < S(0)); t.reserved = 0;
       t.y0 = double(y0); t.yi = double(yi); t.rho = double(rho); t.lambda = st->lambda; t.nu = st->nu;
     }
@@ -313,6 +331,88 @@ __device__ inline int lm_step_thread(LmState* st, const PassResult* trial, const
       return 0;
     }
   }
+}
+
+// One optimizer transition between two passes is executed by ONE WARP (lane = 0..31): accept / reject / terminate on
+// lane 0, the damped solve and the proposal by the warp, then model->setup(x_eval) for every cost term.  Used by
+// lm_step_kernel (one launch per transition) and by the persistent LM kernel (mopt_lm_mono.cuh).
+// Shared memory of one optimizer transition: the LDL^T scratch, the hot part of the state and the pass result.
+struct LmStepShared {
+  LmSolveScratch sc;
+  double hot[kLmHotWords];
+  PassResult trial;
+};
+
+// levenberg_marquadt_dyn.cpp:15-26 (prepare) + the first setup(x0), by one warp.
+__device__ inline void lm_init_warp(LmState* st, CostSlot* slots, const LmInit& in, LmStepShared* sh, int lane) {
+  if (lane == 0) {
+    st->P = in.P; st->n_costs = in.n_costs; st->max_it = in.max_it; st->lm_max_it = in.lm_max_it;
+    st->speculative = in.speculative; st->scalar_f32 = in.scalar_f32; st->lambda_factor = in.lambda_factor;
+    st->flags = in.flags;
+    st->lambda = -1.0; st->nu = 2.0;
+    st->it = 0; st->k = 0; st->phase = LM_PHASE_LIN; st->status = MOPT_MAXIMUM_ITERATIONS_REACHED;
+    st->done = 0; st->executed = 0; st->num_trials = 0; st->num_passes = 0;
+    st->pass_mode = PASS_LINEARIZE;
+  }
+  if (lane < kMaxP) {
+    const double v = lane < in.P ? (in.scalar_f32 ? double(float(in.x0[lane])) : in.x0[lane]) : 0.0;
+    st->x[lane] = v; st->xi[lane] = v; st->x_eval[lane] = v; st->delta[lane] = 0.0;
+    sh->hot[lane] = v;  // setup below reads x_eval from shared memory
+  }
+  for (int i = lane; i < kPackedMax; i += 32) st->cur.v[i] = 0.0;
+  __syncwarp();
+  for (int c = 0; c < in.n_costs; ++c) setup_cost(slots[c].cost, sh->hot, &slots[c].pb, lane, 32, sh->sc.tmp);
+}
+
+// The hot part of the state and the pass result are staged in shared memory by the whole warp (coalesced): the
+// transition is a few thousand DEPENDENT instructions on one lane, and every access to the state in global memory
+// costs an L2 round trip (measured on tst/point2point's cloud: 7 200 cycles for the accept / reject logic alone).
+// Returns the state's `done` flag after the transition.
+template <typename S, int PC>
+__device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, CostSlot* slots, LmStepShared* sh, int lane,
+                                     long long* prof = nullptr) {
+  LmState* st = reinterpret_cast<LmState*>(sh->hot);
+  if (prof && lane == 0) prof[0] = clock64();
+  const int npk = packed_size(PC > 0 ? PC : __ldcg(&gst->P));
+  {
+    const double* g = reinterpret_cast<const double*>(gst);
+    // past the L1: in the persistent kernel the state was last written by another SM (or by this one, earlier)
+    for (int i = lane; i < kLmHotWords; i += 32) sh->hot[i] = __ldcg(g + i);
+    for (int i = lane; i < npk; i += 32) sh->trial.v[i] = __ldcg(&gtrial->v[i]);
+  }
+  __syncwarp();
+  if (prof && lane == 0) prof[1] = clock64();
+  int act = 0;
+  if (lane == 0) act = lm_step_thread<S, PC>(st, &sh->trial, slots[0].cost, gst->trials);
+  act = __shfl_sync(0xffffffffu, act, 0);
+  __syncwarp();  // lane 0's state writes are visible to the warp below
+  if (prof && lane == 0) prof[2] = clock64();
+  if (act == 2) {  // damped solve + proposal, the lanes sharing the factorization
+    lm_solve_propose_warp<S, PC>(st, slots[0].cost, &sh->sc, lane);
+    __syncwarp();
+  }
+  if (prof && lane == 0) prof[3] = clock64();
+  if (act) {
+    const int nc = st->n_costs;
+    for (int c = 0; c < nc; ++c) setup_cost(slots[c].cost, st->x_eval, &slots[c].pb, lane, 32, sh->sc.tmp);
+  }
+  __syncwarp();
+  if (prof && lane == 0) prof[4] = clock64();
+  {
+    double* g = reinterpret_cast<double*>(gst);
+    for (int i = lane; i < kLmHotWords; i += 32) g[i] = sh->hot[i];
+  }
+  __syncwarp();
+  if (prof && lane == 0) prof[5] = clock64();
+  return st->done;
+}
+__device__ inline int lm_step_warp(LmState* st, const PassResult* trial, CostSlot* slots, LmStepShared* sh, int lane,
+                                   long long* prof = nullptr) {
+  const bool f32 = __ldcg(&st->scalar_f32) != 0;
+  if (__ldcg(&st->P) == 6 && false) {  // EXPERIMENT: generic path
+    return f32 ? lm_step_warp_t<float, 6>(st, trial, slots, sh, lane, prof) : lm_step_warp_t<double, 6>(st, trial, slots, sh, lane, prof);
+  }
+  return f32 ? lm_step_warp_t<float, 0>(st, trial, slots, sh, lane, prof) : lm_step_warp_t<double, 0>(st, trial, slots, sh, lane, prof);
 }
 
 #endif  // __CUDACC__

@@ -64,7 +64,10 @@ struct PassArgs {
 // After the call, in the LAST CTA only, s_tot[0..NRAW) holds the grid totals (fp64) and the
 // function returns true for every thread of that CTA.
 // Part 2: s_warp[w * STRIDE + i] holds warp w's total of raw sum i (all warps written, CTA synchronised).
-template <int NRAW, int STRIDE, int THREADS>
+// MASTER (persistent LM kernel only, every CTA co-resident): CTA 0 — not whichever CTA arrives last — waits for the
+// others' partials and does the serial tail (final reduction, assembly, optimizer step), so that code stays in ONE
+// SM's instruction cache from trial to trial instead of being fetched cold by a different SM each time.
+template <int NRAW, int STRIDE, int THREADS, bool MASTER = false>
 __device__ __forceinline__ bool grid_reduce_shared(const PassArgs& a, double* s_tot, const double* s_warp) {
   constexpr int NW = THREADS / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -78,12 +81,23 @@ __device__ __forceinline__ bool grid_reduce_shared(const PassArgs& a, double* s_
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(a.ticket, 1u);
-    s_last = (t == unsigned(G - 1));
+  if constexpr (MASTER) {
+    if (blockIdx.x != 0) {
+      if (threadIdx.x == 0) atomicAdd(a.ticket, 1u);
+      return false;
+    }
+    if (threadIdx.x == 0) {
+      while (*reinterpret_cast<volatile unsigned int*>(a.ticket) != unsigned(G - 1)) {}
+    }
+    __syncthreads();
+  } else {
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(a.ticket, 1u);
+      s_last = (t == unsigned(G - 1));
+    }
+    __syncthreads();
+    if (!s_last) return false;
   }
-  __syncthreads();
-  if (!s_last) return false;
   __threadfence();
   // fixed-order reduction of the G per-CTA partials: lanes stride over CTAs, xor-butterfly combine
   for (int i = warp; i < NRAW; i += NW) {
@@ -99,7 +113,7 @@ __device__ __forceinline__ bool grid_reduce_shared(const PassArgs& a, double* s_
   return true;
 }
 
-template <int NRAW, int V, int NCH, int THREADS>
+template <int NRAW, int V, int NCH, int THREADS, bool MASTER = false>
 __device__ __forceinline__ bool grid_reduce(const double (&lane_val)[NCH], const PassArgs& a, double* s_tot,
                                             double* s_warp /* [THREADS/32][NCH*V] */) {
   constexpr int SHIFT = 5 - Log2<V>::value;  // owner lane of index i is (i << SHIFT)
@@ -109,7 +123,7 @@ __device__ __forceinline__ bool grid_reduce(const double (&lane_val)[NCH], const
     for (int ch = 0; ch < NCH; ++ch) s_warp[warp * (NCH * V) + ch * V + (lane >> SHIFT)] = lane_val[ch];
   }
   __syncthreads();
-  return grid_reduce_shared<NRAW, NCH * V, THREADS>(a, s_tot, s_warp);
+  return grid_reduce_shared<NRAW, NCH * V, THREADS, MASTER>(a, s_tot, s_warp);
 }
 
 // A peer exchange earlier in this stream timed out (a rank died): the totals are meaningless from here on, so every
@@ -236,7 +250,7 @@ static __device__ __noinline__ void p2p_fused_set0(const CostDev* c, const doubl
   for (int i = 0; i < 6; ++i) xs[i] = f32 ? double(float(x[i])) : x[i];
   const double w[3] = {xs[3], xs[4], xs[5]};
   double R[9];
-  if (f32) so3_exp_dev<float>(w, R); else so3_exp_dev<double>(w, R);
+  if (f32) so3_exp_dev<float>(w, R, c->so3_guard); else so3_exp_dev<double>(w, R, c->so3_guard);
   for (int i = 0; i < 9; ++i) set[i] = R[i];
   set[9] = xs[0]; set[10] = xs[1]; set[11] = xs[2];
 }
@@ -248,27 +262,29 @@ static __device__ __noinline__ void p2p_fused_left_jacobian(const CostDev* c, co
     so3_left_jacobian_dev(w, Jl);
   }
 }
-// One entry of J(q) = J0 + q_x J1 + q_y J2 + q_z J3 (setup_p2p_affine, same summation order).
-__device__ inline double p2p_affine_entry(int variant, const double* Jl, int k, int idx) {
-  int r = idx / 6, col = idx % 6;
-  if (variant == MOPT_P2P_REFTEST_COLMAJOR) {  // tst/point2point.cpp:18,71 (see setup_p2p_affine)
-    const int cc = idx / 3, rr = idx % 3;
-    r = rr; col = cc;
-  }
-  if (k == 0) return (col < 3 && r == col) ? 1.0 : 0.0;
-  if (col < 3) return 0.0;
-  const double E[3][9] = {{0, 0, 0, 0, 0, 1, 0, -1, 0}, {0, 0, -1, 0, 0, 0, 1, 0, 0}, {0, 1, 0, -1, 0, 0, 0, 0, 0}};
-  double s = 0.0;
-  for (int m = 0; m < 3; ++m) s += E[k - 1][r * 3 + m] * Jl[m * 3 + (col - 3)];
-  return s;
-}
-
-// Assemble packed (H upper, b, sum) of the 6-parameter problem from the 23 moment totals.
+// Assemble packed (H upper, b, sum) of the 6-parameter problem from the 23 moment totals.  Called by the whole CTA.
+// H(i, j) = sum_{k,l} Mt[k][l] * s_kl(i, j) with s_kl = sum_{a,b} J_k[a][i] C[a][b] J_l[b][j]: the 21 x 16 inner sums
+// s_kl are spread over the CTA (`scratch`, 21 * 16 doubles of shared memory), then one thread per entry adds them
+// up in the (k, l) order of the serial form — same operations in the same order, so the result is bit-identical to
+// one thread doing all 144 products of an entry (which cost ~2.5 us of the last CTA's time on a small problem).
 __device__ inline void p2p_assemble(const double* tot, const double (*jaff)[18], const CostDev* cost, PassResult* out,
-                                    int accumulate, int tid, int nthreads) {
-  constexpr int P = 6;
+                                    int accumulate, int tid, int nthreads, double* scratch) {
+  constexpr int P = 6, NH = P * (P + 1) / 2;
+  double C[9];
+  for (int i = 0; i < 9; ++i) C[i] = cost->has_cov ? cost->cov[i] : ((i % 4 == 0) ? 1.0 : 0.0);
+  for (int w = tid; w < NH * 16; w += nthreads) {
+    const int e = w >> 4, k = (w >> 2) & 3, l = w & 3;
+    int i = 0, rem = e;  // decode (i, j) of the packed upper triangle
+    while (rem >= P - i) { rem -= P - i; ++i; }
+    const int j = i + rem;
+    double s = 0.0;
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) s += jaff[k][a * 6 + i] * C[a + 3 * b] * jaff[l][b * 6 + j];
+    scratch[w] = s;
+  }
+  __syncthreads();
   // augmented moment matrix Mt (4x4, q~ = (1, q)) and St (4x3) = sum w q~ r^T
-  double Mt[4][4], St[4][3], C[9];
+  double Mt[4][4], St[4][3];
   Mt[0][0] = tot[0];
   for (int k = 0; k < 3; ++k) Mt[0][k + 1] = Mt[k + 1][0] = tot[1 + k];
   Mt[1][1] = tot[4]; Mt[1][2] = Mt[2][1] = tot[5]; Mt[1][3] = Mt[3][1] = tot[6];
@@ -276,24 +292,14 @@ __device__ inline void p2p_assemble(const double* tot, const double (*jaff)[18],
   for (int m = 0; m < 3; ++m) St[0][m] = tot[10 + m];
   for (int k = 0; k < 3; ++k)
     for (int m = 0; m < 3; ++m) St[k + 1][m] = tot[13 + k * 3 + m];
-  for (int i = 0; i < 9; ++i) C[i] = cost->has_cov ? cost->cov[i] : ((i % 4 == 0) ? 1.0 : 0.0);
   const int npk = packed_size(P);
   for (int e = tid; e < npk; e += nthreads) {
     double val = 0.0;
-    if (e < P * (P + 1) / 2) {
-      // decode (i, j) of the packed upper triangle
-      int i = 0, rem = e;
-      while (rem >= P - i) { rem -= P - i; ++i; }
-      const int j = i + rem;
+    if (e < NH) {
       for (int k = 0; k < 4; ++k)
-        for (int l = 0; l < 4; ++l) {
-          double s = 0.0;
-          for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b) s += jaff[k][a * 6 + i] * C[a + 3 * b] * jaff[l][b * 6 + j];
-          val += Mt[k][l] * s;
-        }
+        for (int l = 0; l < 4; ++l) val += Mt[k][l] * scratch[e * 16 + k * 4 + l];
     } else if (e < npk - 1) {
-      const int i = e - P * (P + 1) / 2;
+      const int i = e - NH;
       for (int k = 0; k < 4; ++k)
         for (int a = 0; a < 3; ++a)
           for (int b = 0; b < 3; ++b) val += jaff[k][a * 6 + i] * C[a + 3 * b] * St[k][b];
@@ -306,10 +312,13 @@ __device__ inline void p2p_assemble(const double* tot, const double (*jaff)[18],
 
 // Everything after a point2point streaming loop: CTA + grid reduction of the 23 moment sums (dacc[0]: the lane's
 // fp64 total of moment `lane`), then, in the last CTA, assembly of the packed (H, b, sum) and the peer exchange.
-template <bool FUSED, int THREADS>
-__device__ __forceinline__ void p2p_finish(const PassArgs& a, int mode, const double (&dacc)[1], double* s_tot,
+// Returns true in the last CTA (after `out` is complete), false in every other CTA.
+// COHERENT: this launch is the persistent LM kernel (mopt_lm_mono.cuh): the ParamBlock is rewritten by another CTA
+// between passes, so it is read past the (incoherent) L1.
+template <bool FUSED, int THREADS, bool COHERENT = false>
+__device__ __forceinline__ bool p2p_finish(const PassArgs& a, int mode, const double (&dacc)[1], double* s_tot,
                                            double* s_warp) {
-  if (!grid_reduce<kP2PRaw, 32, 1, THREADS>(dacc, a, s_tot, s_warp)) return;
+  if (!grid_reduce<kP2PRaw, 32, 1, THREADS, COHERENT>(dacc, a, s_tot, s_warp)) return false;
   if (mode == PASS_COST) {
     if (threadIdx.x == 0) {
       const int e = packed_size(6) - 1;
@@ -317,8 +326,12 @@ __device__ __forceinline__ void p2p_finish(const PassArgs& a, int mode, const do
     }
   } else {
     __shared__ double s_jl[FUSED ? 9 : 1];
-    __shared__ double s_jaff[FUSED ? 4 : 1][18];
-    const double(*jaff)[18] = FUSED ? s_jaff : a.pb->jaff;
+    __shared__ double s_jaff[(FUSED || COHERENT) ? 4 : 1][18];
+    const double(*jaff)[18] = (FUSED || COHERENT) ? s_jaff : a.pb->jaff;
+    if constexpr (COHERENT && !FUSED) {
+      for (int i = threadIdx.x; i < 4 * 18; i += THREADS) s_jaff[i / 18][i % 18] = __ldcg(&a.pb->jaff[i / 18][i % 18]);
+      __syncthreads();
+    }
     if constexpr (FUSED) {
       // the affine pieces of J, entry by entry (same sums, same order as setup_p2p_affine)
       if (threadIdx.x == 0) {
@@ -331,18 +344,19 @@ __device__ __forceinline__ void p2p_finish(const PassArgs& a, int mode, const do
       for (int i = threadIdx.x; i < 4 * 18; i += THREADS) s_jaff[i / 18][i % 18] = p2p_affine_entry(a.cost->variant, s_jl, i / 18, i % 18);
       __syncthreads();
     }
-    p2p_assemble(s_tot, jaff, a.cost, a.out, a.accumulate, threadIdx.x, THREADS);
+    __shared__ double s_asm[21 * 16];
+    p2p_assemble(s_tot, jaff, a.cost, a.out, a.accumulate, threadIdx.x, THREADS, s_asm);
   }
   peer_push(a, packed_size(6));
+  return true;
 }
 
 // FUSED: model->setup(x) runs inside the kernel (PassArgs::x; host-driven analytical passes), `pb` is not read.
-template <typename ST, typename CT, int LOSS, bool QROT, int THREADS, int MINB, int UNROLL = 2, int FLUSH_ROUNDS = 8,
-          int PF = 0, bool SWP = false, bool FUSED = false>
-__global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArgs a) {
-  const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
-  if (mode == PASS_SKIP) return;
-  if (peer_failed(a)) return;
+// The pass itself, callable from the one-pass kernel below and from the persistent LM kernel (mopt_lm_mono.cuh).
+// Returns true in the last CTA once `out` holds the packed result.
+template <typename ST, typename CT, int LOSS, bool QROT, int THREADS, int UNROLL, int FLUSH_ROUNDS, int PF, bool SWP,
+          bool FUSED, bool COHERENT>
+__device__ __forceinline__ bool p2p_moment_body(const PassArgs& a, const int mode) {
   constexpr int VEC = VecOf<ST>::N;
   constexpr bool kFp32Acc = (sizeof(CT) == 4);
   // fp32 partials are folded into fp64 every FLUSH_ROUNDS*VEC residuals/thread
@@ -363,9 +377,9 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
   }
   CT R[9], t[3];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = CT(set0[i]);
+  for (int i = 0; i < 9; ++i) R[i] = CT(COHERENT ? __ldcg(set0 + i) : set0[i]);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) t[i] = CT(set0[9 + i]);
+  for (int i = 0; i < 3; ++i) t[i] = CT(COHERENT ? __ldcg(set0 + 9 + i) : set0[9 + i]);
   const CT lossp = CT(a.cost->loss_param);
   const bool masked = a.masked != 0;
 
@@ -510,7 +524,16 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArg
   }
   flush();
 
-  p2p_finish<FUSED, THREADS>(a, mode, dacc, s_tot, s_warp);
+  return p2p_finish<FUSED, THREADS, COHERENT>(a, mode, dacc, s_tot, s_warp);
+}
+
+template <typename ST, typename CT, int LOSS, bool QROT, int THREADS, int MINB, int UNROLL = 2, int FLUSH_ROUNDS = 8,
+          int PF = 0, bool SWP = false, bool FUSED = false>
+__global__ void __launch_bounds__(THREADS, MINB) p2p_moment_kernel(const PassArgs a) {
+  const int mode = a.mode_override >= 0 ? a.mode_override : *a.mode_ptr;
+  if (mode == PASS_SKIP) return;
+  if (peer_failed(a)) return;
+  p2p_moment_body<ST, CT, LOSS, QROT, THREADS, UNROLL, FLUSH_ROUNDS, PF, SWP, FUSED, false>(a, mode);
 }
 
 // =============================================================================================

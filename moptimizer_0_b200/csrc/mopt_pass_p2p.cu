@@ -1,5 +1,6 @@
 // Instantiations + dispatch of the point-to-point moment kernel (mopt_pass.cuh).
 #include "mopt_internal.h"
+#include "mopt_lm_mono.cuh"
 #include "mopt_pass_p2p2.cuh"
 
 namespace mopt {
@@ -125,6 +126,52 @@ int launch_loss(const PassLaunch& L, int loss, bool qrot, const PassArgs& a) {
 }
 
 }  // namespace
+
+// ---- persistent LM kernel for small problems (mopt_lm_mono.cuh) ------------------------------------------------
+namespace {
+struct ShapeMono {  // small CTAs: more of them share a small problem; one per SM so the optimizer step does not spill
+  static constexpr int THREADS = 256, MINB = 1, UNROLL = 2, FLUSH = 8;
+};
+
+template <typename ST, typename CT, int LOSS, bool QROT>
+int launch_mono_one(const PassLaunch& L, const PassArgs& a, const MonoArgs& m) {
+  using S = ShapeMono;
+  auto kern = p2p_lm_mono_kernel<ST, CT, LOSS, QROT, S::THREADS, S::MINB, S::UNROLL, S::FLUSH>;
+  const int64_t groups = a.n / VecOf<ST>::N;
+  const int grid = pick_grid(reinterpret_cast<const void*>(kern), S::THREADS, L, groups);  // <= co-resident CTAs
+  PassArgs aa = a;
+  MonoArgs mm = m;
+  void* params[] = {&aa, &mm};
+  MOPT_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(S::THREADS), params, 0,
+                                            L.stream));
+  return MOPT_OK;
+}
+
+template <typename ST, typename CT>
+int launch_mono_loss(const PassLaunch& L, int loss, bool qrot, const PassArgs& a, const MonoArgs& m) {
+  switch (loss) {
+    case MOPT_LOSS_NONE:
+      return qrot ? launch_mono_one<ST, CT, MOPT_LOSS_NONE, true>(L, a, m) : launch_mono_one<ST, CT, MOPT_LOSS_NONE, false>(L, a, m);
+    case MOPT_LOSS_GEMAN_MCCLURE:
+      return qrot ? launch_mono_one<ST, CT, MOPT_LOSS_GEMAN_MCCLURE, true>(L, a, m)
+                  : launch_mono_one<ST, CT, MOPT_LOSS_GEMAN_MCCLURE, false>(L, a, m);
+    case MOPT_LOSS_HUBER:
+      return qrot ? launch_mono_one<ST, CT, MOPT_LOSS_HUBER, true>(L, a, m) : launch_mono_one<ST, CT, MOPT_LOSS_HUBER, false>(L, a, m);
+    default:
+      set_last_error("unknown loss kind");
+      return MOPT_ERR_INVALID_ARGUMENT;
+  }
+}
+}  // namespace
+
+int launch_p2p_lm_mono(const PassLaunch& L, int store_dtype, int compute_dtype, int loss, bool qrot, const PassArgs& a,
+                       const MonoArgs& m) {
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F32) return launch_mono_loss<float, float>(L, loss, qrot, a, m);
+  if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F64) return launch_mono_loss<float, double>(L, loss, qrot, a, m);
+  if (store_dtype == MOPT_F64 && compute_dtype == MOPT_F64) return launch_mono_loss<double, double>(L, loss, qrot, a, m);
+  set_last_error("point2point: store dtype f64 with compute dtype f32 is not supported");
+  return MOPT_ERR_UNSUPPORTED;
+}
 
 int launch_p2p_moment(const PassLaunch& L, int store_dtype, int compute_dtype, int loss, bool qrot, const PassArgs& a) {
   if (store_dtype == MOPT_F32 && compute_dtype == MOPT_F32) {

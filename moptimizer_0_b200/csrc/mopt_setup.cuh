@@ -15,13 +15,16 @@ namespace mopt {
 // levenberg_marquadt_dyn.cpp:9,62-66) lands inside that ball and can never leave it (observed: camera, 50 M
 // observations, fp32 compute).  Inside the ball R differs from I by < 1.2e-6, i.e. below float resolution, so
 // values computed with a float Scalar are unaffected.
+// MOPT_FLAG_REFERENCE_FLOAT_GUARD restores the reference's float threshold (CostDev::so3_guard = 10 eps_f32) for
+// callers that need the literal behaviour of the float instantiation.
+constexpr double kSo3GuardF64 = 10.0 * 2.220446049250313e-16;
+constexpr double kSo3GuardF32 = 10.0 * 1.1920928955078125e-07;
 template <typename S>
-__device__ inline void so3_exp_dev(const double w[3], double R[9]) {
+__device__ inline void so3_exp_dev(const double w[3], double R[9], double guard = kSo3GuardF64) {
   const double n = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
-  const double eps = 2.220446049250313e-16;
-  if (n > 10.0 * eps) {
+  if (n > guard) {
     const double a0 = w[0] / n, a1 = w[1] / n, a2 = w[2] / n;
     const double K[9] = {0.0, -a2, a1, a2, 0.0, -a0, -a1, a0, 0.0};
     double sn, cs;
@@ -72,8 +75,8 @@ __device__ inline void retract_dev(const CostDev& c, const double* x, const doub
   if (c.manifold == MOPT_MANIFOLD_SO3_LEFT && c.rot_offset >= 0) {
     const int o = c.rot_offset;
     double Rx[9], Rd[9], Rn[9];
-    if (f32) { so3_exp_dev<float>(x + o, Rx); so3_exp_dev<float>(delta + o, Rd); }
-    else { so3_exp_dev<double>(x + o, Rx); so3_exp_dev<double>(delta + o, Rd); }
+    if (f32) { so3_exp_dev<float>(x + o, Rx, c.so3_guard); so3_exp_dev<float>(delta + o, Rd, c.so3_guard); }
+    else { so3_exp_dev<double>(x + o, Rx, c.so3_guard); so3_exp_dev<double>(delta + o, Rd, c.so3_guard); }
     for (int r = 0; r < 3; ++r)
       for (int col = 0; col < 3; ++col) {
         double s = 0.0;
@@ -93,7 +96,7 @@ __device__ inline void setup_one_set(const CostDev& c, const double* xs, double*
     case MOPT_MODEL_POINT2POINT: {
       // so3::convert6DOFParameterToMatrix, src/so3.cpp:7-19: x = [t, omega]
       const double w[3] = {xs[3], xs[4], xs[5]};
-      if (c.compute_dtype == MOPT_F32) so3_exp_dev<float>(w, set); else so3_exp_dev<double>(w, set);
+      if (c.compute_dtype == MOPT_F32) so3_exp_dev<float>(w, set, c.so3_guard); else so3_exp_dev<double>(w, set, c.so3_guard);
       set[9] = xs[0]; set[10] = xs[1]; set[11] = xs[2];
       break;
     }
@@ -101,7 +104,7 @@ __device__ inline void setup_one_set(const CostDev& c, const double* xs, double*
       // tst/camera_calibration.cpp:33,37: M = (K * T(x)) * C, 3x4 row-major
       double R[9];
       const double w[3] = {xs[3], xs[4], xs[5]};
-      if (c.compute_dtype == MOPT_F32) so3_exp_dev<float>(w, R); else so3_exp_dev<double>(w, R);
+      if (c.compute_dtype == MOPT_F32) so3_exp_dev<float>(w, R, c.so3_guard); else so3_exp_dev<double>(w, R, c.so3_guard);
       double T[16];
       for (int r = 0; r < 3; ++r) {
         for (int k = 0; k < 3; ++k) T[r * 4 + k] = R[r * 3 + k];
@@ -129,7 +132,7 @@ __device__ inline void setup_one_set(const CostDev& c, const double* xs, double*
       // set = (T(x) C)(3x4 row-major, 12), fx, fy, cx, cy, k1, k2, p1, p2, k3
       double R[9];
       const double w[3] = {xs[3], xs[4], xs[5]};
-      if (c.compute_dtype == MOPT_F32) so3_exp_dev<float>(w, R); else so3_exp_dev<double>(w, R);
+      if (c.compute_dtype == MOPT_F32) so3_exp_dev<float>(w, R, c.so3_guard); else so3_exp_dev<double>(w, R, c.so3_guard);
       const double* C = c.consts;
       for (int r = 0; r < 3; ++r)
         for (int col = 0; col < 4; ++col) {
@@ -191,7 +194,15 @@ __device__ inline void setup_p2p_affine(const CostDev& c, const double* x, doubl
 // Whole ParamBlock for one cost at x.  Call with at least one full warp; lane j builds set j.
 // Emulates the reference's Scalar for the step: with compute_dtype F32 x_j, h_j and x_j +- h_j are
 // rounded to float exactly as `float` arithmetic would (linearization.h:78-89).
-__device__ inline void setup_cost(const CostDev& c, const double* x, ParamBlock* pb, int lane, int nlanes) {
+// `scratch` (optional, >= 9 doubles of shared memory): enables the warp-parallel fast path of the analytical
+// point2point model below.
+__device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double* x, ParamBlock* pb, int lane, double* Jl);
+__device__ inline void setup_cost(const CostDev& c, const double* x, ParamBlock* pb, int lane, int nlanes,
+                                  double* scratch = nullptr) {
+  if (scratch != nullptr && nlanes == 32 && c.model == MOPT_MODEL_POINT2POINT && c.jacobian == MOPT_JAC_ANALYTICAL) {
+    setup_p2p_analytical_warp(c, x, pb, lane, scratch);
+    return;
+  }
   const int P = c.P;
   const bool f32 = (c.compute_dtype == MOPT_F32);
   const int nsets = (c.jacobian == MOPT_JAC_ANALYTICAL) ? 1 : (c.jacobian == MOPT_JAC_FORWARD ? 1 + P : 1 + 2 * P);
@@ -266,6 +277,50 @@ __device__ inline void setup_cost(const CostDev& c, const double* x, ParamBlock*
       }
     }
   }
+}
+
+// One entry of J(q) = J0 + q_x J1 + q_y J2 + q_z J3 (setup_p2p_affine above, same sums in the same order).
+__device__ inline double p2p_affine_entry(int variant, const double* Jl, int k, int idx) {
+  int r = idx / 6, col = idx % 6;
+  if (variant == MOPT_P2P_REFTEST_COLMAJOR) {  // tst/point2point.cpp:18,71 (see setup_p2p_affine)
+    const int cc = idx / 3, rr = idx % 3;
+    r = rr; col = cc;
+  }
+  if (k == 0) return (col < 3 && r == col) ? 1.0 : 0.0;
+  if (col < 3) return 0.0;
+  const double E[3][9] = {{0, 0, 0, 0, 0, 1, 0, -1, 0}, {0, 0, -1, 0, 0, 0, 1, 0, 0}, {0, 1, 0, -1, 0, 0, 0, 0, 0}};
+  double s = 0.0;
+  for (int m = 0; m < 3; ++m) s += E[k - 1][r * 3 + m] * Jl[m * 3 + (col - 3)];
+  return s;
+}
+
+// setup_cost for the analytical point2point model, spread over one warp: lane 0 derives (R, t) and J_l(omega) exactly
+// as setup_one_set / setup_p2p_affine do, then the 72 affine Jacobian entries are formed one per lane (the generic
+// path runs ~1 500 serial instructions on lane 0 for this; the optimizer step of a small problem waits on it).
+__device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double* x, ParamBlock* pb, int lane, double* Jl) {
+  if (lane == 0) {
+    const bool f32 = (c.compute_dtype == MOPT_F32);
+    double xs[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xs[i] = f32 ? double(float(x[i])) : x[i];
+    const double w[3] = {xs[3], xs[4], xs[5]};
+    double R[9];
+    if (f32) so3_exp_dev<float>(w, R, c.so3_guard); else so3_exp_dev<double>(w, R, c.so3_guard);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) pb->sets[0][i] = R[i];
+    pb->sets[0][9] = xs[0]; pb->sets[0][10] = xs[1]; pb->sets[0][11] = xs[2];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Jl[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (c.variant == MOPT_P2P_EXACT) {
+      const double wj[3] = {x[3], x[4], x[5]};
+      so3_left_jacobian_dev(wj, Jl);
+    }
+  }
+  if (lane >= 12 && lane < kSetSize) pb->sets[0][lane] = 0.0;
+  if (lane < c.P) pb->x[lane] = x[lane];
+  __syncwarp();
+  for (int i = lane; i < 4 * 18; i += 32) pb->jaff[i / 18][i % 18] = p2p_affine_entry(c.variant, Jl, i / 18, i % 18);
+  __syncwarp();
 }
 
 }  // namespace mopt

@@ -47,6 +47,18 @@ def test_so3_mirror_host_only(tmp_path):
     assert r.returncode == 0, r.stdout
 
 
+def test_eigen_typed_overloads_host_only(tmp_path):
+    """The reference's Eigen-typed signatures of so3::* and isDeltaSmall (include/moptimizer/so3.h:8-41, delta.h:11-16)
+    compile in the reference's own call forms (MOPTIMIZER_USE_EIGEN) and forward to the raw-array functions.  The
+    image has no Eigen: tests/cpp/eigen_stub/ provides the minimal <Eigen/Dense> surface they touch."""
+    exe = str(tmp_path / "eigen_overloads_test")
+    src = os.path.join(ROOT, "tests", "cpp", "eigen_overloads_test.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-DMOPTIMIZER_USE_EIGEN", "-I", os.path.join(ROOT, "include"),
+                    "-I", os.path.join(ROOT, "tests", "cpp", "eigen_stub"), src, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "eigen overloads ok" in r.stdout, r.stdout
+
+
 def test_affine_fd_model_hooks_host_only(tmp_path):
     """The camera models' AFFINE_FD hooks (csrc/mopt_models.cuh: affine / finish_diff / tail_partials) against the
     literal difference quotient of linearization.h:97-111 taken in long double; nvcc-compiled, runs on the CPU."""

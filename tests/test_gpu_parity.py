@@ -195,6 +195,31 @@ def test_camera_calibration_lm(ctx, x0, iters):
     st.close()
 
 
+def test_reference_float_guard_flag_reproduces_the_float_instantiation(ctx):
+    """MOPT_FLAG_REFERENCE_FLOAT_GUARD: with fp32 compute so3::Exp returns I below |omega| = 10 eps_f32 (src/so3.cpp:47),
+    so inside that ball x and all its finite-difference perturbations give the same rotation and the rotation block of
+    H and b is exactly zero — what the oracle's float instantiation computes
+    (tests/test_oracle_golden.py::test_float_rodrigues_guard_...).  Without the flag the device derives R in fp64
+    with the fp64 guard and the block is alive (the documented deviation)."""
+    pts = np.array(FX["camera"]["points"])
+    pix = np.array(FX["camera"]["pixels"])
+    st = capi.Store(ctx, capi.MODEL_PINHOLE, 5, capi.F64)
+    st.upload(0, pts)
+    st.upload(1, pix)
+    x = [-0.0066, -0.0365, -0.0597, 5e-7, -8e-8, 8e-7]
+    oc = orc.Cost(orc.PINHOLE, 6, 2, 5, a=pts, b=pix, consts=camera_consts(), jac_mode=orc.JAC_FORWARD)
+    Ho, bo, so = orc.linearize(oc, x, orc.F32)
+    assert not Ho[3:, :].any() and not bo[3:].any()
+    for flags in (capi.FLAG_REFERENCE_FLOAT_GUARD, capi.FLAG_REFERENCE_FLOAT_GUARD | capi.FLAG_GENERIC_KERNEL):
+        H, b, s = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE, capi.JAC_FORWARD, capi.F32, consts=camera_consts(),
+                                                      flags=flags), x)
+        assert not H[3:, :].any() and not H[:, 3:].any() and not b[3:].any()
+        assert rel_err(H[:3, :3], Ho[:3, :3]) < 2e-3 and abs(s - so) <= 1e-4 * so   # float finite differences of 5 points
+    H, b, _ = ctx.linearize(st, capi.make_problem(capi.MODEL_PINHOLE, capi.JAC_FORWARD, capi.F32, consts=camera_consts()), x)
+    assert np.abs(np.diag(H)[3:]).min() > 1e5 and np.abs(b[3:]).max() > 1e3
+    st.close()
+
+
 def synthetic_camera(n, seed=5):
     """Points in front of the camera of tst/camera_calibration.cpp:24-30 and their projections + 0.5 px noise."""
     consts = camera_consts()
