@@ -409,7 +409,7 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
 __device__ inline int lm_step_warp(LmState* st, const PassResult* trial, CostSlot* slots, LmStepShared* sh, int lane,
                                    long long* prof = nullptr) {
   const bool f32 = __ldcg(&st->scalar_f32) != 0;
-  if (__ldcg(&st->P) == 6 && false) {  // EXPERIMENT: generic path
+  if (__ldcg(&st->P) == 6) {  // the 6-DoF registration case with unrolled loops
     return f32 ? lm_step_warp_t<float, 6>(st, trial, slots, sh, lane, prof) : lm_step_warp_t<double, 6>(st, trial, slots, sh, lane, prof);
   }
   return f32 ? lm_step_warp_t<float, 0>(st, trial, slots, sh, lane, prof) : lm_step_warp_t<double, 0>(st, trial, slots, sh, lane, prof);

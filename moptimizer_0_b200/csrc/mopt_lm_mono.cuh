@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_lm_mono_kernel(const PassAr
     for (;;) {
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(g) : "l"(m.gen) : "memory");
       if (g >= value) break;
-      __nanosleep(500);
+      __nanosleep(100);
     }
     __threadfence();
   };
