@@ -581,8 +581,13 @@ def run_ours(args):
                "h2d_gbs_total": BYTES_PER_RES * n_total * args.e2e_steps / dt / 1e9,
                "matches_resident": bool(np.array_equal(He, H) and np.array_equal(be, b) and se == s)}
         if pk is not None:
+            # two ceilings, both measured in this run with every rank copying at once: the sum of the ranks' rates, and
+            # what equal shards can reach (every rank moves the same bytes, so the slowest link sets the step time)
+            rates = pk["h2d_pinned_gbs_per_rank"]
             e2e["h2d_ceiling_gbs_total"] = pk["h2d_pinned_gbs_total"]
             e2e["frac_of_h2d_ceiling"] = e2e["h2d_gbs_total"] / pk["h2d_pinned_gbs_total"]
+            e2e["h2d_ceiling_gbs_equal_shards"] = world * min(rates)
+            e2e["frac_of_h2d_ceiling_equal_shards"] = e2e["h2d_gbs_total"] / (world * min(rates))
         e_store.close()
         del ha, hb
 

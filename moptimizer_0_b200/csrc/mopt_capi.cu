@@ -116,7 +116,8 @@ __global__ void ldlt_warp_test_kernel(int n, const double* A, const double* rhs,
   for (int i = lane; i < n * n; i += 32) sc.A[i] = A[i];
   if (lane < n) sc.nb[lane] = rhs[lane];
   __syncwarp();
-  ldlt_solve_warp<double>(n, sc.A, sc.nb, sc.d, sc.tmp, sc.y, sc.tr, lane);
+  if (n == 6) ldlt_solve_warp<double, 6>(n, sc.A, sc.nb, sc.d, sc.tmp, sc.y, sc.tr, lane);  // the unrolled instantiation
+  else ldlt_solve_warp<double>(n, sc.A, sc.nb, sc.d, sc.tmp, sc.y, sc.tr, lane);
   if (lane < n) out[lane] = sc.d[lane];
 }
 
@@ -774,7 +775,7 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
       const char* e = getenv("MOPT_LM_MONO");
       if (e && e[0] == '0') return int64_t(0);
       const char* m = getenv("MOPT_LM_MONO_MAX");
-      return (m && m[0]) ? int64_t(atoll(m)) : int64_t(1) << 18;
+      return (m && m[0]) ? int64_t(atoll(m)) : int64_t(1) << 21;
     }();
     const mopt_problem& p0 = problems[0];
     const bool moment_path = p0.model == MOPT_MODEL_POINT2POINT &&

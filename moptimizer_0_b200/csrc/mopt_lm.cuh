@@ -116,43 +116,54 @@ __device__ inline void lm_finish(LmState* st, int status) {
   st->pass_mode = PASS_SKIP;
 }
 
-// Warp-cooperative form of ldlt_solve_dev: the O(n^3) factorization runs with one lane per matrix row (every
-// row's dot product keeps the serial summation order, so the factors are bit-identical to the serial code);
-// the O(n^2) substitutions stay on lane 0 in the serial order.  A (n x n, column-major), tmp, y and tr live in
-// shared memory.  The serial version cost ~2 500 of the step kernel's 5 300 dependent instructions.
-// NC > 0: the size is known at compile time (the loops unroll: the 6 x 6 point2point case runs ~3x fewer instructions).
+// Warp-cooperative form of ldlt_solve_dev with VIRTUAL pivoting.  Same arithmetic on the same values in the same
+// order as the serial restatement above (bit-identical factors and solution, cross-checked by mopt_ldlt_solve on every
+// call), but
+//   * the symmetric row / column exchanges of a pivot step move no data: a permutation (4 bits per index in one
+//     64-bit word, identical on every lane) maps the algorithm's logical index to the row / column where the value
+//     physically sits.  A must come in as the FULL symmetric matrix: logical entry (r, c), r > c, is read at physical
+//     (perm r, perm c), which holds either the original a_rc = a_cr or, once column c is processed, L(r, c);
+//   * the O(n^3) factorization runs with one lane per matrix row (every row's dot product keeps the serial summation
+//     order), the divisions of a column and of the diagonal solve run one per lane;
+//   * the O(n^2) substitutions stay on lane 0 in the serial order.
+// The earlier form exchanged rows and columns in shared memory with four divergent branches per pivot step: 18 000
+// cycles per 6 x 6 solve on a B200 against ~5 000 now.  A (n x n, column-major, overwritten), tmp, y and tr live in
+// shared memory; n <= 16.  NC > 0: the size is known at compile time (the loops unroll).
 template <typename S, int NC = 0>
 __device__ inline void ldlt_solve_warp(int n_rt, S* A, const S* rhs, S* out, S* tmp, S* y, int* tr, int lane) {
   const int n = NC > 0 ? NC : n_rt;
-#define MOPT_A(r, c) A[(r) + (c) * n]
+  unsigned long long perm = 0xFEDCBA9876543210ull;
+  auto PH = [&](int i) { return int((perm >> (4 * i)) & 15ull); };
+#define MOPT_A(pr, pc) A[(pr) + (pc) * n]
   bool zero_matrix = false;
+#pragma unroll
   for (int k = 0; k < n && !zero_matrix; ++k) {
-    int piv = k;  // every lane scans the diagonal itself: same result, no broadcast needed
-    S best = fabs(MOPT_A(k, k));
+    int piv = k;  // every lane scans the remaining diagonal itself: same result, no broadcast needed
+    S best = fabs(MOPT_A(PH(k), PH(k)));
+#pragma unroll
     for (int i = k + 1; i < n; ++i) {
-      const S v = fabs(MOPT_A(i, i));
+      const S v = fabs(MOPT_A(PH(i), PH(i)));
       if (v > best) { best = v; piv = i; }
     }
     if (lane == 0) tr[k] = piv;
-    __syncwarp();
-    if (piv != k) {  // the four swap loops of the serial code touch disjoint elements: one lane each
-      if (lane < k) { const S t = MOPT_A(k, lane); MOPT_A(k, lane) = MOPT_A(piv, lane); MOPT_A(piv, lane) = t; }
-      else if (lane == k) { const S t = MOPT_A(k, k); MOPT_A(k, k) = MOPT_A(piv, piv); MOPT_A(piv, piv) = t; }
-      else if (lane < piv) { const S t = MOPT_A(lane, k); MOPT_A(lane, k) = MOPT_A(piv, lane); MOPT_A(piv, lane) = t; }
-      else if (lane > piv && lane < n) { const S t = MOPT_A(lane, k); MOPT_A(lane, k) = MOPT_A(lane, piv); MOPT_A(lane, piv) = t; }
-      __syncwarp();
+    {  // exchange logical k and piv
+      const unsigned long long a = (perm >> (4 * k)) & 15ull, b = (perm >> (4 * piv)) & 15ull;
+      perm = (perm & ~(15ull << (4 * k)) & ~(15ull << (4 * piv))) | (b << (4 * k)) | (a << (4 * piv));
     }
+    const int pk = PH(k);
     if (k > 0) {
-      if (lane < k) tmp[lane] = MOPT_A(lane, lane) * MOPT_A(k, lane);
+      if (lane < k) tmp[lane] = MOPT_A(PH(lane), PH(lane)) * MOPT_A(pk, PH(lane));
       __syncwarp();
       if (lane >= k && lane < n) {  // row `lane`: A(r, k) -= sum_c A(r, c) tmp[c]   (r == k: the diagonal update)
+        const int pr = PH(lane);
         S t = S(0);
-        for (int c = 0; c < k; ++c) t += MOPT_A(lane, c) * tmp[c];
-        MOPT_A(lane, k) -= t;
+#pragma unroll
+        for (int c = 0; c < k; ++c) t += MOPT_A(pr, PH(c)) * tmp[c];
+        MOPT_A(pr, pk) -= t;
       }
       __syncwarp();
     }
-    const S akk = MOPT_A(k, k);
+    const S akk = MOPT_A(pk, pk);
     const bool valid = fabs(akk) > S(0);
     if (k == 0 && !valid) {
       if (lane < n) tr[lane] = lane;
@@ -160,18 +171,33 @@ __device__ inline void ldlt_solve_warp(int n_rt, S* A, const S* rhs, S* out, S* 
       __syncwarp();
       break;
     }
-    if (valid && lane > k && lane < n) MOPT_A(lane, k) /= akk;
+    if (valid && lane > k && lane < n) MOPT_A(PH(lane), pk) /= akk;
     __syncwarp();
   }
   if (lane == 0) {
     for (int i = 0; i < n; ++i) y[i] = rhs[i];
     for (int k = 0; k < n; ++k) { const S t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
-    for (int r = 0; r < n; ++r)
-      for (int c = 0; c < r; ++c) y[r] -= MOPT_A(r, c) * y[c];
+    for (int r = 0; r < n; ++r) {
+      const int pr = PH(r);
+      S v = y[r];
+      for (int c = 0; c < r; ++c) v -= MOPT_A(pr, PH(c)) * y[c];
+      y[r] = v;
+    }
+  }
+  __syncwarp();
+  if (lane < n) {  // D^+ with tolerance numeric_limits::min(): one division per lane
     const S tol = (sizeof(S) == 4) ? S(1.17549435e-38) : S(2.2250738585072014e-308);
-    for (int i = 0; i < n; ++i) y[i] = (fabs(MOPT_A(i, i)) > tol) ? y[i] / MOPT_A(i, i) : S(0);
-    for (int r = n - 1; r >= 0; --r)
-      for (int c = r + 1; c < n; ++c) y[r] -= MOPT_A(c, r) * y[c];
+    const S dd = MOPT_A(PH(lane), PH(lane));
+    y[lane] = (fabs(dd) > tol) ? y[lane] / dd : S(0);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    for (int r = n - 1; r >= 0; --r) {
+      const int pr = PH(r);
+      S v = y[r];
+      for (int c = r + 1; c < n; ++c) v -= MOPT_A(PH(c), pr) * y[c];
+      y[r] = v;
+    }
     for (int k = n - 1; k >= 0; --k) { const S t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
     for (int i = 0; i < n; ++i) out[i] = y[i];
   }

@@ -94,10 +94,15 @@ __device__ __forceinline__ void mma_tf32_k4_first(float (&d)[4], unsigned a0, un
                : "r"(a0), "r"(a1), "r"(b0), "f"(0.f));
 }
 
-constexpr int kWideTcCols = 16;                     // parameters 0..P-1, zeros, and sqrt(w) r in column 15
+// Columns (= rows of the transposed tile) of X: parameters 0..P-1, zeros, and sqrt(w) r in the last one.  P <= 7 fits
+// ONE 8-column tile: half the MMAs (n-tile 0 only, the A rows 8..15 are don't-care) and half the shared memory.
+// (Measured for the 6-parameter camera model, 50 M observations: 0.98 ms against 0.75 ms on dense_pass_kernel — with
+// so few columns the shared-memory round trip and the legacy-rate HMMA cost more than the FFMAs they replace, so that
+// model stays on the register kernel; the narrow tile is kept for run-time compiled models with 7 < packed size.)
+__host__ __device__ constexpr int wide_tc_cols(int P) { return P + 1 <= 8 ? 8 : 16; }
 __host__ __device__ constexpr int wide_tc_row(int O) { return 64 * O + 4; }  // floats per parameter row of a warp tile: == 4 mod 32 (ldmatrix conflict-free)
 __host__ __device__ constexpr size_t wide_tc_smem_bytes(int O, int setn, int P, int threads) {
-  return size_t(4) * (size_t(threads / 32) * kWideTcCols * wide_tc_row(O) + size_t(1 + 2 * P) * ((setn + 3) / 4 * 4) + P) + 16;
+  return size_t(4) * (size_t(threads / 32) * wide_tc_cols(P) * wide_tc_row(O) + size_t(1 + 2 * P) * ((setn + 3) / 4 * 4) + P) + 16;
 }
 
 template <class M, int THREADS, int MINB, int FLUSH_GROUPS = 4>
@@ -106,7 +111,9 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
   if (mode == PASS_SKIP) return;
   if (peer_failed(a)) return;
   constexpr int P = M::P, O = M::O, NS = M::NS;
-  static_assert(P + 1 <= kWideTcCols, "wide_tc_kernel: at most 15 parameters (one 16 x 16 Gram tile)");
+  static_assert(P + 1 <= 16, "wide_tc_kernel: at most 15 parameters (one 16 x 16 Gram tile)");
+  constexpr int kWideTcCols = wide_tc_cols(P);
+  constexpr int NTILES = kWideTcCols / 8;       // 8-column output tiles of the m16n8 MMA
   constexpr int NRAW = P * (P + 1) / 2 + P + 1;
   constexpr int NCH = (NRAW + 31) / 32;
   constexpr int STRIDE = NCH * 32;
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
   constexpr int NAFF = M::NAFF;
 
   extern __shared__ __align__(16) unsigned char wide_tc_smem[];
-  float* s_x = reinterpret_cast<float*>(wide_tc_smem);          // [NW][16][ROW]
+  float* s_x = reinterpret_cast<float*>(wide_tc_smem);          // [NW][kWideTcCols][ROW]
   float* s_sets = s_x + size_t(NW) * kWideTcCols * ROW;         // [NSETS][SETN]
   float* s_h = s_sets + NSETS * SETN;                           // [P]: the step actually taken, H_j
   __shared__ double s_warp[NW * STRIDE];
@@ -161,17 +168,18 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
   };
 
   // fp32 accumulators, n-tile 0 / 1 of the m16n8 output fragments: S = X_hi^T X_hi and T = X_hi^T X_lo
-  float cs[2][4], ct[2][4];
-  double ds[2][4], dt[2][4];
+  float cs[NTILES][4], ct[NTILES][4];
+  double ds[NTILES][4], dt[NTILES][4];
 #pragma unroll
-  for (int t = 0; t < 2; ++t)
+  for (int t = 0; t < NTILES; ++t)
 #pragma unroll
     for (int q = 0; q < 4; ++q) { cs[t][q] = 0.f; ct[t][q] = 0.f; ds[t][q] = 0.0; dt[t][q] = 0.0; }
   F2 acc_e2(0.f);
   double dacc_e2 = 0.0;
 
-  // ldmatrix row address of this lane: matrix (lane / 8) = rows 0-7 | 8-15 of X at k columns +0 | +4
-  const float* ld_base = tile + ((lane & 7) + 8 * ((lane >> 3) & 1)) * ROW + 4 * (lane >> 4);
+  // ldmatrix row address of this lane: matrix (lane / 8) = rows 0-7 | 8-15 of X at k columns +0 | +4 (with one
+  // 8-row tile the "rows 8-15" matrices re-read rows 0-7: they only feed output rows nobody reads)
+  const float* ld_base = tile + ((lane & 7) + (NTILES == 2 ? 8 * ((lane >> 3) & 1) : 0)) * ROW + 4 * (lane >> 4);
 
   const int64_t ngroups = (a.n + 63) / 64;
   const int64_t wstride = int64_t(gridDim.x) * NW;
@@ -259,29 +267,30 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
       static_assert(KSTEPS % 2 == 0, "k-steps are processed in pairs");
 #pragma unroll 2
       for (int ks = 0; ks < KSTEPS; ks += 2) {
-        float ps[2][4];
+        float ps[NTILES][4];
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           unsigned x[4], hi[4];
           float lo[4];
           ldmatrix_x4(ld_base + (ks + kk) * 8, x);  // x0, x1: rows g, g + 8 at k = t;  x2, x3: the same rows at k = t + 4
 #pragma unroll
-          for (int q = 0; q < 4; ++q) split_tf32(x[q], hi[q], lo[q]);
+          for (int q = 0; q < 4; q += (NTILES == 2 ? 1 : 2)) split_tf32(x[q], hi[q], lo[q]);
+          if constexpr (NTILES == 1) { hi[1] = 0u; hi[3] = 0u; }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {  // the two k4 halves of this k-step
             if (kk == 0 && h == 0) {
               mma_tf32_k4_first(ps[0], hi[0], hi[1], hi[0]);
-              mma_tf32_k4_first(ps[1], hi[0], hi[1], hi[1]);
+              if constexpr (NTILES == 2) mma_tf32_k4_first(ps[1], hi[0], hi[1], hi[1]);
             } else {
               mma_tf32_k4(ps[0], hi[2 * h], hi[2 * h + 1], hi[2 * h]);
-              mma_tf32_k4(ps[1], hi[2 * h], hi[2 * h + 1], hi[2 * h + 1]);
+              if constexpr (NTILES == 2) mma_tf32_k4(ps[1], hi[2 * h], hi[2 * h + 1], hi[2 * h + 1]);
             }
             mma_tf32_k4(ct[0], hi[2 * h], hi[2 * h + 1], __float_as_uint(lo[2 * h]));
-            mma_tf32_k4(ct[1], hi[2 * h], hi[2 * h + 1], __float_as_uint(lo[2 * h + 1]));
+            if constexpr (NTILES == 2) mma_tf32_k4(ct[1], hi[2 * h], hi[2 * h + 1], __float_as_uint(lo[2 * h + 1]));
           }
         }
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < NTILES; ++t)
 #pragma unroll
           for (int q = 0; q < 4; ++q) cs[t][q] += ps[t][q];
       }
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
     }
     if (++since_flush >= FLUSH_GROUPS) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+      for (int t = 0; t < NTILES; ++t)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           ds[t][q] += double(cs[t][q]); cs[t][q] = 0.f;
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
     }
   }
 #pragma unroll
-  for (int t = 0; t < 2; ++t)
+  for (int t = 0; t < NTILES; ++t)
 #pragma unroll
     for (int q = 0; q < 4; ++q) { ds[t][q] += double(cs[t][q]); dt[t][q] += double(ct[t][q]); }
   dacc_e2 += double(acc_e2.v.x) + double(acc_e2.v.y);
@@ -310,18 +319,19 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
   // S + T + T^T: every lane parks its T entries in the warp's (now idle) tile, then adds T(i, j) + T(j, i) to its S
   // entries; every needed entry of the packed layout (H upper row-major, b, sum) has exactly one owner lane.
   __syncwarp();
-  double* tt = reinterpret_cast<double*>(tile);  // [16][16]
+  double* tt = reinterpret_cast<double*>(tile);  // [16][16] (rows / columns >= kWideTcCols hold don't-care values)
 #pragma unroll
-  for (int t = 0; t < 2; ++t)
+  for (int t = 0; t < NTILES; ++t)
 #pragma unroll
     for (int q = 0; q < 4; ++q) tt[((lane >> 2) + 8 * (q >> 1)) * 16 + 8 * t + 2 * (lane & 3) + (q & 1)] = dt[t][q];
   __syncwarp();
   double* mine = s_warp + warp * STRIDE;
 #pragma unroll
-  for (int t = 0; t < 2; ++t)
+  for (int t = 0; t < NTILES; ++t)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int i = (lane >> 2) + 8 * (q >> 1), j = 8 * t + 2 * (lane & 3) + (q & 1);
+      if (i >= kWideTcCols) continue;
       const double v = ds[t][q] + (tt[i * 16 + j] + tt[j * 16 + i]);
       if (i < P && j < P && i <= j) mine[tri_index(P, i, j)] = v;
       else if (i < P && j == kWideTcCols - 1) mine[P * (P + 1) / 2 + i] = v;
