@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KERNELS = [  # key, substring of the kernel name, residuals per launch
     ("p2p_gen2_f32", "p2p_moment2_kernel", 100_000_000),
     ("camera6_central_f32", "dense_pass_kernel<PinholeModel", 50_000_000),
-    ("camera15_central_f32", "wide_pass_kernel<PinholeDistortModel", 50_000_000),
+    ("camera15_central_f32", "wide_tc_kernel<PinholeDistortModel", 50_000_000),
     ("curve_central_f32", "dense_pass_kernel<ExpCurveModel", 10_000_000),
 ]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "inst": 1.0, "": 1.0,
@@ -27,8 +27,11 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "inst": 1.0, "":
 
 
 def main():
-    rep = sys.argv[1]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rep = sys.argv[1]  # an .ncu-rep, or the output of `ncu -i <rep> --page raw --csv` (for captures too large to bring back)
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
 
@@ -58,12 +61,13 @@ def main():
             "duration_us": val(r, "gpu__time_duration.sum"),
             "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "fma_pipe_pct": val(r, "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+            "tensor_pipe_inst_per_residual": (val(r, "smsp__inst_executed_pipe_tensor.sum") or 0.0) / n,
             "tensor_pipe_pct": val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
             "dram_pct": val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
             "registers": val(r, "launch__registers_per_thread"),
             "shared_bank_conflicts": val(r, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
             "shared_wavefronts": val(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
-            "source": "profiles/" + os.path.basename(rep).replace(".ncu-rep", "_ncu_raw.csv"),
+            "source": "profiles/" + os.path.basename(rep).replace(".ncu-rep", "").replace("_rawpage.csv", "") + "_ncu_raw.csv",
         }
     path = os.path.join(ROOT, "profiles", "kernel_inst_counts.json")
     with open(path, "w") as f:
