@@ -314,7 +314,12 @@ def alu_roofline(key, n, ms, bytes_per, pk, counts, hbm_peak):
         if c.get("fma_pipe_inst_per_residual"):
             f = c["fma_pipe_inst_per_residual"] * n / (ms * 1e-3) / 1e9
             out["fma_pipe"] = {"achieved": f, "peak": issue_peak, "frac": f / issue_peak,
-                               "note": "FMA-pipe warp instructions per second (FFMA2 counted twice) against the same peak"}
+                               "note": "FMA-pipe warp instructions per second against the same peak (an FFMA2 is one instruction "
+                                       "and occupies the pipe for two cycles)"}
+        if c.get("tensor_pipe_inst_per_residual"):
+            out["tensor_pipe"] = {"mma_per_residual": c["tensor_pipe_inst_per_residual"],
+                                  "busy_pct_in_capture": c.get("tensor_pipe_pct"),
+                                  "note": "mma.sync m16n8k4 TF32 (3xTF32 Gram matrix); share of cycles from the ncu capture"}
     else:
         out.update({"achieved": None, "peak": None, "unit": "G warp-inst/s", "frac": None})
     return out

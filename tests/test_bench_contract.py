@@ -62,3 +62,30 @@ def test_committed_bench_lines_carry_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["dtype"] == "f32" and d["scaling"] == "weak"
     # algorithmic bytes vs measured DRAM traffic of the same launch: no wasted re-reads
     assert 1.0 <= d["roofline"]["traffic"] / d["roofline"]["algorithmic_bytes_per_launch"] < 1.01
+
+
+def test_committed_round2_lines_cover_every_baseline_config():
+    """Round 2's recorded lines: every BASELINE configuration with a roofline, measured ceilings, the same workload
+    keys in both arms, and — at N > 1 — the exchanged result bit-identical to the single-GPU sums."""
+    sys.path.insert(0, ROOT)
+    import bench
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r2_bench_n1_allconfigs.json")).read().strip().splitlines()[-1])
+    assert d["roofline"]["bound"] == "hbm" and d["roofline"]["frac"] > 1.0 and d["e2e"]["matches_resident"] is True
+    assert set(d["configs"]) >= {"curve_10M_central", "camera_50M_P6_central", "camera_50M_P15_central", "fachada_lm"}
+    for key in ("curve_10M_central", "camera_50M_P6_central", "camera_50M_P15_central"):
+        c = d["configs"][key]
+        assert c["ms"] > 0 and c["Gres_per_s"] > 0 and c["roofline"]["bound"] == "fp32_issue" and c["roofline"]["hbm_frac"] > 0
+    assert d["configs"]["fachada_lm"]["status"] == "CONVERGED" and d["configs"]["fachada_lm"]["sequence"] == "AAAAA"
+    assert d["peaks"]["fp32_fma_tflops"] > 10 and d["peaks"]["hbm_read_gbs"] > 1000 and d["e2e"]["frac_of_h2d_ceiling"] > 0.9
+    ref = json.loads(open(os.path.join(ROOT, "profiles", "r2_bench_reference_arm.json")).read().strip().splitlines()[-1])
+    assert ref["config"] == d["config"] == bench.workload_config(100_000_000, 100_000_000)
+    assert abs(ref["check"]["sum_rtr"] - d["check"]["sum_rtr"]) <= 1e-8 * d["check"]["sum_rtr"]   # same 100 M rows
+    for name in ("r2_bench_n2.json", "r2_bench_n8.json"):
+        m = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        v = m["check"]["vs_single_gpu"]
+        assert v["bit_identical"] is True and v["H_rel"] == 0.0 and v["b_rel"] == 0.0 and v["sum_rel"] == 0.0
+        assert m["configs"]["p2p_1B_strong"]["n_total"] == 1_000_000_000 and m["lm"]["status"] == "SMALL_DELTA"
+    # the issue-slot rooflines use instruction counts from a committed ncu capture of the same kernels
+    counts = json.loads(open(os.path.join(ROOT, "profiles", "kernel_inst_counts.json")).read())
+    assert counts["p2p_gen2_f32"]["issue_active_pct"] < 45 and counts["camera15_central_f32"]["tensor_pipe_pct"] > 0
+    assert 1.0 <= counts["p2p_gen2_f32"]["dram_bytes_per_launch"] / 2.4e9 < 1.01
