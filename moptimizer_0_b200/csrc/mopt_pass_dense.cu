@@ -1,5 +1,8 @@
 // Instantiations + dispatch of the generic dense pass kernel (mopt_pass.cuh).
+#include <cstdlib>
+
 #include "mopt_internal.h"
+#include "mopt_pass_dense_f2.cuh"
 
 namespace mopt {
 namespace {
@@ -22,6 +25,33 @@ int launch_shape(const PassLaunch& L, const PassArgs& a) {
   kern<<<grid, THREADS, 0, L.stream>>>(a);
   MOPT_CUDA_TRY(cudaGetLastError());
   return MOPT_OK;
+}
+
+// Second generation for fp32 finite differences of models with an affine first stage (mopt_pass_dense_f2.cuh): two
+// observations per thread in packed fp32.  MOPT_DENSE_F2_SHAPE in the environment selects the launch shape (A/B).
+template <class M, int THREADS, int MINB>
+int launch_f2_shape(const PassLaunch& L, const PassArgs& a) {
+  auto kern = dense_f2_kernel<M, THREADS, MINB>;
+  PassLaunch L2 = L;
+  L2.ctas_per_sm = 0;
+  const int grid = pick_grid(reinterpret_cast<const void*>(kern), THREADS, L2, a.n / 4);
+  kern<<<grid, THREADS, 0, L.stream>>>(a);
+  MOPT_CUDA_TRY(cudaGetLastError());
+  return MOPT_OK;
+}
+template <class M>
+int launch_f2(const PassLaunch& L, const PassArgs& a) {
+  static const int shape = [] {
+    const char* e = getenv("MOPT_DENSE_F2_SHAPE");
+    return (e && e[0]) ? atoi(e) : 0;
+  }();
+  switch (shape) {
+    case 1: return launch_f2_shape<M, 256, 1>(L, a);
+    case 2: return launch_f2_shape<M, 128, 3>(L, a);
+    case 3: return launch_f2_shape<M, 128, 4>(L, a);
+    case 4: return launch_f2_shape<M, 256, 3>(L, a);
+    default: return launch_f2_shape<M, 256, 2>(L, a);
+  }
 }
 
 template <class M, typename ST, typename CT, bool NUMERIC>
@@ -51,6 +81,11 @@ int launch_one(const PassLaunch& L, const PassArgs& a) {
   // MOPT_FLAG_GENERIC_KERNEL), off by default with fp64 compute — the literal form is the one compared with the
   // reference's fp64 arithmetic — and on with MOPT_FLAG_STABLE_FD.
   if constexpr (NUMERIC && HasAffineStage<M>::value) {
+    if constexpr (sizeof(ST) == 4 && sizeof(CT) == 4) {
+      // fp32, C = I, no NaN-masked rows: two observations per thread in packed fp32
+      // (mopt_ctx_set_launch(.., 1024) keeps dense_pass_kernel for A/B on the same box)
+      if (L.affine_fd && L.identity_cov && !a.masked && L.threads != 1024) return launch_f2<M>(L, a);
+    }
     if (L.affine_fd) return launch_shape<M, ST, CT, NUMERIC, kThreads, kMinB, true>(L, a);
   }
   return launch_shape<M, ST, CT, NUMERIC, kThreads, kMinB>(L, a);

@@ -257,7 +257,7 @@ def test_camera_fp32_common_denominator_differences(ctx, jac, x, tol):
     errs = dict(H=rel_err(H, Ho), b=rel_err(b, bo), Hc=rel_err(H, Hc), bc=rel_err(b, bc), Hg=rel_err(Hg, Ho),
                 bg=rel_err(bg, bo))
     print("camera fp32 jac=%d x0=%s:" % (jac, x[0]), {k: "%.2e" % v for k, v in errs.items()})
-    assert s == sg and abs(s - so) <= 1e-5 * so
+    assert abs(s - sg) <= 1e-6 * sg and abs(s - so) <= 1e-5 * so  # two kernels: same residuals, different summation order
     if jac == capi.JAC_CENTRAL:
         assert errs["H"] < tol and errs["b"] < tol, errs
     else:
