@@ -464,6 +464,10 @@ int ctx_alloc(mopt_ctx* ctx) {
   MOPT_CUDA_TRY(cudaMalloc(&ctx->d_xerr_dev, sizeof(int)));
   MOPT_CUDA_TRY(cudaMemset(ctx->d_xerr_dev, 0, sizeof(int)));
   ctx->flags_capacity = 4096;
+  if (const char* e = getenv("MOPT_LM_FLAG_RING")) {  // test knob: a small ring makes an ordinary solve wrap it
+    const int v = atoi(e);
+    if (v >= 8 && v <= 4096) ctx->flags_capacity = v;
+  }
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_flags, sizeof(int) * ctx->flags_capacity, cudaHostAllocMapped));
   MOPT_CUDA_TRY(cudaHostGetDevicePointer(&ctx->d_flags, ctx->h_flags, 0));
   for (int i = 0; i < 2; ++i) {
