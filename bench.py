@@ -705,15 +705,15 @@ def run_ours(args):
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                          "frac_of_read_stream": (achieved / pk["hbm_read_gbs"]) if pk else None,
                          "achieved_from": "24 B x n_per_gpu / (CUDA-event time of the K timed steps / K) on the "
-                                          "context's stream; a step = this kernel alone (model->setup(x) runs inside it; sharded contexts "
-                                          "launch the one-warp setup kernel before it)",
+                                          "context's stream; a step = this kernel alone (model->setup(x) and, for N > 1, the exchange of "
+                                          "the packed result run inside it)",
                          "kernel": "p2p_moment_kernel<float,float,HUBER,QROT,...,FUSED>" if gen1 else
                                    "p2p_moment2_kernel<HUBER,QROT,...> (csrc/mopt_pass_p2p2.cuh)",
                          "algorithmic_bytes_per_launch": BYTES_PER_RES * n},
             "clocks": sampler.summary(),
-            # per step: the pass kernel with setup fused in (single GPU) or setup kernel + pass kernel (sharded contexts)
-            # (+ NCCL's kernel or the separate consumer kernel when selected)
-            "gpu_launches": ((1 if world == 1 or os.environ.get("MOPT_FUSED_SETUP", "")[:1] not in ("", "0") else 2) + (1 if world > 1 and (collective == "nccl" or os.environ.get("MOPT_PEER_CONSUMER") == "kernel") else 0)) * args.steps,
+            # per step: the pass kernel with setup(x) and, for N > 1, the peer exchange fused in
+            # (+ the setup kernel with MOPT_FUSED_SETUP=0, + NCCL's kernel or the separate consumer kernel when selected)
+            "gpu_launches": ((2 if os.environ.get("MOPT_FUSED_SETUP", "")[:1] == "0" else 1) + (1 if world > 1 and (collective == "nccl" or os.environ.get("MOPT_PEER_CONSUMER") == "kernel") else 0)) * args.steps,
             "check": {"sum_rtr": s, "H00": float(H[0, 0]), "b0": float(b[0])},
         }
         if vs_single is not None:

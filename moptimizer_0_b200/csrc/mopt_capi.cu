@@ -90,7 +90,8 @@ __global__ void lm_init_kernel(LmState* st, CostSlot* slots, LmInit in) {
 __device__ long long g_step_prof[8];  // MOPT_LM_MONO_TRACE=1: clock64 stamps of the last solving lm_step_kernel
 
 // One optimizer transition between passes; also publishes the done flag of this slot to the host.
-__global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* slots, int* flag, const int* xerr, int prof) {
+__global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* slots, int* flag, const int* xerr, int prof,
+                               int P, int scalar_f32) {
   __shared__ LmStepShared s_sh;
   const int lane = threadIdx.x;
   if (*reinterpret_cast<const volatile int*>(xerr)) {  // a peer exchange timed out: `trial` is not a total
@@ -101,7 +102,7 @@ __global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* s
     return;
   }
   long long stamps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const int done = lm_step_warp(st, trial, slots, &s_sh, lane, prof ? stamps : nullptr);
+  const int done = lm_step_warp(st, trial, slots, &s_sh, lane, P, scalar_f32 != 0, prof ? stamps : nullptr);
   if (lane == 0) {
     *flag = done;
     if (prof && stamps[3] - stamps[2] > 1000)  // a transition that solved
@@ -258,17 +259,17 @@ PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate
 // result to every peer when the NVLink exchange is open.
 // Host-driven passes of the analytical point2point model carry x into the kernel, which runs setup(x) itself
 // (PassArgs::fused_setup): the step is one kernel instead of setup kernel + pass kernel.
-// Single-GPU contexts only by default: at 2 GPUs in lock step the A/B (scripts/fused_setup_ab.sh,
-// profiles/r1_fused_setup_ab_n2.txt: fused 0.390 / 0.384 ms, two kernels 0.385 / 0.395 ms per step) shows no
-// difference beyond that box's run-to-run spread, so sharded contexts keep the two-kernel sequence the 4- and
-// 8-GPU numbers were measured with.  MOPT_FUSED_SETUP=1 fuses there too, MOPT_FUSED_SETUP=0 never fuses.
+// Sharded contexts too since round 2: with the second-generation kernel the 2-GPU A/B gives 0.3501 ms per lock-step
+// step fused against 0.3565 ms with the setup kernel in front (round 1's kernel showed no difference,
+// profiles/r1_fused_setup_ab_n2.txt); the packed results are bit-identical either way (bench.py check.vs_single_gpu
+// compares a fused single-GPU context with the sharded ones).  MOPT_FUSED_SETUP=0 never fuses.
 bool can_fuse_setup(const mopt_ctx* ctx, const mopt_problem* p) {
   static const int env = [] {
     const char* e = getenv("MOPT_FUSED_SETUP");
     return (e && e[0]) ? (e[0] == '0' ? 0 : 1) : -1;
   }();
   if (env == 0) return false;
-  if (ctx->world > 1 && env != 1) return false;
+  (void)ctx;
   return p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL &&
          p->manifold == MOPT_MANIFOLD_ADDITIVE;
 }
@@ -848,7 +849,7 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
         MOPT_TRY(launch_pass(ctx, stores[c], &problems[c], c, c > 0 ? 1 : 0, -1, c == n_costs - 1));
       MOPT_TRY(allreduce_trial(ctx, P, -1));
       lm_step_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_lm, ctx->d_trial, ctx->d_slots, ctx->d_flags + slot_index(enq),
-                                                ctx->d_xerr_dev, step_prof ? 1 : 0);
+                                                ctx->d_xerr_dev, step_prof ? 1 : 0, in.P, in.scalar_f32);
       MOPT_CUDA_TRY(cudaGetLastError());
       MOPT_TRY(user_setups());
       *last_slot = enq;

@@ -396,10 +396,10 @@ __device__ inline void lm_init_warp(LmState* st, CostSlot* slots, const LmInit& 
 // Returns the state's `done` flag after the transition.
 template <typename S, int PC>
 __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, CostSlot* slots, LmStepShared* sh, int lane,
-                                     long long* prof = nullptr) {
+                                     int P_rt, long long* prof = nullptr) {
   LmState* st = reinterpret_cast<LmState*>(sh->hot);
   if (prof && lane == 0) prof[0] = clock64();
-  const int npk = packed_size(PC > 0 ? PC : __ldcg(&gst->P));
+  const int npk = packed_size(PC > 0 ? PC : P_rt);
   {
     const double* g = reinterpret_cast<const double*>(gst);
     // past the L1: in the persistent kernel the state was last written by another SM (or by this one, earlier)
@@ -432,13 +432,14 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
   if (prof && lane == 0) prof[5] = clock64();
   return st->done;
 }
+// P and the Scalar of the LM arithmetic are launch-time constants of a minimize() call: the callers pass them as
+// kernel arguments instead of reading them from the state (two dependent L2 round trips per transition).
 __device__ inline int lm_step_warp(LmState* st, const PassResult* trial, CostSlot* slots, LmStepShared* sh, int lane,
-                                   long long* prof = nullptr) {
-  const bool f32 = __ldcg(&st->scalar_f32) != 0;
-  if (__ldcg(&st->P) == 6) {  // the 6-DoF registration case with unrolled loops
-    return f32 ? lm_step_warp_t<float, 6>(st, trial, slots, sh, lane, prof) : lm_step_warp_t<double, 6>(st, trial, slots, sh, lane, prof);
+                                   int P, bool f32, long long* prof = nullptr) {
+  if (P == 6) {  // the 6-DoF registration case with unrolled loops
+    return f32 ? lm_step_warp_t<float, 6>(st, trial, slots, sh, lane, P, prof) : lm_step_warp_t<double, 6>(st, trial, slots, sh, lane, P, prof);
   }
-  return f32 ? lm_step_warp_t<float, 0>(st, trial, slots, sh, lane, prof) : lm_step_warp_t<double, 0>(st, trial, slots, sh, lane, prof);
+  return f32 ? lm_step_warp_t<float, 0>(st, trial, slots, sh, lane, P, prof) : lm_step_warp_t<double, 0>(st, trial, slots, sh, lane, P, prof);
 }
 
 #endif  // __CUDACC__

@@ -18,7 +18,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KERNELS = [  # key, substring of the kernel name, residuals per launch
     ("p2p_gen2_f32", "p2p_moment2_kernel", 100_000_000),
-    ("camera6_central_f32", "dense_pass_kernel<PinholeModel", 50_000_000),
+    ("camera6_central_f32", "dense_f2_kernel<PinholeModel", 50_000_000),
     ("camera15_central_f32", "wide_tc_kernel<PinholeDistortModel", 50_000_000),
     ("curve_central_f32", "dense_pass_kernel<ExpCurveModel", 10_000_000),
 ]
