@@ -80,7 +80,9 @@ struct PassLaunch {
 
 // mopt_pass_p2p.cu
 int launch_p2p_moment(const PassLaunch& L, int store_dtype, int compute_dtype, int loss, bool qrot, const PassArgs& a);
-// mopt_pass_p2p.cu: the whole LM loop of a small single-cost point2point problem in one cooperative launch
+// mopt_pass_p2p2.cu: second generation, fp32 store + fp32 compute
+int launch_p2p_moment_gen2(const PassLaunch& L, int loss, bool qrot, const PassArgs& a);
+// mopt_lm_mono.cu: the whole LM loop of a small single-cost point2point problem in one cooperative launch
 int launch_p2p_lm_mono(const PassLaunch& L, int store_dtype, int compute_dtype, int loss, bool qrot, const PassArgs& a,
                        const MonoArgs& m);
 // mopt_pass_dense.cu

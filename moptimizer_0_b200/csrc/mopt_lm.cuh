@@ -370,7 +370,7 @@ struct LmStepShared {
 };
 
 // levenberg_marquadt_dyn.cpp:15-26 (prepare) + the first setup(x0), by one warp.
-__device__ inline void lm_init_warp(LmState* st, CostSlot* slots, const LmInit& in, LmStepShared* sh, int lane) {
+static __device__ __noinline__ void lm_init_warp(LmState* st, CostSlot* slots, const LmInit& in, LmStepShared* sh, int lane) {
   if (lane == 0) {
     st->P = in.P; st->n_costs = in.n_costs; st->max_it = in.max_it; st->lm_max_it = in.lm_max_it;
     st->speculative = in.speculative; st->scalar_f32 = in.scalar_f32; st->lambda_factor = in.lambda_factor;
@@ -434,8 +434,10 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
 }
 // P and the Scalar of the LM arithmetic are launch-time constants of a minimize() call: the callers pass them as
 // kernel arguments instead of reading them from the state (two dependent L2 round trips per transition).
-__device__ inline int lm_step_warp(LmState* st, const PassResult* trial, CostSlot* slots, LmStepShared* sh, int lane,
-                                   int P, bool f32, long long* prof = nullptr) {
+// __noinline__: one copy per translation unit instead of one per kernel instantiation (the persistent LM kernel alone
+// has 18; inlined, that translation unit took six minutes to compile).
+static __device__ __noinline__ int lm_step_warp(LmState* st, const PassResult* trial, CostSlot* slots, LmStepShared* sh, int lane,
+                                                int P, bool f32, long long* prof = nullptr) {
   if (P == 6) {  // the 6-DoF registration case with unrolled loops
     return f32 ? lm_step_warp_t<float, 6>(st, trial, slots, sh, lane, P, prof) : lm_step_warp_t<double, 6>(st, trial, slots, sh, lane, P, prof);
   }

@@ -23,13 +23,29 @@ struct MonoArgs {
   unsigned long long* gen;      // grid-barrier generation counter: monotonic over the context's life, never reset
   unsigned long long gen_base;  // its value when this launch starts
   int max_slots;
+  int loss, qrot;               // mopt_loss_kind / "the moments are taken in q = R p" of the pass, chosen at run time here
   LmInit init;                  // prepare() arguments: CTA 0 initialises the state before the first pass
   unsigned long long* dbg;  // optional (MOPT_LM_MONO_TRACE=1): 4 globaltimer stamps per trial from the last CTA
 };
 
 #ifdef __CUDACC__
 
-template <typename ST, typename CT, int LOSS, bool QROT, int THREADS, int MINB, int UNROLL, int FLUSH_ROUNDS>
+// The loss kind and the Jacobian form are run-time switches over the six instantiations of the pass body (a small
+// problem does not care), so that there is ONE entry per (store, compute) type pair: ptxas compiles the optimizer
+// transition once per entry, and with a kernel per (loss, form) this translation unit took six minutes to build.
+template <typename ST, typename CT, int THREADS, int UNROLL, int FLUSH_ROUNDS>
+__device__ __forceinline__ bool p2p_mono_pass(const PassArgs& a, int mode, int loss, bool qrot) {
+#define MOPT_MONO_BODY(L, Q) p2p_moment_body<ST, CT, L, Q, THREADS, UNROLL, FLUSH_ROUNDS, 0, false, false, true>(a, mode)
+  switch (loss) {
+    case MOPT_LOSS_NONE: return qrot ? MOPT_MONO_BODY(MOPT_LOSS_NONE, true) : MOPT_MONO_BODY(MOPT_LOSS_NONE, false);
+    case MOPT_LOSS_GEMAN_MCCLURE:
+      return qrot ? MOPT_MONO_BODY(MOPT_LOSS_GEMAN_MCCLURE, true) : MOPT_MONO_BODY(MOPT_LOSS_GEMAN_MCCLURE, false);
+    default: return qrot ? MOPT_MONO_BODY(MOPT_LOSS_HUBER, true) : MOPT_MONO_BODY(MOPT_LOSS_HUBER, false);
+  }
+#undef MOPT_MONO_BODY
+}
+
+template <typename ST, typename CT, int THREADS, int MINB, int UNROLL, int FLUSH_ROUNDS>
 __global__ void __launch_bounds__(THREADS, MINB) p2p_lm_mono_kernel(const PassArgs a, const MonoArgs m) {
   __shared__ LmStepShared s_sh;
   auto open_barrier = [&](unsigned long long value) {  // thread 0 of the CTA that did the serial work
@@ -61,7 +77,7 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_lm_mono_kernel(const PassAr
     if (mode == PASS_SKIP) break;
     unsigned long long t_begin = 0;
     if (m.dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
-    const bool last = p2p_moment_body<ST, CT, LOSS, QROT, THREADS, UNROLL, FLUSH_ROUNDS, 0, false, false, true>(a, mode);
+    const bool last = p2p_mono_pass<ST, CT, THREADS, UNROLL, FLUSH_ROUNDS>(a, mode, m.loss, m.qrot != 0);
     const unsigned long long target = m.gen_base + 2ull + (unsigned long long)(slot);
     if (last) {
       __syncthreads();  // `out` complete (assembled by the whole CTA)
