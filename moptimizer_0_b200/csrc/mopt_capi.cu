@@ -101,7 +101,7 @@ __global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* s
     }
     return;
   }
-  long long stamps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long stamps[16] = {0};
   const int done = lm_step_warp(st, trial, slots, &s_sh, lane, P, scalar_f32 != 0, prof ? stamps : nullptr);
   if (lane == 0) {
     *flag = done;
@@ -818,10 +818,14 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
           std::fprintf(stderr, "mono trial %2d: pass %6.2f us  step %6.2f us  open %5.2f us  (next begins +%6.2f us)\n", s,
                        (h[s * 4 + 1] - h[s * 4]) * 1e-3, (h[s * 4 + 2] - h[s * 4 + 1]) * 1e-3, (h[s * 4 + 3] - h[s * 4 + 2]) * 1e-3,
                        h[(s + 1) * 4] ? (double(h[(s + 1) * 4]) - double(h[s * 4 + 3])) * 1e-3 : 0.0);
-        for (int s = 0; s < 24 && h[256 + s * 8 + 5]; ++s) {
-          const unsigned long long* q = h + 256 + s * 8;
-          std::fprintf(stderr, "mono step %2d (cycles): stage-in %llu  state machine %llu  solve+propose %llu  setup %llu  write-back %llu\n",
+        for (int s = 0; s < 16 && h[256 + s * 16 + 5]; ++s) {
+          const unsigned long long* q = h + 256 + s * 16;
+          std::fprintf(stderr, "mono step %2d (cycles): stage-in %llu  state machine %llu  solve+propose %llu  setup %llu  write-back %llu",
                        s, q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4]);
+          if (q[10] > q[6] && q[6] > q[2])
+            std::fprintf(stderr, "  | build A %llu  factor %llu  forward %llu  D %llu  backward %llu  propose %llu", q[6] - q[2],
+                         q[7] - q[6], q[8] - q[7], q[9] - q[8], q[10] - q[9], q[3] - q[10]);
+          std::fprintf(stderr, "\n");
         }
       }
       return finish_lm(ctx, P, x, report);

@@ -34,6 +34,7 @@ struct LmState {
 // Everything of LmState before the trace: what an optimizer transition reads and writes (staged in shared memory).
 constexpr int kLmHotWords = int(offsetof(LmState, trials) / 8);
 static_assert(offsetof(LmState, trials) % 8 == 0, "LmState hot part is copied in 8-byte words");
+static_assert(kPackedMax <= 160, "lm_step_warp_t stages the pass result with five loads per lane");
 
 // Arguments of levenberg_marquadt_dyn.cpp:15-26 (prepare), passed by value to the kernel that initialises the state.
 struct LmInit {
@@ -130,7 +131,8 @@ __device__ inline void lm_finish(LmState* st, int status) {
 // cycles per 6 x 6 solve on a B200 against ~5 000 now.  A (n x n, column-major, overwritten), tmp, y and tr live in
 // shared memory; n <= 16.  NC > 0: the size is known at compile time (the loops unroll).
 template <typename S, int NC = 0>
-__device__ inline void ldlt_solve_warp(int n_rt, S* A, const S* rhs, S* out, S* tmp, S* y, int* tr, int lane) {
+__device__ inline void ldlt_solve_warp(int n_rt, S* A, const S* rhs, S* out, S* tmp, S* y, int* tr, int lane,
+                                       long long* prof = nullptr) {
   const int n = NC > 0 ? NC : n_rt;
   unsigned long long perm = 0xFEDCBA9876543210ull;
   auto PH = [&](int i) { return int((perm >> (4 * i)) & 15ull); };
@@ -174,6 +176,7 @@ __device__ inline void ldlt_solve_warp(int n_rt, S* A, const S* rhs, S* out, S* 
     if (valid && lane > k && lane < n) MOPT_A(PH(lane), pk) /= akk;
     __syncwarp();
   }
+  if (prof && lane == 0) prof[7] = clock64();
   if (lane == 0) {
     for (int i = 0; i < n; ++i) y[i] = rhs[i];
     for (int k = 0; k < n; ++k) { const S t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
@@ -185,12 +188,14 @@ __device__ inline void ldlt_solve_warp(int n_rt, S* A, const S* rhs, S* out, S* 
     }
   }
   __syncwarp();
+  if (prof && lane == 0) prof[8] = clock64();
   if (lane < n) {  // D^+ with tolerance numeric_limits::min(): one division per lane
     const S tol = (sizeof(S) == 4) ? S(1.17549435e-38) : S(2.2250738585072014e-308);
     const S dd = MOPT_A(PH(lane), PH(lane));
     y[lane] = (fabs(dd) > tol) ? y[lane] / dd : S(0);
   }
   __syncwarp();
+  if (prof && lane == 0) prof[9] = clock64();
   if (lane == 0) {
     for (int r = n - 1; r >= 0; --r) {
       const int pr = PH(r);
@@ -202,6 +207,7 @@ __device__ inline void ldlt_solve_warp(int n_rt, S* A, const S* rhs, S* out, S* 
     for (int i = 0; i < n; ++i) out[i] = y[i];
   }
   __syncwarp();
+  if (prof && lane == 0) prof[10] = clock64();
 #undef MOPT_A
 }
 
@@ -214,7 +220,8 @@ struct LmSolveScratch {
 // Solve (H + lambda diag(H)) delta = -b (levenberg_marquadt_dyn.cpp:65,78-80), xi = x (+) delta (:83), executed by
 // one full warp: the lanes build the damped matrix and factor it together.
 template <typename S, int PC = 0>
-__device__ inline void lm_solve_propose_warp(LmState* st, const CostDev& cost0, LmSolveScratch* sc, int lane) {
+__device__ inline void lm_solve_propose_warp(LmState* st, const CostDev& cost0, LmSolveScratch* sc, int lane,
+                                             long long* prof = nullptr) {
   const int P = PC > 0 ? PC : st->P;
   S* A = reinterpret_cast<S*>(sc->A);
   S* nb = reinterpret_cast<S*>(sc->nb);
@@ -227,7 +234,8 @@ __device__ inline void lm_solve_propose_warp(LmState* st, const CostDev& cost0, 
   }
   if (lane < P) nb[lane] = -S(st->cur.v[P * (P + 1) / 2 + lane]);
   __syncwarp();
-  ldlt_solve_warp<S, PC>(P, A, nb, d, reinterpret_cast<S*>(sc->tmp), reinterpret_cast<S*>(sc->y), sc->tr, lane);
+  if (prof && lane == 0) prof[6] = clock64();
+  ldlt_solve_warp<S, PC>(P, A, nb, d, reinterpret_cast<S*>(sc->tmp), reinterpret_cast<S*>(sc->y), sc->tr, lane, prof);
   if (lane == 0) {
     for (int i = 0; i < P; ++i) st->delta[i] = double(d[i]);
     if (cost0.manifold == MOPT_MANIFOLD_SO3_LEFT) {
@@ -402,9 +410,27 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
   const int npk = packed_size(PC > 0 ? PC : P_rt);
   {
     const double* g = reinterpret_cast<const double*>(gst);
-    // past the L1: in the persistent kernel the state was last written by another SM (or by this one, earlier)
-    for (int i = lane; i < kLmHotWords; i += 32) sh->hot[i] = __ldcg(g + i);
-    for (int i = lane; i < npk; i += 32) sh->trial.v[i] = __ldcg(&gtrial->v[i]);
+    // past the L1: in the persistent kernel the state was last written by another SM (or by this one, earlier).
+    // All loads are issued before the first store (the compiler cannot prove that the generic pointers do not alias
+    // and would otherwise serialise eight L2 round trips).
+    constexpr int kPerLane = (kLmHotWords + 31) / 32;
+    double tmp[kPerLane];
+#pragma unroll
+    for (int q = 0; q < kPerLane; ++q) tmp[q] = (lane + 32 * q < kLmHotWords) ? __ldcg(g + lane + 32 * q) : 0.0;
+    double tr0 = 0.0, tr1 = 0.0, tr2 = 0.0, tr3 = 0.0, tr4 = 0.0;  // npk <= kPackedMax = 152 <= 5 * 32
+    if (lane < npk) tr0 = __ldcg(&gtrial->v[lane]);
+    if (lane + 32 < npk) tr1 = __ldcg(&gtrial->v[lane + 32]);
+    if (lane + 64 < npk) tr2 = __ldcg(&gtrial->v[lane + 64]);
+    if (lane + 96 < npk) tr3 = __ldcg(&gtrial->v[lane + 96]);
+    if (lane + 128 < npk) tr4 = __ldcg(&gtrial->v[lane + 128]);
+#pragma unroll
+    for (int q = 0; q < kPerLane; ++q)
+      if (lane + 32 * q < kLmHotWords) sh->hot[lane + 32 * q] = tmp[q];
+    if (lane < npk) sh->trial.v[lane] = tr0;
+    if (lane + 32 < npk) sh->trial.v[lane + 32] = tr1;
+    if (lane + 64 < npk) sh->trial.v[lane + 64] = tr2;
+    if (lane + 96 < npk) sh->trial.v[lane + 96] = tr3;
+    if (lane + 128 < npk) sh->trial.v[lane + 128] = tr4;
   }
   __syncwarp();
   if (prof && lane == 0) prof[1] = clock64();
@@ -414,7 +440,7 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
   __syncwarp();  // lane 0's state writes are visible to the warp below
   if (prof && lane == 0) prof[2] = clock64();
   if (act == 2) {  // damped solve + proposal, the lanes sharing the factorization
-    lm_solve_propose_warp<S, PC>(st, slots[0].cost, &sh->sc, lane);
+    lm_solve_propose_warp<S, PC>(st, slots[0].cost, &sh->sc, lane, prof);
     __syncwarp();
   }
   if (prof && lane == 0) prof[3] = clock64();

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_lm_mono_kernel(const PassAr
       if (m.dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_pass));
       if (threadIdx.x < 32)
         lm_step_warp(m.st, a.out, m.slots, &s_sh, threadIdx.x, m.init.P, m.init.scalar_f32 != 0,
-                     (m.dbg && slot < 24) ? reinterpret_cast<long long*>(m.dbg) + 256 + slot * 8 : nullptr);
+                     (m.dbg && slot < 16) ? reinterpret_cast<long long*>(m.dbg) + 256 + slot * 16 : nullptr);
       __syncthreads();
       if (threadIdx.x == 0) {
         if (m.dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_step));

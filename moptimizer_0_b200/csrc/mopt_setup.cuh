@@ -19,16 +19,20 @@ namespace mopt {
 // callers that need the literal behaviour of the float instantiation.
 constexpr double kSo3GuardF64 = 10.0 * 2.220446049250313e-16;
 constexpr double kSo3GuardF32 = 10.0 * 1.1920928955078125e-07;
+// `trig` (optional): receives {n, sin n, cos n} when they were evaluated (n > guard), so that a caller that needs the
+// same sine and cosine again (the left Jacobian at the same omega) does not pay for them twice; trig[0] = -1 otherwise.
 template <typename S>
-__device__ inline void so3_exp_dev(const double w[3], double R[9], double guard = kSo3GuardF64) {
+__device__ inline void so3_exp_dev(const double w[3], double R[9], double guard = kSo3GuardF64, double* trig = nullptr) {
   const double n = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if (trig) trig[0] = -1.0;
   if (n > guard) {
     const double a0 = w[0] / n, a1 = w[1] / n, a2 = w[2] / n;
     const double K[9] = {0.0, -a2, a1, a2, 0.0, -a0, -a1, a0, 0.0};
     double sn, cs;
     sincos(n, &sn, &cs);
+    if (trig) { trig[0] = n; trig[1] = sn; trig[2] = cs; }
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) {
         double kk = 0.0;
@@ -39,7 +43,10 @@ __device__ inline void so3_exp_dev(const double w[3], double R[9], double guard 
 }
 
 // Closed-form left Jacobian of SO(3): I + (1-cos)/th^2 [w]x + (th-sin)/th^3 [w]x^2.
-__device__ inline void so3_left_jacobian_dev(const double w[3], double J[9]) {
+// `trig` (optional) = {n, sin n, cos n} from so3_exp_dev at the same omega: used only when n equals this function's own
+// theta bit for bit, and sincos(x) is bit-identical to sin(x), cos(x) (scripts/check_sincos_identity.cu: 0 mismatches in
+// 2^30 samples), so the result does not depend on whether it is given.
+__device__ inline void so3_left_jacobian_dev(const double w[3], double J[9], const double* trig = nullptr) {
   const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   const double th = sqrt(th2);
   double A, B;
@@ -47,8 +54,11 @@ __device__ inline void so3_left_jacobian_dev(const double w[3], double J[9]) {
     A = 0.5 - th2 / 24.0;
     B = 1.0 / 6.0 - th2 / 120.0;
   } else {
-    A = (1.0 - cos(th)) / th2;
-    B = (th - sin(th)) / (th2 * th);
+    double sn, cs;
+    if (trig != nullptr && trig[0] == th) { sn = trig[1]; cs = trig[2]; }
+    else { cs = cos(th); sn = sin(th); }
+    A = (1.0 - cs) / th2;
+    B = (th - sn) / (th2 * th);
   }
   const double K[9] = {0.0, -w[2], w[1], w[2], 0.0, -w[0], -w[1], w[0], 0.0};
   for (int r = 0; r < 3; ++r)
@@ -304,8 +314,8 @@ __device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double*
 #pragma unroll
     for (int i = 0; i < 6; ++i) xs[i] = f32 ? double(float(x[i])) : x[i];
     const double w[3] = {xs[3], xs[4], xs[5]};
-    double R[9];
-    if (f32) so3_exp_dev<float>(w, R, c.so3_guard); else so3_exp_dev<double>(w, R, c.so3_guard);
+    double R[9], trig[3];
+    if (f32) so3_exp_dev<float>(w, R, c.so3_guard, trig); else so3_exp_dev<double>(w, R, c.so3_guard, trig);
 #pragma unroll
     for (int i = 0; i < 9; ++i) pb->sets[0][i] = R[i];
     pb->sets[0][9] = xs[0]; pb->sets[0][10] = xs[1]; pb->sets[0][11] = xs[2];
@@ -313,7 +323,7 @@ __device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double*
     for (int i = 0; i < 9; ++i) Jl[i] = (i % 4 == 0) ? 1.0 : 0.0;
     if (c.variant == MOPT_P2P_EXACT) {
       const double wj[3] = {x[3], x[4], x[5]};
-      so3_left_jacobian_dev(wj, Jl);
+      so3_left_jacobian_dev(wj, Jl, trig);  // same omega with a double Scalar: one sincos serves both
     }
   }
   if (lane >= 12 && lane < kSetSize) pb->sets[0][lane] = 0.0;
