@@ -72,6 +72,10 @@ class LmTrial(C.Structure):
                 ("nu", C.c_double)]
 
 
+_TRIAL_DTYPE = np.dtype([("outer_iteration", "<i4"), ("k", "<i4"), ("accepted", "<i4"), ("reserved", "<i4"),
+                         ("y0", "<f8"), ("yi", "<f8"), ("rho", "<f8"), ("lambda_", "<f8"), ("nu", "<f8")])
+
+
 class LmReport(C.Structure):
     _fields_ = [("status", C.c_int32), ("executed_iterations", C.c_int32), ("num_trials", C.c_int32),
                 ("num_passes", C.c_int32), ("final_cost", C.c_double), ("trials", LmTrial * MAX_TRACE)]
@@ -334,8 +338,11 @@ class Context:
         opt.max_iterations, opt.lm_max_iterations = max_iterations, lm_iterations
         opt.scalar_dtype, opt.speculative = scalar_dtype, 1 if speculative else 0
         opt.flags = LM_STAGNATION_STOP if stagnation_stop else 0
-        x = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).copy())
-        rep = LmReport()
+        x = np.array(x0, dtype=np.float64)
+        # the report is 57 KB (1024-entry trace): one per context, copied out of by LmResult (a small solve is ~100 us)
+        rep = self.__dict__.get("_lm_report")
+        if rep is None:
+            rep = self._lm_report = LmReport()
         check(lib().mopt_lm_minimize(self._h, n, hs, ps, C.byref(opt), _dp(x), C.byref(rep)))
         return LmResult(x, rep)
 
@@ -348,12 +355,22 @@ class LmResult:
         self.num_passes = rep.num_passes
         self.final_cost = rep.final_cost
         n = rep.num_trials
-        self.trace = np.array([[t.outer_iteration, t.k, t.y0, t.yi, t.rho, t.lambda_, t.nu, t.accepted]
-                               for t in rep.trials[:n]], dtype=np.float64).reshape(n, 8)
+        self._trials = np.frombuffer(rep, dtype=_TRIAL_DTYPE, count=n, offset=LmReport.trials.offset).copy()
+        self._trace = None
+
+    @property
+    def trace(self) -> np.ndarray:
+        """[num_trials, 8]: outer_iteration, k, y0, yi, rho, lambda, nu, accepted."""
+        if self._trace is None:
+            t = self._trials
+            self._trace = np.stack([t[f].astype(np.float64) for f in
+                                    ("outer_iteration", "k", "y0", "yi", "rho", "lambda_", "nu", "accepted")],
+                                   axis=1).reshape(len(t), 8)
+        return self._trace
 
     @property
     def sequence(self) -> str:
-        return "".join("A" if r[7] else "R" for r in self.trace)
+        return "".join("A" if a else "R" for a in self._trials["accepted"])
 
 
 class Store:

@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <cmath>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -102,7 +103,7 @@ __global__ void lm_step_kernel(LmState* st, const PassResult* trial, CostSlot* s
     return;
   }
   long long stamps[16] = {0};
-  const int done = lm_step_warp(st, trial, slots, &s_sh, lane, P, scalar_f32 != 0, prof ? stamps : nullptr);
+  const int done = lm_step_warp(st, trial, slots, &s_sh, lane, P, scalar_f32 != 0, LmStepIo{}, prof ? stamps : nullptr);
   if (lane == 0) {
     *flag = done;
     if (prof && stamps[3] - stamps[2] > 1000)  // a transition that solved
@@ -405,14 +406,18 @@ int fetch_result(mopt_ctx* ctx, int P, double* H, double* b, double* sum) {
 }
 
 // Copies the final optimizer state back: x, status, iteration count and trace (end of mopt_lm_minimize).
-int finish_lm(mopt_ctx* ctx, int P, double* x, mopt_lm_report* report) {
+// on_host: the kernel wrote the final state and the trace into ctx->h_lm itself (mapped memory; persistent LM kernel)
+// and the stream has been synchronised: no copy, no second round trip.
+int finish_lm(mopt_ctx* ctx, int P, double* x, mopt_lm_report* report, bool on_host = false) {
   // the state is 57 KB with its 1024-entry trace: fetch the hot part and the first trials, the rest only if used
   LmState* hs = ctx->h_lm;
   constexpr int kFirstTrials = 48;
   const size_t first = offsetof(LmState, trials) + sizeof(mopt_lm_trial) * kFirstTrials;
-  MOPT_CUDA_TRY(cudaMemcpyAsync(hs, ctx->d_lm, first, cudaMemcpyDeviceToHost, ctx->stream));
-  MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (hs->num_trials > kFirstTrials) {
+  if (!on_host) {
+    MOPT_CUDA_TRY(cudaMemcpyAsync(hs, ctx->d_lm, first, cudaMemcpyDeviceToHost, ctx->stream));
+    MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  if (!on_host && hs->num_trials > kFirstTrials) {
     const int more = (hs->num_trials < MOPT_MAX_TRACE ? hs->num_trials : MOPT_MAX_TRACE) - kFirstTrials;
     MOPT_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(hs) + first, reinterpret_cast<const char*>(ctx->d_lm) + first,
                                   sizeof(mopt_lm_trial) * size_t(more), cudaMemcpyDeviceToHost, ctx->stream));
@@ -453,7 +458,8 @@ int ctx_alloc(mopt_ctx* ctx) {
   MOPT_CUDA_TRY(cudaMalloc(&ctx->d_lm, sizeof(LmState)));
   MOPT_CUDA_TRY(cudaMemset(ctx->d_lm, 0, sizeof(LmState)));
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_result, sizeof(PassResult), cudaHostAllocDefault));
-  MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_lm, sizeof(LmState), cudaHostAllocDefault));
+  MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_lm, sizeof(LmState), cudaHostAllocMapped));
+  MOPT_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_lm_host), ctx->h_lm, 0));
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_slot, sizeof(CostSlot), cudaHostAllocDefault));
   MOPT_CUDA_TRY(cudaMalloc(&ctx->d_xbuf, sizeof(XSlot) * 2 * kMaxWorld));
   MOPT_CUDA_TRY(cudaMemset(ctx->d_xbuf, 0, sizeof(XSlot) * 2 * kMaxWorld));
@@ -792,6 +798,8 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
       PassLaunch L{ctx->stream, ctx->num_sms, ctx->ctas_per_sm, ctx->threads};
       MonoArgs m;
       m.st = ctx->d_lm;
+      m.host_st = ctx->d_lm_host;
+      ctx->h_lm->done = 0;
       m.slots = ctx->d_slots;
       m.gen = ctx->d_gen;
       const int64_t slots64 = int64_t(opt.max_iterations) * (int64_t(opt.lm_max_iterations) + 1) + 2;
@@ -808,27 +816,36 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
         m.dbg = d_dbg;
       }
       const bool qrot = p0.jacobian == MOPT_JAC_ANALYTICAL && (p0.variant == MOPT_P2P_EXACT || p0.variant == MOPT_P2P_LEFT);
+      const auto h0 = std::chrono::steady_clock::now();
       MOPT_TRY(launch_p2p_lm_mono(L, stores[0]->dtype, p0.compute_dtype, p0.loss, qrot, a, m));
+      const auto h1 = std::chrono::steady_clock::now();
       MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      const auto h2 = std::chrono::steady_clock::now();
       if (d_dbg) {
+        std::fprintf(stderr, "mono host: launch call %.1f us, wait for the kernel %.1f us\n",
+                     std::chrono::duration<double, std::micro>(h1 - h0).count(),
+                     std::chrono::duration<double, std::micro>(h2 - h1).count());
         unsigned long long h[512];
         MOPT_CUDA_TRY(cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(d_dbg);
+        std::fprintf(stderr, "mono kernel: init %.2f us, loop %.2f us (CTA 0), last data CTA leaves %+.2f us after CTA 0\n",
+                     (h[501] - h[500]) * 1e-3, (h[502] - h[501]) * 1e-3, (double(h[503]) - double(h[502])) * 1e-3);
         for (int s = 0; s < 64 && h[s * 4 + 3]; ++s)
           std::fprintf(stderr, "mono trial %2d: pass %6.2f us  step %6.2f us  open %5.2f us  (next begins +%6.2f us)\n", s,
                        (h[s * 4 + 1] - h[s * 4]) * 1e-3, (h[s * 4 + 2] - h[s * 4 + 1]) * 1e-3, (h[s * 4 + 3] - h[s * 4 + 2]) * 1e-3,
                        h[(s + 1) * 4] ? (double(h[(s + 1) * 4]) - double(h[s * 4 + 3])) * 1e-3 : 0.0);
-        for (int s = 0; s < 16 && h[256 + s * 16 + 5]; ++s) {
+        for (int s = 0; s < 15 && h[256 + s * 16 + 5]; ++s) {
           const unsigned long long* q = h + 256 + s * 16;
           std::fprintf(stderr, "mono step %2d (cycles): stage-in %llu  state machine %llu  solve+propose %llu  setup %llu  write-back %llu",
                        s, q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - q[4]);
           if (q[10] > q[6] && q[6] > q[2])
             std::fprintf(stderr, "  | build A %llu  factor %llu  forward %llu  D %llu  backward %llu  propose %llu", q[6] - q[2],
                          q[7] - q[6], q[8] - q[7], q[9] - q[8], q[10] - q[9], q[3] - q[10]);
+          if (q[11] > q[3]) std::fprintf(stderr, "  | barrier opened %llu cycles into the setup", q[11] - q[3]);
           std::fprintf(stderr, "\n");
         }
       }
-      return finish_lm(ctx, P, x, report);
+      return finish_lm(ctx, P, x, report, /*on_host=*/true);
     }
   }
 

@@ -23,6 +23,7 @@ struct mopt_ctx {
   // pinned host mirrors
   mopt::PassResult* h_result = nullptr;
   mopt::LmState* h_lm = nullptr;
+  mopt::LmState* d_lm_host = nullptr;  // device address of h_lm (mapped): the persistent LM kernel reports through it
   mopt::CostSlot* h_slot = nullptr;  // staging for cost constants
   int* h_flags = nullptr;            // per-slot done flags written by lm_step_kernel (mapped)
   int* d_flags = nullptr;            // device alias of h_flags

@@ -236,14 +236,20 @@ __device__ inline void lm_solve_propose_warp(LmState* st, const CostDev& cost0, 
   __syncwarp();
   if (prof && lane == 0) prof[6] = clock64();
   ldlt_solve_warp<S, PC>(P, A, nb, d, reinterpret_cast<S*>(sc->tmp), reinterpret_cast<S*>(sc->y), sc->tr, lane, prof);
-  if (lane == 0) {
-    for (int i = 0; i < P; ++i) st->delta[i] = double(d[i]);
-    if (cost0.manifold == MOPT_MANIFOLD_SO3_LEFT) {
+  if (cost0.manifold == MOPT_MANIFOLD_SO3_LEFT) {
+    if (lane == 0) {
+      for (int i = 0; i < P; ++i) st->delta[i] = double(d[i]);
       retract_dev(cost0, st->x, st->delta, st->xi, sizeof(S) == 4);  // opt-in manifold update
-    } else {
-      for (int i = 0; i < P; ++i) st->xi[i] = double(S(st->x[i]) + d[i]);  // levenberg_marquadt_dyn.cpp:83
+      for (int i = 0; i < P; ++i) st->x_eval[i] = st->xi[i];
     }
-    for (int i = 0; i < P; ++i) st->x_eval[i] = st->xi[i];
+  } else if (lane < P) {  // one parameter per lane
+    const S dl = d[lane];
+    const double xi = double(S(st->x[lane]) + dl);  // levenberg_marquadt_dyn.cpp:83
+    st->delta[lane] = double(dl);
+    st->xi[lane] = xi;
+    st->x_eval[lane] = xi;
+  }
+  if (lane == 0) {
     st->phase = LM_PHASE_TRIAL;
     st->pass_mode = st->speculative ? PASS_LINEARIZE : PASS_COST;
   }
@@ -377,6 +383,22 @@ struct LmStepShared {
   PassResult trial;
 };
 
+// How a transition finds its inputs.  The launch-per-trial path stages the state from and to global memory around
+// every transition; the persistent kernel keeps it in CTA 0's shared memory from the first trial to the last
+// (load_state on the first, store_state on the last or once `done` is set), gets the pass result in shared memory
+// from the pass itself (trial_staged) and reads the cost constants from a shared-memory copy (cost0): every one of
+// these was an L2 round trip of ~800 cycles in the dependent chain of a trial.
+struct LmStepIo {
+  bool load_state = true, store_state = true, trial_staged = false;
+  const CostDev* cost0 = nullptr;  // cost term 0's constants if the caller holds a copy, else read from the slot
+  // persistent kernel: the grid barrier word, this trial's target and a shared-memory flag — a set-up that knows when
+  // the next pass's own inputs are complete releases the waiting CTAs itself (SetupEarlyOpen, mopt_setup.cuh)
+  unsigned long long* gen = nullptr;
+  unsigned long long gen_target = 0;
+  int* opened = nullptr;
+  LmState* host_state = nullptr;  // mapped host memory: the trace and the final state are written there as well
+};
+
 // levenberg_marquadt_dyn.cpp:15-26 (prepare) + the first setup(x0), by one warp.
 static __device__ __noinline__ void lm_init_warp(LmState* st, CostSlot* slots, const LmInit& in, LmStepShared* sh, int lane) {
   if (lane == 0) {
@@ -404,7 +426,7 @@ static __device__ __noinline__ void lm_init_warp(LmState* st, CostSlot* slots, c
 // Returns the state's `done` flag after the transition.
 template <typename S, int PC>
 __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, CostSlot* slots, LmStepShared* sh, int lane,
-                                     int P_rt, long long* prof = nullptr) {
+                                     int P_rt, const LmStepIo& io, long long* prof = nullptr) {
   LmState* st = reinterpret_cast<LmState*>(sh->hot);
   if (prof && lane == 0) prof[0] = clock64();
   const int npk = packed_size(PC > 0 ? PC : P_rt);
@@ -415,44 +437,60 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
     // and would otherwise serialise eight L2 round trips).
     constexpr int kPerLane = (kLmHotWords + 31) / 32;
     double tmp[kPerLane];
+    if (io.load_state) {
 #pragma unroll
-    for (int q = 0; q < kPerLane; ++q) tmp[q] = (lane + 32 * q < kLmHotWords) ? __ldcg(g + lane + 32 * q) : 0.0;
+      for (int q = 0; q < kPerLane; ++q) tmp[q] = (lane + 32 * q < kLmHotWords) ? __ldcg(g + lane + 32 * q) : 0.0;
+    }
     double tr0 = 0.0, tr1 = 0.0, tr2 = 0.0, tr3 = 0.0, tr4 = 0.0;  // npk <= kPackedMax = 152 <= 5 * 32
-    if (lane < npk) tr0 = __ldcg(&gtrial->v[lane]);
-    if (lane + 32 < npk) tr1 = __ldcg(&gtrial->v[lane + 32]);
-    if (lane + 64 < npk) tr2 = __ldcg(&gtrial->v[lane + 64]);
-    if (lane + 96 < npk) tr3 = __ldcg(&gtrial->v[lane + 96]);
-    if (lane + 128 < npk) tr4 = __ldcg(&gtrial->v[lane + 128]);
+    if (!io.trial_staged) {
+      if (lane < npk) tr0 = __ldcg(&gtrial->v[lane]);
+      if (lane + 32 < npk) tr1 = __ldcg(&gtrial->v[lane + 32]);
+      if (lane + 64 < npk) tr2 = __ldcg(&gtrial->v[lane + 64]);
+      if (lane + 96 < npk) tr3 = __ldcg(&gtrial->v[lane + 96]);
+      if (lane + 128 < npk) tr4 = __ldcg(&gtrial->v[lane + 128]);
+    }
+    if (io.load_state) {
 #pragma unroll
-    for (int q = 0; q < kPerLane; ++q)
-      if (lane + 32 * q < kLmHotWords) sh->hot[lane + 32 * q] = tmp[q];
-    if (lane < npk) sh->trial.v[lane] = tr0;
-    if (lane + 32 < npk) sh->trial.v[lane + 32] = tr1;
-    if (lane + 64 < npk) sh->trial.v[lane + 64] = tr2;
-    if (lane + 96 < npk) sh->trial.v[lane + 96] = tr3;
-    if (lane + 128 < npk) sh->trial.v[lane + 128] = tr4;
+      for (int q = 0; q < kPerLane; ++q)
+        if (lane + 32 * q < kLmHotWords) sh->hot[lane + 32 * q] = tmp[q];
+    }
+    if (!io.trial_staged) {
+      if (lane < npk) sh->trial.v[lane] = tr0;
+      if (lane + 32 < npk) sh->trial.v[lane + 32] = tr1;
+      if (lane + 64 < npk) sh->trial.v[lane + 64] = tr2;
+      if (lane + 96 < npk) sh->trial.v[lane + 96] = tr3;
+      if (lane + 128 < npk) sh->trial.v[lane + 128] = tr4;
+    }
   }
   __syncwarp();
   if (prof && lane == 0) prof[1] = clock64();
+  const CostDev& cost0 = io.cost0 ? *io.cost0 : slots[0].cost;
   int act = 0;
-  if (lane == 0) act = lm_step_thread<S, PC>(st, &sh->trial, slots[0].cost, gst->trials);
+  if (lane == 0) act = lm_step_thread<S, PC>(st, &sh->trial, cost0, io.host_state ? io.host_state->trials : gst->trials);
   act = __shfl_sync(0xffffffffu, act, 0);
   __syncwarp();  // lane 0's state writes are visible to the warp below
   if (prof && lane == 0) prof[2] = clock64();
   if (act == 2) {  // damped solve + proposal, the lanes sharing the factorization
-    lm_solve_propose_warp<S, PC>(st, slots[0].cost, &sh->sc, lane, prof);
+    lm_solve_propose_warp<S, PC>(st, cost0, &sh->sc, lane, prof);
     __syncwarp();
   }
   if (prof && lane == 0) prof[3] = clock64();
   if (act) {
     const int nc = st->n_costs;
-    for (int c = 0; c < nc; ++c) setup_cost(slots[c].cost, st->x_eval, &slots[c].pb, lane, 32, sh->sc.tmp);
+    const SetupEarlyOpen eo{io.gen, (io.gen_target << 2) | (unsigned long long)(st->pass_mode), io.opened, prof};
+    for (int c = 0; c < nc; ++c)
+      setup_cost(c == 0 ? cost0 : slots[c].cost, st->x_eval, &slots[c].pb, lane, 32, sh->sc.tmp,
+                 (io.gen != nullptr && nc == 1) ? &eo : nullptr);
   }
   __syncwarp();
   if (prof && lane == 0) prof[4] = clock64();
-  {
+  if (io.store_state || st->done) {
     double* g = reinterpret_cast<double*>(gst);
     for (int i = lane; i < kLmHotWords; i += 32) g[i] = sh->hot[i];
+    if (io.host_state) {
+      double* h = reinterpret_cast<double*>(io.host_state);
+      for (int i = lane; i < kLmHotWords; i += 32) h[i] = sh->hot[i];
+    }
   }
   __syncwarp();
   if (prof && lane == 0) prof[5] = clock64();
@@ -463,11 +501,13 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
 // __noinline__: one copy per translation unit instead of one per kernel instantiation (the persistent LM kernel alone
 // has 18; inlined, that translation unit took six minutes to compile).
 static __device__ __noinline__ int lm_step_warp(LmState* st, const PassResult* trial, CostSlot* slots, LmStepShared* sh, int lane,
-                                                int P, bool f32, long long* prof = nullptr) {
+                                                int P, bool f32, const LmStepIo& io, long long* prof = nullptr) {
   if (P == 6) {  // the 6-DoF registration case with unrolled loops
-    return f32 ? lm_step_warp_t<float, 6>(st, trial, slots, sh, lane, P, prof) : lm_step_warp_t<double, 6>(st, trial, slots, sh, lane, P, prof);
+    return f32 ? lm_step_warp_t<float, 6>(st, trial, slots, sh, lane, P, io, prof)
+               : lm_step_warp_t<double, 6>(st, trial, slots, sh, lane, P, io, prof);
   }
-  return f32 ? lm_step_warp_t<float, 0>(st, trial, slots, sh, lane, P, prof) : lm_step_warp_t<double, 0>(st, trial, slots, sh, lane, P, prof);
+  return f32 ? lm_step_warp_t<float, 0>(st, trial, slots, sh, lane, P, io, prof)
+             : lm_step_warp_t<double, 0>(st, trial, slots, sh, lane, P, io, prof);
 }
 
 #endif  // __CUDACC__

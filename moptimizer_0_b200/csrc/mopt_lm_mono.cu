@@ -1,5 +1,7 @@
 // Instantiations + dispatch of the persistent LM kernel for small problems (mopt_lm_mono.cuh).  Its own translation
 // unit so that the library builds in parallel.
+#include <mutex>
+
 #include "mopt_internal.h"
 #include "mopt_lm_mono.cuh"
 
@@ -19,7 +21,24 @@ int launch_mono_loss(const PassLaunch& L, int loss, bool qrot, const PassArgs& a
   }
   auto kern = p2p_lm_mono_kernel<ST, CT, S::THREADS, S::MINB, S::UNROLL, S::FLUSH>;
   const int64_t groups = a.n / VecOf<ST>::N;
-  const int grid = pick_grid(reinterpret_cast<const void*>(kern), S::THREADS, L, groups);  // <= co-resident CTAs
+  // data CTAs as the pass kernel would size them, plus CTA 0 (the optimizer); all co-resident
+  // (the occupancy query behind pick_grid costs microseconds: once per instantiation and launch shape)
+  static std::mutex mu;
+  static int cached_key = -1, cached_co = 0;
+  const int key = L.num_sms * 64 + L.ctas_per_sm;
+  int co_resident;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached_key != key) {
+      cached_co = pick_grid(reinterpret_cast<const void*>(kern), S::THREADS, L, int64_t(1) << 40);
+      cached_key = key;
+    }
+    co_resident = cached_co;
+  }
+  int64_t need = (groups + S::THREADS - 1) / S::THREADS;
+  int data = int(need < co_resident - 1 ? need : co_resident - 1);
+  if (data < 1) data = 1;
+  const int grid = data + 1;
   PassArgs aa = a;
   MonoArgs mm = m;
   mm.loss = loss;

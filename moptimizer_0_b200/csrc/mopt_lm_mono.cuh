@@ -19,6 +19,7 @@ namespace mopt {
 
 struct MonoArgs {
   LmState* st;
+  LmState* host_st;             // mapped host copy of the state: final state and trace are written there too
   CostSlot* slots;
   unsigned long long* gen;      // grid-barrier generation counter: monotonic over the context's life, never reset
   unsigned long long gen_base;  // its value when this launch starts
@@ -34,71 +35,104 @@ struct MonoArgs {
 // problem does not care), so that there is ONE entry per (store, compute) type pair: ptxas compiles the optimizer
 // transition once per entry, and with a kernel per (loss, form) this translation unit took six minutes to build.
 template <typename ST, typename CT, int THREADS, int UNROLL, int FLUSH_ROUNDS>
-__device__ __forceinline__ bool p2p_mono_pass(const PassArgs& a, int mode, int loss, bool qrot) {
+__device__ __forceinline__ void p2p_mono_pass(const PassArgs& a, int mode, int loss, bool qrot) {
 #define MOPT_MONO_BODY(L, Q) p2p_moment_body<ST, CT, L, Q, THREADS, UNROLL, FLUSH_ROUNDS, 0, false, false, true>(a, mode)
   switch (loss) {
-    case MOPT_LOSS_NONE: return qrot ? MOPT_MONO_BODY(MOPT_LOSS_NONE, true) : MOPT_MONO_BODY(MOPT_LOSS_NONE, false);
+    case MOPT_LOSS_NONE: qrot ? MOPT_MONO_BODY(MOPT_LOSS_NONE, true) : MOPT_MONO_BODY(MOPT_LOSS_NONE, false); break;
     case MOPT_LOSS_GEMAN_MCCLURE:
-      return qrot ? MOPT_MONO_BODY(MOPT_LOSS_GEMAN_MCCLURE, true) : MOPT_MONO_BODY(MOPT_LOSS_GEMAN_MCCLURE, false);
-    default: return qrot ? MOPT_MONO_BODY(MOPT_LOSS_HUBER, true) : MOPT_MONO_BODY(MOPT_LOSS_HUBER, false);
+      qrot ? MOPT_MONO_BODY(MOPT_LOSS_GEMAN_MCCLURE, true) : MOPT_MONO_BODY(MOPT_LOSS_GEMAN_MCCLURE, false);
+      break;
+    default: qrot ? MOPT_MONO_BODY(MOPT_LOSS_HUBER, true) : MOPT_MONO_BODY(MOPT_LOSS_HUBER, false); break;
   }
 #undef MOPT_MONO_BODY
 }
 
+// CTA 0 is the optimizer: it takes no residuals.  Per trial it (a) forms the parts of the assembly that depend on its
+// own set-up alone while CTAs 1.. stream their residuals, (b) waits for their partials, finishes (H, b, sum) in shared
+// memory, (c) runs the transition on warp 0 with the state resident in shared memory, and (d) releases the data CTAs
+// as soon as the next pass's (R, t) is written — the rest of the set-up (left Jacobian, 72 affine entries) overlaps
+// the pass.  The barrier's word carries the control word of the next pass in its two low bits (PassMode < 4): a
+// waiting CTA learns "linearize / cost only / stop" from the very load that releases it.
 template <typename ST, typename CT, int THREADS, int MINB, int UNROLL, int FLUSH_ROUNDS>
 __global__ void __launch_bounds__(THREADS, MINB) p2p_lm_mono_kernel(const PassArgs a, const MonoArgs m) {
-  __shared__ LmStepShared s_sh;
-  auto open_barrier = [&](unsigned long long value) {  // thread 0 of the CTA that did the serial work
-    __threadfence();  // state, ParamBlock and control word before the barrier opens
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(m.gen), "l"(value) : "memory");
+  __shared__ LmStepShared s_sh;  // CTA 0: LDL^T scratch, the optimizer state (resident from the first trial to the last), the pass result
+  __shared__ CostDev s_cost;     // CTA 0: the cost term's constants for the optimizer step
+  __shared__ int s_mode, s_opened;
+  auto open_barrier = [&](unsigned long long value, int mode) {  // thread 0 of CTA 0
+    // (the release covers the ParamBlock written by this CTA before the __syncthreads that precedes the call)
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(m.gen), "l"((value << 2) | (unsigned long long)(mode)) : "memory");
   };
-  auto wait_barrier = [&](unsigned long long value) {  // thread 0 of every other CTA
+  auto wait_barrier = [&](unsigned long long value) -> int {  // thread 0 of every other CTA
     unsigned long long g;
     for (;;) {
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(g) : "l"(m.gen) : "memory");
-      if (g >= value) break;
-      __nanosleep(100);
+      if ((g >> 2) >= value) break;
+      __nanosleep(40);
     }
-    __threadfence();
+    return int(g & 3ull);
   };
+  const bool master = blockIdx.x == 0;
+  if (m.dbg && master && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); m.dbg[500] = t; }
   // prepare() + the first setup(x0): CTA 0, everyone else waits (no separate init kernel, no launch gap)
-  if (blockIdx.x == 0) {
+  if (master) {
+    for (int i = threadIdx.x; i < int(sizeof(CostDev) / 4); i += THREADS)
+      reinterpret_cast<int*>(&s_cost)[i] = reinterpret_cast<const int*>(&m.slots[0].cost)[i];
     if (threadIdx.x < 32) lm_init_warp(m.st, m.slots, m.init, &s_sh, threadIdx.x);
     __syncthreads();
-    if (threadIdx.x == 0) open_barrier(m.gen_base + 1);
+    if (threadIdx.x == 0) {
+      s_mode = PASS_LINEARIZE;
+      open_barrier(m.gen_base + 1, PASS_LINEARIZE);
+    }
   } else if (threadIdx.x == 0) {
-    wait_barrier(m.gen_base + 1);
+    s_mode = wait_barrier(m.gen_base + 1);
   }
   __syncthreads();
+  if (m.dbg && master && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); m.dbg[501] = t; }
   for (int slot = 0; slot < m.max_slots; ++slot) {
-    // the control word and the ParamBlock were written by another CTA, possibly on another SM: read past the L1
-    // (the barrier also fences, which drops this SM's L1 lines)
-    const int mode = __ldcg(a.mode_ptr);
+    const int mode = s_mode;  // written before the __syncthreads that ends the previous iteration
     if (mode == PASS_SKIP) break;
-    unsigned long long t_begin = 0;
-    if (m.dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
-    const bool last = p2p_mono_pass<ST, CT, THREADS, UNROLL, FLUSH_ROUNDS>(a, mode, m.loss, m.qrot != 0);
     const unsigned long long target = m.gen_base + 2ull + (unsigned long long)(slot);
-    if (last) {
-      __syncthreads();  // `out` complete (assembled by the whole CTA)
-      unsigned long long t_pass = 0, t_step = 0, t_open = 0;
+    if (!master) {
+      p2p_mono_pass<ST, CT, THREADS, UNROLL, FLUSH_ROUNDS>(a, mode, m.loss, m.qrot != 0);
+      if (threadIdx.x == 0) s_mode = wait_barrier(target);
+    } else {
+      unsigned long long t_begin = 0, t_pass = 0, t_step = 0, t_open = 0;
+      if (m.dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));
+      p2p_master_tail<THREADS>(a, mode, &s_sh.trial);
+      if (threadIdx.x == 0) s_opened = 0;
+      __syncthreads();  // the pass result complete (assembled by the whole CTA, in shared memory)
       if (m.dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_pass));
-      if (threadIdx.x < 32)
-        lm_step_warp(m.st, a.out, m.slots, &s_sh, threadIdx.x, m.init.P, m.init.scalar_f32 != 0,
-                     (m.dbg && slot < 16) ? reinterpret_cast<long long*>(m.dbg) + 256 + slot * 16 : nullptr);
+      if (threadIdx.x < 32) {
+        LmStepIo io;
+        io.load_state = (slot == 0);
+        io.store_state = (slot == m.max_slots - 1);  // and whenever the state machine ends (lm_step_warp_t)
+        io.trial_staged = true;
+        io.cost0 = &s_cost;
+        io.gen = m.gen;
+        io.gen_target = target;
+        io.opened = &s_opened;
+        io.host_state = m.host_st;
+        lm_step_warp(m.st, &s_sh.trial, m.slots, &s_sh, threadIdx.x, m.init.P, m.init.scalar_f32 != 0, io,
+                     (m.dbg && slot < 15) ? reinterpret_cast<long long*>(m.dbg) + 256 + slot * 16 : nullptr);
+      }
       __syncthreads();
       if (threadIdx.x == 0) {
         if (m.dbg) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_step));
-        open_barrier(target);
+        const int next = reinterpret_cast<const LmState*>(s_sh.hot)->pass_mode;
+        s_mode = next;
+        if (!s_opened) open_barrier(target, next);
         if (m.dbg && slot < 64) {
           asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_open));
           m.dbg[slot * 4 + 0] = t_begin; m.dbg[slot * 4 + 1] = t_pass; m.dbg[slot * 4 + 2] = t_step; m.dbg[slot * 4 + 3] = t_open;
         }
       }
-    } else if (threadIdx.x == 0) {
-      wait_barrier(target);
     }
     __syncthreads();
+  }
+  if (m.dbg && threadIdx.x == 0 && (master || blockIdx.x == gridDim.x - 1)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    m.dbg[master ? 502 : 503] = t;
   }
 }
 

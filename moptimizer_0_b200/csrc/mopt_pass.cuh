@@ -64,32 +64,64 @@ struct PassArgs {
 // After the call, in the LAST CTA only, s_tot[0..NRAW) holds the grid totals (fp64) and the
 // function returns true for every thread of that CTA.
 // Part 2: s_warp[w * STRIDE + i] holds warp w's total of raw sum i (all warps written, CTA synchronised).
-// MASTER (persistent LM kernel only, every CTA co-resident): CTA 0 — not whichever CTA arrives last — waits for the
-// others' partials and does the serial tail (final reduction, assembly, optimizer step), so that code stays in ONE
-// SM's instruction cache from trial to trial instead of being fetched cold by a different SM each time.
+// MASTER (persistent LM kernel only, every CTA co-resident): CTA 0 of that kernel takes no residuals; it waits for the
+// partials of the gridDim.x - 1 data CTAs and does the serial tail (grid_final_reduce, assembly, optimizer step), so
+// that code stays in ONE SM's instruction cache from trial to trial and overlaps its set-up work with the pass.  The
+// data CTAs (this function, MASTER = true) number themselves blockIdx.x - 1 and always return false.
+template <int NRAW, int THREADS>
+__device__ __forceinline__ void grid_final_reduce(const double* partials, int G, double* s_tot) {
+  constexpr int NW = THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // fixed-order reduction of the G per-CTA partials: lanes stride over CTAs, xor-butterfly combine.  A warp owns rows
+  // warp, warp + NW, ...; it walks them TOGETHER (all their loads in flight at once, the butterflies interleaved):
+  // every row still adds the same values in the same order, and the tail of a pass is one L2 round trip plus one
+  // butterfly instead of ROWS of each in sequence.
+  constexpr int ROWS = (NRAW + NW - 1) / NW;
+  constexpr int RB = ROWS < 4 ? ROWS : 4;  // rows in flight per warp (bounded: the tail must not set the kernel's register count)
+  for (int q0 = 0; q0 < ROWS; q0 += RB) {
+    double s[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) s[q] = 0.0;
+    for (int c = lane; c < G; c += 32) {
+      double v[RB];
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        const int i = warp + (q0 + q) * NW;
+        v[q] = (i < NRAW) ? __ldcg(partials + size_t(i) * G + c) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < RB; ++q) s[q] += v[q];
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < RB; ++q) s[q] += shfl_xor(s[q], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < RB; ++q)
+        if (warp + (q0 + q) * NW < NRAW) s_tot[warp + (q0 + q) * NW] = s[q];
+    }
+  }
+}
+
 template <int NRAW, int STRIDE, int THREADS, bool MASTER = false>
 __device__ __forceinline__ bool grid_reduce_shared(const PassArgs& a, double* s_tot, const double* s_warp) {
   constexpr int NW = THREADS / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ bool s_last;
-  const int G = gridDim.x;
+  const int G = MASTER ? int(gridDim.x) - 1 : int(gridDim.x);
+  const int bid = MASTER ? int(blockIdx.x) - 1 : int(blockIdx.x);
   for (int i = threadIdx.x; i < NRAW; i += THREADS) {
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) s += s_warp[w * STRIDE + i];
-    a.partials[size_t(i) * G + blockIdx.x] = s;
+    a.partials[size_t(i) * G + bid] = s;
   }
   __threadfence();
   __syncthreads();
   if constexpr (MASTER) {
-    if (blockIdx.x != 0) {
-      if (threadIdx.x == 0) atomicAdd(a.ticket, 1u);
-      return false;
-    }
-    if (threadIdx.x == 0) {
-      while (*reinterpret_cast<volatile unsigned int*>(a.ticket) != unsigned(G - 1)) {}
-    }
-    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(a.ticket, 1u);
+    return false;
   } else {
     if (threadIdx.x == 0) {
       const unsigned int t = atomicAdd(a.ticket, 1u);
@@ -99,15 +131,7 @@ __device__ __forceinline__ bool grid_reduce_shared(const PassArgs& a, double* s_
     if (!s_last) return false;
   }
   __threadfence();
-  // fixed-order reduction of the G per-CTA partials: lanes stride over CTAs, xor-butterfly combine
-  for (int i = warp; i < NRAW; i += NW) {
-    const volatile double* p = a.partials + size_t(i) * G;
-    double s = 0.0;
-    for (int c = lane; c < G; c += 32) s += p[c];
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) s += shfl_xor(s, o);
-    if (lane == 0) s_tot[i] = s;
-  }
+  grid_final_reduce<NRAW, THREADS>(a.partials, G, s_tot);
   if (threadIdx.x == 0) *a.ticket = 0u;  // ready for the next launch (stream-ordered)
   __syncthreads();
   return true;
@@ -267,22 +291,36 @@ static __device__ __noinline__ void p2p_fused_left_jacobian(const CostDev* c, co
 // s_kl are spread over the CTA (`scratch`, 21 * 16 doubles of shared memory), then one thread per entry adds them
 // up in the (k, l) order of the serial form — same operations in the same order, so the result is bit-identical to
 // one thread doing all 144 products of an entry (which cost ~2.5 us of the last CTA's time on a small problem).
-__device__ inline void p2p_assemble(const double* tot, const double (*jaff)[18], const CostDev* cost, PassResult* out,
-                                    int accumulate, int tid, int nthreads, double* scratch) {
+__device__ inline void p2p_assemble_inner(const double (*jaff)[18], const CostDev* cost, bool has_cov, int tid, int nthreads,
+                                          double* scratch) {
   constexpr int P = 6, NH = P * (P + 1) / 2;
+  // C = I (no covariance): the a != b terms of every sum are exact zeros and adding them changes nothing, so they are
+  // skipped — the chains the last CTA waits on are 3, 16 and 12 fused multiply-adds long instead of 9, 16 and 36 (the
+  // six entries of b were the longest: 2 200 cycles of dependent fp64 on a B200).  The products are spelled with
+  // intrinsics so that both forms round identically wherever this function is inlined.
   double C[9];
-  for (int i = 0; i < 9; ++i) C[i] = cost->has_cov ? cost->cov[i] : ((i % 4 == 0) ? 1.0 : 0.0);
+  for (int i = 0; i < 9; ++i) C[i] = has_cov ? cost->cov[i] : ((i % 4 == 0) ? 1.0 : 0.0);
   for (int w = tid; w < NH * 16; w += nthreads) {
     const int e = w >> 4, k = (w >> 2) & 3, l = w & 3;
     int i = 0, rem = e;  // decode (i, j) of the packed upper triangle
     while (rem >= P - i) { rem -= P - i; ++i; }
     const int j = i + rem;
     double s = 0.0;
-    for (int a = 0; a < 3; ++a)
-      for (int b = 0; b < 3; ++b) s += jaff[k][a * 6 + i] * C[a + 3 * b] * jaff[l][b * 6 + j];
+    if (has_cov) {
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) s = __fma_rn(__dmul_rn(jaff[k][a * 6 + i], C[a + 3 * b]), jaff[l][b * 6 + j], s);
+    } else {
+      for (int a = 0; a < 3; ++a) s = __fma_rn(jaff[k][a * 6 + i], jaff[l][a * 6 + j], s);
+    }
     scratch[w] = s;
   }
-  __syncthreads();
+}
+// Second half (after a CTA-wide synchronisation): needs the 23 totals.
+__device__ inline void p2p_assemble_outer(const double* tot, const double (*jaff)[18], const CostDev* cost, bool has_cov,
+                                          PassResult* out, int accumulate, int tid, int nthreads, const double* scratch) {
+  constexpr int P = 6, NH = P * (P + 1) / 2;
+  double C[9];
+  for (int i = 0; i < 9; ++i) C[i] = has_cov ? cost->cov[i] : ((i % 4 == 0) ? 1.0 : 0.0);
   // augmented moment matrix Mt (4x4, q~ = (1, q)) and St (4x3) = sum w q~ r^T
   double Mt[4][4], St[4][3];
   Mt[0][0] = tot[0];
@@ -297,17 +335,28 @@ __device__ inline void p2p_assemble(const double* tot, const double (*jaff)[18],
     double val = 0.0;
     if (e < NH) {
       for (int k = 0; k < 4; ++k)
-        for (int l = 0; l < 4; ++l) val += Mt[k][l] * scratch[e * 16 + k * 4 + l];
+        for (int l = 0; l < 4; ++l) val = __fma_rn(Mt[k][l], scratch[e * 16 + k * 4 + l], val);
     } else if (e < npk - 1) {
       const int i = e - NH;
-      for (int k = 0; k < 4; ++k)
-        for (int a = 0; a < 3; ++a)
-          for (int b = 0; b < 3; ++b) val += jaff[k][a * 6 + i] * C[a + 3 * b] * St[k][b];
+      if (has_cov) {
+        for (int k = 0; k < 4; ++k)
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) val = __fma_rn(__dmul_rn(jaff[k][a * 6 + i], C[a + 3 * b]), St[k][b], val);
+      } else {
+        for (int k = 0; k < 4; ++k)
+          for (int a = 0; a < 3; ++a) val = __fma_rn(jaff[k][a * 6 + i], St[k][a], val);
+      }
     } else {
       val = tot[22];
     }
     out->v[e] = accumulate ? out->v[e] + val : val;
   }
+}
+__device__ inline void p2p_assemble(const double* tot, const double (*jaff)[18], const CostDev* cost, bool has_cov,
+                                    PassResult* out, int accumulate, int tid, int nthreads, double* scratch) {
+  p2p_assemble_inner(jaff, cost, has_cov, tid, nthreads, scratch);
+  __syncthreads();
+  p2p_assemble_outer(tot, jaff, cost, has_cov, out, accumulate, tid, nthreads, scratch);
 }
 
 // Everything after a point2point streaming loop: CTA + grid reduction of the 23 moment sums (dacc[0]: the lane's
@@ -319,36 +368,71 @@ template <bool FUSED, int THREADS, bool COHERENT = false>
 __device__ __forceinline__ bool p2p_finish(const PassArgs& a, int mode, const double (&dacc)[1], double* s_tot,
                                            double* s_warp) {
   if (!grid_reduce<kP2PRaw, 32, 1, THREADS, COHERENT>(dacc, a, s_tot, s_warp)) return false;
+  if constexpr (COHERENT) {
+    return false;  // data CTAs of the persistent LM kernel: p2p_master_tail (CTA 0) takes it from here
+  } else {
+    const bool has_cov = a.cost->has_cov != 0;
+    if (mode == PASS_COST) {
+      if (threadIdx.x == 0) {
+        const int e = packed_size(6) - 1;
+        a.out->v[e] = a.accumulate ? a.out->v[e] + s_tot[22] : s_tot[22];
+      }
+    } else {
+      __shared__ double s_jl[FUSED ? 9 : 1];
+      __shared__ double s_jaff[FUSED ? 4 : 1][18];
+      const double(*jaff)[18] = FUSED ? s_jaff : a.pb->jaff;
+      if constexpr (FUSED) {
+        // the affine pieces of J, entry by entry (same sums, same order as setup_p2p_affine)
+        if (threadIdx.x == 0) {
+          double xl[6];  // a copy: taking the address of a kernel parameter would spill the whole PassArgs to local memory
+#pragma unroll
+          for (int i = 0; i < 6; ++i) xl[i] = a.x.v[i];
+          p2p_fused_left_jacobian(a.cost, xl, s_jl);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * 18; i += THREADS) s_jaff[i / 18][i % 18] = p2p_affine_entry(a.cost->variant, s_jl, i / 18, i % 18);
+        __syncthreads();
+      }
+      __shared__ double s_asm[21 * 16];
+      p2p_assemble(s_tot, jaff, a.cost, has_cov, a.out, a.accumulate, threadIdx.x, THREADS, s_asm);
+    }
+    peer_push(a, packed_size(6));
+    return true;
+  }
+}
+
+// CTA 0 of the persistent LM kernel: everything of a pass that is not streaming.  The Jacobian pieces this CTA's own
+// set-up wrote and the 21 x 16 inner sums that depend on them alone are taken care of WHILE the data CTAs stream;
+// then the totals of their partials, the outer sums, and the packed (H, b, sum) lands in `out` (shared memory).
+template <int THREADS>
+__device__ __forceinline__ void p2p_master_tail(const PassArgs& a, int mode, PassResult* out) {
+  static_assert(THREADS >= 4 * 18, "one ParamBlock::jaff entry per thread");
+  __shared__ double s_tot[32];
+  __shared__ double s_jaff[4][18];
+  __shared__ double s_asm[21 * 16];
+  const int G = int(gridDim.x) - 1;
+  const bool has_cov = a.cost->has_cov != 0;
+  if (mode != PASS_COST) {
+    if (threadIdx.x < 4 * 18) (&s_jaff[0][0])[threadIdx.x] = __ldcg(&a.pb->jaff[0][0] + threadIdx.x);
+    __syncthreads();
+    p2p_assemble_inner(s_jaff, a.cost, has_cov, threadIdx.x, THREADS, s_asm);
+  }
+  if (threadIdx.x == 0) {
+    while (*reinterpret_cast<volatile unsigned int*>(a.ticket) != unsigned(G)) {}
+  }
+  __syncthreads();
+  __threadfence();
+  grid_final_reduce<kP2PRaw, THREADS>(a.partials, G, s_tot);
+  if (threadIdx.x == 0) *a.ticket = 0u;
+  __syncthreads();
   if (mode == PASS_COST) {
     if (threadIdx.x == 0) {
       const int e = packed_size(6) - 1;
-      a.out->v[e] = a.accumulate ? a.out->v[e] + s_tot[22] : s_tot[22];
+      out->v[e] = a.accumulate ? out->v[e] + s_tot[22] : s_tot[22];
     }
   } else {
-    __shared__ double s_jl[FUSED ? 9 : 1];
-    __shared__ double s_jaff[(FUSED || COHERENT) ? 4 : 1][18];
-    const double(*jaff)[18] = (FUSED || COHERENT) ? s_jaff : a.pb->jaff;
-    if constexpr (COHERENT && !FUSED) {
-      for (int i = threadIdx.x; i < 4 * 18; i += THREADS) s_jaff[i / 18][i % 18] = __ldcg(&a.pb->jaff[i / 18][i % 18]);
-      __syncthreads();
-    }
-    if constexpr (FUSED) {
-      // the affine pieces of J, entry by entry (same sums, same order as setup_p2p_affine)
-      if (threadIdx.x == 0) {
-        double xl[6];  // a copy: taking the address of a kernel parameter would spill the whole PassArgs to local memory
-#pragma unroll
-        for (int i = 0; i < 6; ++i) xl[i] = a.x.v[i];
-        p2p_fused_left_jacobian(a.cost, xl, s_jl);
-      }
-      __syncthreads();
-      for (int i = threadIdx.x; i < 4 * 18; i += THREADS) s_jaff[i / 18][i % 18] = p2p_affine_entry(a.cost->variant, s_jl, i / 18, i % 18);
-      __syncthreads();
-    }
-    __shared__ double s_asm[21 * 16];
-    p2p_assemble(s_tot, jaff, a.cost, a.out, a.accumulate, threadIdx.x, THREADS, s_asm);
+    p2p_assemble_outer(s_tot, s_jaff, a.cost, has_cov, out, a.accumulate, threadIdx.x, THREADS, s_asm);
   }
-  peer_push(a, packed_size(6));
-  return true;
 }
 
 // FUSED: model->setup(x) runs inside the kernel (PassArgs::x; host-driven analytical passes), `pb` is not read.
@@ -357,6 +441,9 @@ __device__ __forceinline__ bool p2p_finish(const PassArgs& a, int mode, const do
 template <typename ST, typename CT, int LOSS, bool QROT, int THREADS, int UNROLL, int FLUSH_ROUNDS, int PF, bool SWP,
           bool FUSED, bool COHERENT>
 __device__ __forceinline__ bool p2p_moment_body(const PassArgs& a, const int mode) {
+  // COHERENT: a data CTA of the persistent LM kernel, whose CTA 0 takes no residuals (grid_reduce_shared)
+  const int bid = COHERENT ? int(blockIdx.x) - 1 : int(blockIdx.x);
+  const int nb = COHERENT ? int(gridDim.x) - 1 : int(gridDim.x);
   constexpr int VEC = VecOf<ST>::N;
   constexpr bool kFp32Acc = (sizeof(CT) == 4);
   // fp32 partials are folded into fp64 every FLUSH_ROUNDS*VEC residuals/thread
@@ -396,9 +483,9 @@ __device__ __forceinline__ bool p2p_moment_body(const PassArgs& a, const int mod
   double dacc[1] = {0.0};
 
   const int64_t ngroups = a.n / VEC;
-  const int64_t stride = int64_t(gridDim.x) * THREADS;
+  const int64_t stride = int64_t(nb) * THREADS;
   const int64_t full_rounds = ngroups / stride;
-  const int64_t g0 = int64_t(blockIdx.x) * THREADS + threadIdx.x;
+  const int64_t g0 = int64_t(bid) * THREADS + threadIdx.x;
 
   auto flush = [&]() {
     const CT v = warp_reduce_transpose<32>(acc);
@@ -426,7 +513,7 @@ __device__ __forceinline__ bool p2p_moment_body(const PassArgs& a, const int mod
   // flight no longer bounds the DRAM queue depth.
   auto prefetch_round = [&](int64_t rr) {
     if (PF > 0 && threadIdx.x == 0 && rr < full_rounds) {
-      const int64_t e0 = (int64_t(blockIdx.x) * THREADS + rr * stride) * VEC;
+      const int64_t e0 = (int64_t(bid) * THREADS + rr * stride) * VEC;
       constexpr unsigned bytes = THREADS * VEC * sizeof(ST);
       l2_prefetch_bulk(sx + e0, bytes); l2_prefetch_bulk(sy + e0, bytes); l2_prefetch_bulk(sz + e0, bytes);
       l2_prefetch_bulk(tx + e0, bytes); l2_prefetch_bulk(ty + e0, bytes); l2_prefetch_bulk(tz + e0, bytes);
@@ -513,7 +600,7 @@ __device__ __forceinline__ bool p2p_moment_body(const PassArgs& a, const int mod
   {  // ragged last round + scalar tail (n % VEC residuals)
     const int64_t g = g0 + full_rounds * stride;
     if (g < ngroups) do_group(g);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (bid == 0 && threadIdx.x == 0) {
       for (int64_t i = ngroups * VEC; i < a.n; ++i) {
         if (mode == PASS_COST)
           p2p_cost_only<CT>(masked, R, t, CT(sx[i]), CT(sy[i]), CT(sz[i]), CT(tx[i]), CT(ty[i]), CT(tz[i]), acc);

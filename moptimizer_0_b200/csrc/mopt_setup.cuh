@@ -19,54 +19,97 @@ namespace mopt {
 // callers that need the literal behaviour of the float instantiation.
 constexpr double kSo3GuardF64 = 10.0 * 2.220446049250313e-16;
 constexpr double kSo3GuardF32 = 10.0 * 1.1920928955078125e-07;
-// `trig` (optional): receives {n, sin n, cos n} when they were evaluated (n > guard), so that a caller that needs the
-// same sine and cosine again (the left Jacobian at the same omega) does not pay for them twice; trig[0] = -1 otherwise.
+// The roundings of so3::Exp and of the left Jacobian are spelled out (intrinsics, no compiler-chosen contraction):
+// the same values come out of the serial forms below (fused into the pass kernels, finite-difference set-ups) and of
+// the warp-parallel form of the optimizer step (so3_exp_jl_warp), wherever they are inlined.
+__device__ inline double so3_norm2_dev(const double w[3]) {
+  return __fma_rn(w[2], w[2], __fma_rn(w[1], w[1], __dmul_rn(w[0], w[0])));
+}
+// (K^2)(r, c) for K = hat(k)
+__device__ inline double so3_hat2_entry(const double K[9], int r, int c) {
+  return __fma_rn(K[r * 3 + 2], K[6 + c], __fma_rn(K[r * 3 + 1], K[3 + c], __dmul_rn(K[r * 3], K[c])));
+}
+// R = I + sin(n) K + (1 - cos(n)) K^2, K = hat(axis)
+__device__ inline void so3_exp_entries(const double a[3], double sn, double cs, double R[9]) {
+  const double K[9] = {0.0, -a[2], a[1], a[2], 0.0, -a[0], -a[1], a[0], 0.0};
+  const double omc = __dsub_rn(1.0, cs);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      R[r * 3 + c] = __dadd_rn(r == c ? 1.0 : 0.0, __fma_rn(sn, K[r * 3 + c], __dmul_rn(omc, so3_hat2_entry(K, r, c))));
+}
+// J = I + A [w]x + B [w]x^2
+__device__ inline void so3_left_jacobian_entries(const double w[3], double A, double B, double J[9]) {
+  const double K[9] = {0.0, -w[2], w[1], w[2], 0.0, -w[0], -w[1], w[0], 0.0};
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      J[r * 3 + c] = __fma_rn(B, so3_hat2_entry(K, r, c), __fma_rn(A, K[r * 3 + c], r == c ? 1.0 : 0.0));
+}
+
 template <typename S>
-__device__ inline void so3_exp_dev(const double w[3], double R[9], double guard = kSo3GuardF64, double* trig = nullptr) {
-  const double n = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+__device__ inline void so3_exp_dev(const double w[3], double R[9], double guard = kSo3GuardF64) {
+  const double n = sqrt(so3_norm2_dev(w));
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
-  if (trig) trig[0] = -1.0;
   if (n > guard) {
-    const double a0 = w[0] / n, a1 = w[1] / n, a2 = w[2] / n;
-    const double K[9] = {0.0, -a2, a1, a2, 0.0, -a0, -a1, a0, 0.0};
+    const double a[3] = {w[0] / n, w[1] / n, w[2] / n};
     double sn, cs;
     sincos(n, &sn, &cs);
-    if (trig) { trig[0] = n; trig[1] = sn; trig[2] = cs; }
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) {
-        double kk = 0.0;
-        for (int k = 0; k < 3; ++k) kk += K[r * 3 + k] * K[k * 3 + c];
-        R[r * 3 + c] += sn * K[r * 3 + c] + (1.0 - cs) * kk;
-      }
+    so3_exp_entries(a, sn, cs, R);
   }
 }
 
 // Closed-form left Jacobian of SO(3): I + (1-cos)/th^2 [w]x + (th-sin)/th^3 [w]x^2.
-// `trig` (optional) = {n, sin n, cos n} from so3_exp_dev at the same omega: used only when n equals this function's own
-// theta bit for bit, and sincos(x) is bit-identical to sin(x), cos(x) (scripts/check_sincos_identity.cu: 0 mismatches in
-// 2^30 samples), so the result does not depend on whether it is given.
-__device__ inline void so3_left_jacobian_dev(const double w[3], double J[9], const double* trig = nullptr) {
-  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+__device__ inline void so3_left_jacobian_dev(const double w[3], double J[9]) {
+  const double th2 = so3_norm2_dev(w);
   const double th = sqrt(th2);
   double A, B;
   if (th2 < 1e-8) {
-    A = 0.5 - th2 / 24.0;
-    B = 1.0 / 6.0 - th2 / 120.0;
+    A = __dsub_rn(0.5, th2 / 24.0);
+    B = __dsub_rn(1.0 / 6.0, th2 / 120.0);
   } else {
     double sn, cs;
-    if (trig != nullptr && trig[0] == th) { sn = trig[1]; cs = trig[2]; }
-    else { cs = cos(th); sn = sin(th); }
-    A = (1.0 - cs) / th2;
-    B = (th - sn) / (th2 * th);
+    sincos(th, &sn, &cs);
+    A = __dsub_rn(1.0, cs) / th2;
+    B = __dsub_rn(th, sn) / __dmul_rn(th2, th);
   }
-  const double K[9] = {0.0, -w[2], w[1], w[2], 0.0, -w[0], -w[1], w[0], 0.0};
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) {
-      double kk = 0.0;
-      for (int k = 0; k < 3; ++k) kk += K[r * 3 + k] * K[k * 3 + c];
-      J[r * 3 + c] = (r == c ? 1.0 : 0.0) + A * K[r * 3 + c] + B * kk;
-    }
+  so3_left_jacobian_entries(w, A, B, J);
+}
+
+// so3::Exp(w) and, if want_jl, J_l(wj) together, by one full warp: the two square roots are ONE instruction sequence
+// (lane 0: |w|, lane 1: |wj|), likewise the two sincos and the five divisions (lanes 0-2: the axis, lanes 3-4: the
+// two Jacobian coefficients); everything else every lane computes for itself.  Same operations on the same values as
+// so3_exp_dev / so3_left_jacobian_dev (bit-identical results); the dependent chain is sqrt -> sincos -> division
+// instead of sqrt -> 3 divisions -> sincos -> sqrt -> sincos -> 2 divisions (a division is ~800 cycles on a B200).
+__device__ inline void so3_exp_jl_warp(const double w[3], const double wj[3], double guard, bool want_jl, int lane,
+                                       double R[9], double Jl[9]) {
+  const unsigned full = 0xffffffffu;
+  const double n2 = so3_norm2_dev(w), th2 = so3_norm2_dev(wj);
+  const double rt = sqrt(lane == 1 ? th2 : n2);
+  const double n = __shfl_sync(full, rt, 0), th = __shfl_sync(full, rt, 1);
+  double s_, c_;
+  sincos(lane == 1 ? th : n, &s_, &c_);
+  const double sn = __shfl_sync(full, s_, 0), cs = __shfl_sync(full, c_, 0);
+  const double snj = __shfl_sync(full, s_, 1), csj = __shfl_sync(full, c_, 1);
+  const bool small = th2 < 1e-8;
+  double num = 1.0, den = 1.0;
+  if (lane < 3) { num = lane == 0 ? w[0] : (lane == 1 ? w[1] : w[2]); den = n; }
+  else if (lane == 3) { num = small ? th2 : __dsub_rn(1.0, csj); den = small ? 24.0 : th2; }
+  else if (lane == 4) { num = small ? th2 : __dsub_rn(th, snj); den = small ? 120.0 : __dmul_rn(th2, th); }
+  const double q = num / den;
+  const double a[3] = {__shfl_sync(full, q, 0), __shfl_sync(full, q, 1), __shfl_sync(full, q, 2)};
+  const double q3 = __shfl_sync(full, q, 3), q4 = __shfl_sync(full, q, 4);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = Jl[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if (n > guard) so3_exp_entries(a, sn, cs, R);
+  if (want_jl) {
+    const double A = small ? __dsub_rn(0.5, q3) : q3;
+    const double B = small ? __dsub_rn(1.0 / 6.0, q4) : q4;
+    so3_left_jacobian_entries(wj, A, B, Jl);
+  }
 }
 
 // src/so3.cpp:96-105 — so3::Log as the reference defines it (first-order branch below theta = 1e-3).
@@ -206,11 +249,21 @@ __device__ inline void setup_p2p_affine(const CostDev& c, const double* x, doubl
 // rounded to float exactly as `float` arithmetic would (linearization.h:78-89).
 // `scratch` (optional, >= 9 doubles of shared memory): enables the warp-parallel fast path of the analytical
 // point2point model below.
-__device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double* x, ParamBlock* pb, int lane, double* Jl);
+// Persistent LM kernel: the grid barrier word and the value that releases the CTAs waiting for the next pass.  A
+// set-up that can tell when the pass's own inputs are complete opens the barrier there (and sets *opened); otherwise
+// the caller opens it after the set-up.
+struct SetupEarlyOpen {
+  unsigned long long* gen;
+  unsigned long long value;
+  int* opened;  // shared memory
+  long long* prof;  // optional clock64 stamps (slot 11: the barrier opened)
+};
+__device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double* x, ParamBlock* pb, int lane, double* Jl,
+                                                 const SetupEarlyOpen* early);
 __device__ inline void setup_cost(const CostDev& c, const double* x, ParamBlock* pb, int lane, int nlanes,
-                                  double* scratch = nullptr) {
+                                  double* scratch = nullptr, const SetupEarlyOpen* early = nullptr) {
   if (scratch != nullptr && nlanes == 32 && c.model == MOPT_MODEL_POINT2POINT && c.jacobian == MOPT_JAC_ANALYTICAL) {
-    setup_p2p_analytical_warp(c, x, pb, lane, scratch);
+    setup_p2p_analytical_warp(c, x, pb, lane, scratch, early);
     return;
   }
   const int P = c.P;
@@ -307,28 +360,40 @@ __device__ inline double p2p_affine_entry(int variant, const double* Jl, int k, 
 // setup_cost for the analytical point2point model, spread over one warp: lane 0 derives (R, t) and J_l(omega) exactly
 // as setup_one_set / setup_p2p_affine do, then the 72 affine Jacobian entries are formed one per lane (the generic
 // path runs ~1 500 serial instructions on lane 0 for this; the optimizer step of a small problem waits on it).
-__device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double* x, ParamBlock* pb, int lane, double* Jl) {
-  if (lane == 0) {
-    const bool f32 = (c.compute_dtype == MOPT_F32);
-    double xs[6];
+__device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double* x, ParamBlock* pb, int lane, double* Jl,
+                                                 const SetupEarlyOpen* early) {
+  const bool f32 = (c.compute_dtype == MOPT_F32);
+  double xs[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) xs[i] = f32 ? double(float(x[i])) : x[i];
-    const double w[3] = {xs[3], xs[4], xs[5]};
-    double R[9], trig[3];
-    if (f32) so3_exp_dev<float>(w, R, c.so3_guard, trig); else so3_exp_dev<double>(w, R, c.so3_guard, trig);
+  for (int i = 0; i < 6; ++i) xs[i] = f32 ? double(float(x[i])) : x[i];
+  const double w[3] = {xs[3], xs[4], xs[5]};
+  const double wj[3] = {x[3], x[4], x[5]};  // the Jacobian takes omega with a double Scalar
+  double R[9], J[9];
+  so3_exp_jl_warp(w, wj, c.so3_guard, c.variant == MOPT_P2P_EXACT, lane, R, J);
+  if (lane < 9) {
+    double v = R[0];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) pb->sets[0][i] = R[i];
-    pb->sets[0][9] = xs[0]; pb->sets[0][10] = xs[1]; pb->sets[0][11] = xs[2];
+    for (int i = 1; i < 9; ++i) v = (lane == i) ? R[i] : v;
+    pb->sets[0][lane] = v;
+    double j = J[0];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Jl[i] = (i % 4 == 0) ? 1.0 : 0.0;
-    if (c.variant == MOPT_P2P_EXACT) {
-      const double wj[3] = {x[3], x[4], x[5]};
-      so3_left_jacobian_dev(wj, Jl, trig);  // same omega with a double Scalar: one sincos serves both
-    }
+    for (int i = 1; i < 9; ++i) j = (lane == i) ? J[i] : j;
+    Jl[lane] = j;
+  } else if (lane < 12) {
+    pb->sets[0][lane] = lane == 9 ? xs[0] : (lane == 10 ? xs[1] : xs[2]);
+  } else if (lane < kSetSize) {
+    pb->sets[0][lane] = 0.0;
   }
-  if (lane >= 12 && lane < kSetSize) pb->sets[0][lane] = 0.0;
   if (lane < c.P) pb->x[lane] = x[lane];
   __syncwarp();
+  // The pass needs (R, t) when it starts and the Jacobian pieces only when its last CTA assembles the result: the
+  // persistent LM kernel releases the other CTAs here, before the 72 affine entries are formed.
+  if (early && early->gen && lane == 0) {
+    // release: the ParamBlock stores of the other lanes are ordered before it by the __syncwarp above
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(early->gen), "l"(early->value) : "memory");
+    *early->opened = 1;
+    if (early->prof) early->prof[11] = clock64();
+  }
   for (int i = lane; i < 4 * 18; i += 32) pb->jaff[i / 18][i % 18] = p2p_affine_entry(c.variant, Jl, i / 18, i % 18);
   __syncwarp();
 }
