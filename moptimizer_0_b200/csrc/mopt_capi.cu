@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <cmath>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -466,8 +467,8 @@ int ctx_alloc(mopt_ctx* ctx) {
   MOPT_CUDA_TRY(cudaHostAlloc(&ctx->h_xerr, sizeof(int), cudaHostAllocMapped));
   *ctx->h_xerr = 0;
   MOPT_CUDA_TRY(cudaHostGetDevicePointer(&ctx->d_xerr, ctx->h_xerr, 0));
-  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_gen, sizeof(unsigned long long)));
-  MOPT_CUDA_TRY(cudaMemset(ctx->d_gen, 0, sizeof(unsigned long long)));
+  MOPT_CUDA_TRY(cudaMalloc(&ctx->d_gen, 32 * sizeof(unsigned long long)));
+  MOPT_CUDA_TRY(cudaMemset(ctx->d_gen, 0, 32 * sizeof(unsigned long long)));
   MOPT_CUDA_TRY(cudaMalloc(&ctx->d_xerr_dev, sizeof(int)));
   MOPT_CUDA_TRY(cudaMemset(ctx->d_xerr_dev, 0, sizeof(int)));
   ctx->flags_capacity = 4096;
@@ -799,9 +800,13 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
       MonoArgs m;
       m.st = ctx->d_lm;
       m.host_st = ctx->d_lm_host;
+      m.host_flag = ctx->d_flags;  // word 0 of the mapped flag ring (idle: this path and the launch-per-trial path exclude each other)
+      reinterpret_cast<volatile int*>(ctx->h_flags)[0] = 0;
+      static const int generic_p = [] { const char* e = getenv("MOPT_LM_GENERIC_P"); return (e && e[0] == '1') ? 1 : 0; }();
+      m.generic_p = generic_p;
       ctx->h_lm->done = 0;
       m.slots = ctx->d_slots;
-      m.gen = ctx->d_gen;
+      m.rt_words = ctx->d_gen;
       const int64_t slots64 = int64_t(opt.max_iterations) * (int64_t(opt.lm_max_iterations) + 1) + 2;
       m.max_slots = int(slots64 < INT32_MAX ? slots64 : INT32_MAX);
       m.init = in;  // prepare() + the first setup(x0) run inside the kernel too (CTA 0, before the first pass)
@@ -819,7 +824,23 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
       const auto h0 = std::chrono::steady_clock::now();
       MOPT_TRY(launch_p2p_lm_mono(L, stores[0]->dtype, p0.compute_dtype, p0.loss, qrot, a, m));
       const auto h1 = std::chrono::steady_clock::now();
-      MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      // The kernel's last act is to set the mapped flag (after a system-scope fence behind the state and the trace):
+      // spinning on it sees the end ~5 us before cudaStreamSynchronize would return (kernel teardown + driver
+      // wake-up).  The stream is queried now and then so that a failed launch cannot hang the caller; with the
+      // trace on, the stream is drained as before (the stamps are read back).
+      if (trace) {
+        MOPT_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      } else {
+        for (int spins = 0;; ++spins) {
+          if (reinterpret_cast<volatile int*>(ctx->h_flags)[0] != 0) break;
+          if ((spins & 4095) == 4095) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) break;  // finished (the flag is set by now, or the state says why not)
+            if (q != cudaErrorNotReady) MOPT_CUDA_TRY(q);
+          }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+      }
       const auto h2 = std::chrono::steady_clock::now();
       if (d_dbg) {
         std::fprintf(stderr, "mono host: launch call %.1f us, wait for the kernel %.1f us\n",

@@ -51,8 +51,8 @@ struct mopt_ctx {
   unsigned long long xseq = 0;
   int* h_xerr = nullptr;                         // mapped: set by the consumer kernel on a wait timeout
   int* d_xerr = nullptr;
-  unsigned long long* d_gen = nullptr;           // grid-barrier generation counter of the persistent LM kernel (never reset)
-  unsigned long long mono_gen = 0;               // its value after the launches so far
+  unsigned long long* d_gen = nullptr;           // persistent LM kernel: the 24 tagged words that carry (R, t) and act as its grid barrier (publish_rt)
+  unsigned long long mono_gen = 0;               // barrier targets handed out so far (monotonic over the context's life)
   int* d_xerr_dev = nullptr;                     // device-resident copy, read by the kernels that follow a failed exchange
 };
 

@@ -259,16 +259,23 @@ __device__ inline void lm_solve_propose_warp(LmState* st, const CostDev& cost0, 
 // One transition of the optimizer, run by ONE thread.  Returns 0 if the optimization ended, 1 if a new evaluation
 // point x_eval was set (the caller then runs model setup for every cost), 2 if the damped system has to be solved
 // and a step proposed first (lm_solve_propose_warp, by the whole warp), followed by the same setup.
+// Bit 2 (value 4) of the result: the caller must copy the whole pass result into st->cur (by the warp, one word per
+// lane: on one thread the 28 shared-memory load / store pairs are a 1 000-cycle dependent chain); the thread has
+// read what it needs of the new linearization from `trial` itself.
 // `st` may be a shared-memory copy of the hot part of the state (everything before `trials`): the trace is written
 // through `trials` (the array of the state in global memory), never through st->trials.
+constexpr int kLmCopyTrial = 4;
 template <typename S, int PC = 0>
 __device__ inline int lm_step_thread(LmState* st, const PassResult* trial, const CostDev& cost0, mopt_lm_trial* trials) {
   if (st->done) return 0;
   const int P = PC > 0 ? PC : st->P;
   const int npk = packed_size(P);
   st->num_passes += 1;
+  int copy = 0;                      // kLmCopyTrial once the accepted linearization is the one in `trial`
+  const PassResult* lin = &st->cur;  // where (H, b, y0) of the accepted point are to be read from below
   if (st->phase == LM_PHASE_LIN) {
-    for (int i = 0; i < npk; ++i) st->cur.v[i] = trial->v[i];
+    copy = kLmCopyTrial;
+    lin = trial;
   } else {
     const S yi = S(trial->v[npk - 1]);
     const S y0 = S(st->cur.v[npk - 1]);
@@ -330,15 +337,17 @@ __device__ inline int lm_step_thread(LmState* st, const PassResult* trial, const
       st->lambda = double(S(double(lam) * f));
       st->it += 1;
       if (st->it >= st->max_it) {
-        if (st->speculative)
-          for (int i = 0; i < npk; ++i) st->cur.v[i] = trial->v[i];
-        else
-          st->cur.v[npk - 1] = trial->v[npk - 1];
+        if (st->speculative) {
+          lm_finish(st, MOPT_MAXIMUM_ITERATIONS_REACHED);
+          return kLmCopyTrial;  // done (bits 0-1 clear); the final state holds the trial's linearization
+        }
+        st->cur.v[npk - 1] = trial->v[npk - 1];
         lm_finish(st, MOPT_MAXIMUM_ITERATIONS_REACHED);
         return 0;
       }
       if (st->speculative) {
-        for (int i = 0; i < npk; ++i) st->cur.v[i] = trial->v[i];
+        copy = kLmCopyTrial;
+        lin = trial;
       } else {
         st->cur.v[npk - 1] = trial->v[npk - 1];
         for (int i = 0; i < P; ++i) st->x_eval[i] = st->x[i];
@@ -348,27 +357,27 @@ __device__ inline int lm_step_thread(LmState* st, const PassResult* trial, const
       }
     }
   }
-  // start of an outer iteration (:62-77) with (H, b, y0) = cur
+  // start of an outer iteration (:62-77) with (H, b, y0) = *lin
   for (;;) {
-    const S y0 = S(st->cur.v[npk - 1]);
+    const S y0 = S(lin->v[npk - 1]);
     if (is_cost_small<S>(y0)) {
       lm_finish(st, MOPT_CONVERGED);
-      return 0;
+      return copy;
     }
     if (st->lambda < 0.0) {
       S mx = S(0);
-      for (int i = 0; i < P; ++i) mx = fmax(mx, fabs(S(st->cur.v[tri_index(P, i, i)])));
+      for (int i = 0; i < P; ++i) mx = fmax(mx, fabs(S(lin->v[tri_index(P, i, i)])));
       st->lambda = double(S(st->lambda_factor) * mx);
     }
     st->nu = 2.0;
     st->k = 0;
     if (st->lm_max_it > 0) {
-      return 2;
+      return 2 | copy;
     }
     st->it += 1;
     if (st->it >= st->max_it) {
       lm_finish(st, MOPT_MAXIMUM_ITERATIONS_REACHED);
-      return 0;
+      return copy;
     }
   }
 }
@@ -391,12 +400,15 @@ struct LmStepShared {
 struct LmStepIo {
   bool load_state = true, store_state = true, trial_staged = false;
   const CostDev* cost0 = nullptr;  // cost term 0's constants if the caller holds a copy, else read from the slot
-  // persistent kernel: the grid barrier word, this trial's target and a shared-memory flag — a set-up that knows when
-  // the next pass's own inputs are complete releases the waiting CTAs itself (SetupEarlyOpen, mopt_setup.cuh)
-  unsigned long long* gen = nullptr;
+  // persistent kernel: where (R, t) of the next pass is published, this trial's barrier target and a shared-memory
+  // flag — a set-up that knows when the next pass's own inputs are complete releases the waiting CTAs itself
+  // (SetupEarlyOpen, publish_rt, mopt_setup.cuh)
+  unsigned long long* rt_words = nullptr;
   unsigned long long gen_target = 0;
   int* opened = nullptr;
-  LmState* host_state = nullptr;  // mapped host memory: the trace and the final state are written there as well
+  bool generic_p = false;  // A/B: run the P = 6 case through the generic-size code (loops instead of unrolled)
+  LmState* host_state = nullptr;  // mapped host memory: the trace and the final state are written there as well,
+  int* host_flag = nullptr;       // then this word is set (after a system-scope fence): the host may stop waiting
 };
 
 // levenberg_marquadt_dyn.cpp:15-26 (prepare) + the first setup(x0), by one warp.
@@ -469,6 +481,11 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
   if (lane == 0) act = lm_step_thread<S, PC>(st, &sh->trial, cost0, io.host_state ? io.host_state->trials : gst->trials);
   act = __shfl_sync(0xffffffffu, act, 0);
   __syncwarp();  // lane 0's state writes are visible to the warp below
+  if (act & kLmCopyTrial) {  // the accepted linearization is the one this pass produced
+    for (int i = lane; i < npk; i += 32) st->cur.v[i] = sh->trial.v[i];
+    __syncwarp();
+    act &= ~kLmCopyTrial;
+  }
   if (prof && lane == 0) prof[2] = clock64();
   if (act == 2) {  // damped solve + proposal, the lanes sharing the factorization
     lm_solve_propose_warp<S, PC>(st, cost0, &sh->sc, lane, prof);
@@ -477,10 +494,10 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
   if (prof && lane == 0) prof[3] = clock64();
   if (act) {
     const int nc = st->n_costs;
-    const SetupEarlyOpen eo{io.gen, (io.gen_target << 2) | (unsigned long long)(st->pass_mode), io.opened, prof};
+    const SetupEarlyOpen eo{io.rt_words, (io.gen_target << 2) | (unsigned long long)(st->pass_mode), io.opened, prof};
     for (int c = 0; c < nc; ++c)
       setup_cost(c == 0 ? cost0 : slots[c].cost, st->x_eval, &slots[c].pb, lane, 32, sh->sc.tmp,
-                 (io.gen != nullptr && nc == 1) ? &eo : nullptr);
+                 (io.rt_words != nullptr && nc == 1) ? &eo : nullptr);
   }
   __syncwarp();
   if (prof && lane == 0) prof[4] = clock64();
@@ -490,6 +507,9 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
     if (io.host_state) {
       double* h = reinterpret_cast<double*>(io.host_state);
       for (int i = lane; i < kLmHotWords; i += 32) h[i] = sh->hot[i];
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0 && io.host_flag) *reinterpret_cast<volatile int*>(io.host_flag) = 1;
     }
   }
   __syncwarp();
@@ -502,7 +522,7 @@ __device__ inline int lm_step_warp_t(LmState* gst, const PassResult* gtrial, Cos
 // has 18; inlined, that translation unit took six minutes to compile).
 static __device__ __noinline__ int lm_step_warp(LmState* st, const PassResult* trial, CostSlot* slots, LmStepShared* sh, int lane,
                                                 int P, bool f32, const LmStepIo& io, long long* prof = nullptr) {
-  if (P == 6) {  // the 6-DoF registration case with unrolled loops
+  if (P == 6 && !io.generic_p) {  // the 6-DoF registration case with unrolled loops
     return f32 ? lm_step_warp_t<float, 6>(st, trial, slots, sh, lane, P, io, prof)
                : lm_step_warp_t<double, 6>(st, trial, slots, sh, lane, P, io, prof);
   }

@@ -440,8 +440,9 @@ __device__ __forceinline__ void p2p_master_tail(const PassArgs& a, int mode, Pas
 // Returns true in the last CTA once `out` holds the packed result.
 template <typename ST, typename CT, int LOSS, bool QROT, int THREADS, int UNROLL, int FLUSH_ROUNDS, int PF, bool SWP,
           bool FUSED, bool COHERENT>
-__device__ __forceinline__ bool p2p_moment_body(const PassArgs& a, const int mode) {
-  // COHERENT: a data CTA of the persistent LM kernel, whose CTA 0 takes no residuals (grid_reduce_shared)
+__device__ __forceinline__ bool p2p_moment_body(const PassArgs& a, const int mode, const double* rt = nullptr) {
+  // COHERENT: a data CTA of the persistent LM kernel, whose CTA 0 takes no residuals (grid_reduce_shared); (R, t)
+  // comes in `rt` (shared memory, received with the barrier: publish_rt) instead of the ParamBlock
   const int bid = COHERENT ? int(blockIdx.x) - 1 : int(blockIdx.x);
   const int nb = COHERENT ? int(gridDim.x) - 1 : int(gridDim.x);
   constexpr int VEC = VecOf<ST>::N;
@@ -452,7 +453,7 @@ __device__ __forceinline__ bool p2p_moment_body(const PassArgs& a, const int mod
   __shared__ double s_tot[32];
 
   __shared__ double s_set0[FUSED ? 12 : 1];
-  const double* set0 = FUSED ? s_set0 : a.pb->sets[0];
+  const double* set0 = FUSED ? s_set0 : (COHERENT ? rt : a.pb->sets[0]);
   if constexpr (FUSED) {
     if (threadIdx.x == 0) {
       double xl[6];  // a copy: taking the address of a kernel parameter would spill the whole PassArgs to local memory
@@ -464,9 +465,9 @@ __device__ __forceinline__ bool p2p_moment_body(const PassArgs& a, const int mod
   }
   CT R[9], t[3];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = CT(COHERENT ? __ldcg(set0 + i) : set0[i]);
+  for (int i = 0; i < 9; ++i) R[i] = CT(set0[i]);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) t[i] = CT(COHERENT ? __ldcg(set0 + 9 + i) : set0[9 + i]);
+  for (int i = 0; i < 3; ++i) t[i] = CT(set0[9 + i]);
   const CT lossp = CT(a.cost->loss_param);
   const bool masked = a.masked != 0;
 

@@ -25,28 +25,39 @@ constexpr double kSo3GuardF32 = 10.0 * 1.1920928955078125e-07;
 __device__ inline double so3_norm2_dev(const double w[3]) {
   return __fma_rn(w[2], w[2], __fma_rn(w[1], w[1], __dmul_rn(w[0], w[0])));
 }
-// (K^2)(r, c) for K = hat(k)
-__device__ inline double so3_hat2_entry(const double K[9], int r, int c) {
-  return __fma_rn(K[r * 3 + 2], K[6 + c], __fma_rn(K[r * 3 + 1], K[3 + c], __dmul_rn(K[r * 3], K[c])));
+// hat(v)(i, j): [[0, -v2, v1], [v2, 0, -v0], [-v1, v0, 0]], for run-time or compile-time (i, j)
+__device__ inline double so3_hat_entry(const double v[3], int i, int j) {
+  if (i == j) return 0.0;
+  const int k = 3 - i - j;
+  const double x = k == 0 ? v[0] : (k == 1 ? v[1] : v[2]);
+  return ((j - i + 3) % 3 == 1) ? -x : x;
 }
-// R = I + sin(n) K + (1 - cos(n)) K^2, K = hat(axis)
-__device__ inline void so3_exp_entries(const double a[3], double sn, double cs, double R[9]) {
-  const double K[9] = {0.0, -a[2], a[1], a[2], 0.0, -a[0], -a[1], a[0], 0.0};
+// (K^2)(r, c) for K = hat(v)
+__device__ inline double so3_hat2_entry(const double v[3], int r, int c) {
+  return __fma_rn(so3_hat_entry(v, r, 2), so3_hat_entry(v, 2, c),
+                  __fma_rn(so3_hat_entry(v, r, 1), so3_hat_entry(v, 1, c),
+                           __dmul_rn(so3_hat_entry(v, r, 0), so3_hat_entry(v, 0, c))));
+}
+// R = I + sin(n) K + (1 - cos(n)) K^2, K = hat(axis): entry (r, c)
+__device__ inline double so3_exp_entry(const double a[3], double sn, double cs, int r, int c) {
   const double omc = __dsub_rn(1.0, cs);
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      R[r * 3 + c] = __dadd_rn(r == c ? 1.0 : 0.0, __fma_rn(sn, K[r * 3 + c], __dmul_rn(omc, so3_hat2_entry(K, r, c))));
+  return __dadd_rn(r == c ? 1.0 : 0.0, __fma_rn(sn, so3_hat_entry(a, r, c), __dmul_rn(omc, so3_hat2_entry(a, r, c))));
 }
-// J = I + A [w]x + B [w]x^2
-__device__ inline void so3_left_jacobian_entries(const double w[3], double A, double B, double J[9]) {
-  const double K[9] = {0.0, -w[2], w[1], w[2], 0.0, -w[0], -w[1], w[0], 0.0};
+// J = I + A [w]x + B [w]x^2: entry (r, c)
+__device__ inline double so3_left_jacobian_entry(const double w[3], double A, double B, int r, int c) {
+  return __fma_rn(B, so3_hat2_entry(w, r, c), __fma_rn(A, so3_hat_entry(w, r, c), r == c ? 1.0 : 0.0));
+}
+__device__ inline void so3_exp_entries(const double a[3], double sn, double cs, double R[9]) {
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      J[r * 3 + c] = __fma_rn(B, so3_hat2_entry(K, r, c), __fma_rn(A, K[r * 3 + c], r == c ? 1.0 : 0.0));
+    for (int c = 0; c < 3; ++c) R[r * 3 + c] = so3_exp_entry(a, sn, cs, r, c);
+}
+__device__ inline void so3_left_jacobian_entries(const double w[3], double A, double B, double J[9]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) J[r * 3 + c] = so3_left_jacobian_entry(w, A, B, r, c);
 }
 
 template <typename S>
@@ -81,11 +92,14 @@ __device__ inline void so3_left_jacobian_dev(const double w[3], double J[9]) {
 
 // so3::Exp(w) and, if want_jl, J_l(wj) together, by one full warp: the two square roots are ONE instruction sequence
 // (lane 0: |w|, lane 1: |wj|), likewise the two sincos and the five divisions (lanes 0-2: the axis, lanes 3-4: the
-// two Jacobian coefficients); everything else every lane computes for itself.  Same operations on the same values as
-// so3_exp_dev / so3_left_jacobian_dev (bit-identical results); the dependent chain is sqrt -> sincos -> division
-// instead of sqrt -> 3 divisions -> sincos -> sqrt -> sincos -> 2 divisions (a division is ~800 cycles on a B200).
-__device__ inline void so3_exp_jl_warp(const double w[3], const double wj[3], double guard, bool want_jl, int lane,
-                                       double R[9], double Jl[9]) {
+// two Jacobian coefficients); the entries every lane forms for itself (one entry per lane with run-time indices was
+// measured slower: 5 200 against 3 700 cycles to the point where R is complete).  Same operations on the same values
+// as so3_exp_dev / so3_left_jacobian_dev (bit-identical results); the dependent chain is sqrt -> sincos -> division
+// instead of sqrt -> 3 divisions -> sincos -> sqrt -> sincos -> 2 divisions.
+// R is complete on return; the Jacobian is left as its two coefficients (so3_left_jacobian_entries(wj, A, B, J) forms it)
+// so that a caller with someone waiting for R can hand it over first.
+__device__ inline void so3_exp_jl_warp(const double w[3], const double wj[3], double guard, int lane, double R[9],
+                                       double& A, double& B) {
   const unsigned full = 0xffffffffu;
   const double n2 = so3_norm2_dev(w), th2 = so3_norm2_dev(wj);
   const double rt = sqrt(lane == 1 ? th2 : n2);
@@ -103,12 +117,22 @@ __device__ inline void so3_exp_jl_warp(const double w[3], const double wj[3], do
   const double a[3] = {__shfl_sync(full, q, 0), __shfl_sync(full, q, 1), __shfl_sync(full, q, 2)};
   const double q3 = __shfl_sync(full, q, 3), q4 = __shfl_sync(full, q, 4);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = Jl[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
   if (n > guard) so3_exp_entries(a, sn, cs, R);
-  if (want_jl) {
-    const double A = small ? __dsub_rn(0.5, q3) : q3;
-    const double B = small ? __dsub_rn(1.0 / 6.0, q4) : q4;
-    so3_left_jacobian_entries(wj, A, B, Jl);
+  A = small ? __dsub_rn(0.5, q3) : q3;
+  B = small ? __dsub_rn(1.0 / 6.0, q4) : q4;
+}
+
+// Persistent LM kernel: (R, t) of the next pass travels to the data CTAs in 24 self-validating 8-byte words — word
+// 2 i carries the low half and word 2 i + 1 the high half of value i (R row-major, then t) in its upper 32 bits, and
+// every word carries the same tag in its lower 32 bits: ((barrier target) << 2 | PassMode) truncated to 32 bits.
+// An 8-byte store is single-copy atomic, so a reader that finds the expected tag in a word has that word of THIS
+// publication: no fence on either side, and the wait for the optimizer and the load of (R, t) are one L2 round trip.
+__device__ inline void publish_rt(unsigned long long* words, unsigned long long value, double v, int lane) {
+  if (lane < 24) {
+    const unsigned half = (lane & 1) ? unsigned(__double2hiint(v)) : unsigned(__double2loint(v));
+    const unsigned long long wv = ((unsigned long long)(half) << 32) | (value & 0xffffffffull);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(words + lane), "l"(wv) : "memory");
   }
 }
 
@@ -249,14 +273,14 @@ __device__ inline void setup_p2p_affine(const CostDev& c, const double* x, doubl
 // rounded to float exactly as `float` arithmetic would (linearization.h:78-89).
 // `scratch` (optional, >= 9 doubles of shared memory): enables the warp-parallel fast path of the analytical
 // point2point model below.
-// Persistent LM kernel: the grid barrier word and the value that releases the CTAs waiting for the next pass.  A
-// set-up that can tell when the pass's own inputs are complete opens the barrier there (and sets *opened); otherwise
-// the caller opens it after the set-up.
+// Persistent LM kernel: where the next pass's (R, t) is published (publish_rt) and the tag that releases the CTAs
+// waiting for it.  A set-up that can tell when the pass's own inputs are complete publishes there (and sets *opened);
+// otherwise the caller does after the set-up.
 struct SetupEarlyOpen {
-  unsigned long long* gen;
-  unsigned long long value;
-  int* opened;  // shared memory
-  long long* prof;  // optional clock64 stamps (slot 11: the barrier opened)
+  unsigned long long* rt_words;
+  unsigned long long value;  // (barrier target << 2) | PassMode
+  int* opened;      // shared memory
+  long long* prof;  // optional clock64 stamps (slot 11: published)
 };
 __device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double* x, ParamBlock* pb, int lane, double* Jl,
                                                  const SetupEarlyOpen* early);
@@ -368,8 +392,25 @@ __device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double*
   for (int i = 0; i < 6; ++i) xs[i] = f32 ? double(float(x[i])) : x[i];
   const double w[3] = {xs[3], xs[4], xs[5]};
   const double wj[3] = {x[3], x[4], x[5]};  // the Jacobian takes omega with a double Scalar
-  double R[9], J[9];
-  so3_exp_jl_warp(w, wj, c.so3_guard, c.variant == MOPT_P2P_EXACT, lane, R, J);
+  double R[9], J[9], A, B;
+  so3_exp_jl_warp(w, wj, c.so3_guard, lane, R, A, B);
+  // The pass needs (R, t) when it starts and the Jacobian pieces only when its result is assembled: the persistent LM
+  // kernel releases the data CTAs here, before anything else of the set-up is stored.
+  if (early && early->rt_words) {
+    const int idx = lane >> 1;
+    double v = R[0];
+#pragma unroll
+    for (int i = 1; i < 9; ++i) v = (idx == i) ? R[i] : v;
+    v = (idx == 9) ? xs[0] : (idx == 10 ? xs[1] : (idx == 11 ? xs[2] : v));
+    publish_rt(early->rt_words, early->value, v, lane);
+    if (lane == 0) {
+      *early->opened = 1;
+      if (early->prof) early->prof[11] = clock64();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) J[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if (c.variant == MOPT_P2P_EXACT) so3_left_jacobian_entries(wj, A, B, J);
   if (lane < 9) {
     double v = R[0];
 #pragma unroll
@@ -386,14 +427,6 @@ __device__ inline void setup_p2p_analytical_warp(const CostDev& c, const double*
   }
   if (lane < c.P) pb->x[lane] = x[lane];
   __syncwarp();
-  // The pass needs (R, t) when it starts and the Jacobian pieces only when its last CTA assembles the result: the
-  // persistent LM kernel releases the other CTAs here, before the 72 affine entries are formed.
-  if (early && early->gen && lane == 0) {
-    // release: the ParamBlock stores of the other lanes are ordered before it by the __syncwarp above
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(early->gen), "l"(early->value) : "memory");
-    *early->opened = 1;
-    if (early->prof) early->prof[11] = clock64();
-  }
   for (int i = lane; i < 4 * 18; i += 32) pb->jaff[i / 18][i % 18] = p2p_affine_entry(c.variant, Jl, i / 18, i % 18);
   __syncwarp();
 }
