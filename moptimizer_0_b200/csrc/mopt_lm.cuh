@@ -412,24 +412,31 @@ struct LmStepIo {
 };
 
 // levenberg_marquadt_dyn.cpp:15-26 (prepare) + the first setup(x0), by one warp.
-static __device__ __noinline__ void lm_init_warp(LmState* st, CostSlot* slots, const LmInit& in, LmStepShared* sh, int lane) {
+// `st` may be the shared-memory copy of the state itself (persistent kernel: resident = true, cost0 = its copy of the
+// cost constants); otherwise it is the state in global memory and sh->hot is only borrowed for x0.
+static __device__ __noinline__ void lm_init_warp(LmState* st, CostSlot* slots, const LmInit& in, LmStepShared* sh, int lane,
+                                                 bool resident = false, const CostDev* cost0 = nullptr) {
   if (lane == 0) {
     st->P = in.P; st->n_costs = in.n_costs; st->max_it = in.max_it; st->lm_max_it = in.lm_max_it;
     st->speculative = in.speculative; st->scalar_f32 = in.scalar_f32; st->lambda_factor = in.lambda_factor;
     st->flags = in.flags;
+    st->pad0_ = 0;
     st->lambda = -1.0; st->nu = 2.0;
     st->it = 0; st->k = 0; st->phase = LM_PHASE_LIN; st->status = MOPT_MAXIMUM_ITERATIONS_REACHED;
     st->done = 0; st->executed = 0; st->num_trials = 0; st->num_passes = 0;
     st->pass_mode = PASS_LINEARIZE;
+    st->pad_ = 0;
   }
   if (lane < kMaxP) {
     const double v = lane < in.P ? (in.scalar_f32 ? double(float(in.x0[lane])) : in.x0[lane]) : 0.0;
     st->x[lane] = v; st->xi[lane] = v; st->x_eval[lane] = v; st->delta[lane] = 0.0;
-    sh->hot[lane] = v;  // setup below reads x_eval from shared memory
+    if (!resident) sh->hot[lane] = v;  // setup below reads x_eval from shared memory
   }
   for (int i = lane; i < kPackedMax; i += 32) st->cur.v[i] = 0.0;
   __syncwarp();
-  for (int c = 0; c < in.n_costs; ++c) setup_cost(slots[c].cost, sh->hot, &slots[c].pb, lane, 32, sh->sc.tmp);
+  const double* x = resident ? st->x_eval : sh->hot;
+  for (int c = 0; c < in.n_costs; ++c)
+    setup_cost((c == 0 && cost0) ? *cost0 : slots[c].cost, x, &slots[c].pb, lane, 32, sh->sc.tmp);
 }
 
 // The hot part of the state and the pass result are staged in shared memory by the whole warp (coalesced): the

@@ -96,8 +96,9 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_lm_mono_kernel(const PassAr
   if (master) {
     for (int i = threadIdx.x; i < int(sizeof(CostDev) / 4); i += THREADS)
       reinterpret_cast<int*>(&s_cost)[i] = reinterpret_cast<const int*>(&m.slots[0].cost)[i];
-    if (threadIdx.x < 32) {
-      lm_init_warp(m.st, m.slots, m.init, &s_sh, threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x < 32) {  // the state is born in shared memory; global memory sees it when the loop ends
+      lm_init_warp(reinterpret_cast<LmState*>(s_sh.hot), m.slots, m.init, &s_sh, threadIdx.x, true, &s_cost);
       __syncwarp();
       publish_from_pb(m.gen_base + 1, PASS_LINEARIZE);
     }
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(THREADS, MINB) p2p_lm_mono_kernel(const PassAr
       if (m.dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_pass));
       if (threadIdx.x < 32) {
         LmStepIo io;
-        io.load_state = (slot == 0);
+        io.load_state = false;
         io.store_state = (slot == m.max_slots - 1);  // and whenever the state machine ends (lm_step_warp_t)
         io.trial_staged = true;
         io.cost0 = &s_cost;
