@@ -221,6 +221,9 @@ __host__ __device__ __forceinline__ float fast_rcp(float x) {
 #endif
 }
 __host__ __device__ __forceinline__ double fast_rcp(double x) { return 1.0 / x; }
+// |x| < t in every lane of a value (scalars here; the packed pair F2 has its own overload)
+__host__ __device__ __forceinline__ bool all_abs_below(float x, float t) { return fabsf(x) < t; }
+__host__ __device__ __forceinline__ bool all_abs_below(double x, float t) { return fabs(x) < double(t); }
 
 // TMA bulk prefetch of `bytes` (multiple of 16, 16-byte aligned source) into L2.
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {

@@ -63,6 +63,8 @@ MOPT_HD F2 fma(F2 a, F2 b, F2 c) {
 #endif
 }
 MOPT_HD F2 fast_rcp(F2 a) { return F2(fast_rcp(a.v.x), fast_rcp(a.v.y)); }
+MOPT_HD F2 exp(F2 a) { return F2(expf(a.v.x), expf(a.v.y)); }
+MOPT_HD bool all_abs_below(F2 a, float t) { return fabsf(a.v.x) < t && fabsf(a.v.y) < t; }
 
 // ---- tensor-core helpers -----------------------------------------------------------------------------------
 __device__ __forceinline__ void ldmatrix_x4(const float* p, unsigned (&r)[4]) {

@@ -2,7 +2,7 @@
 """profiles/kernel_inst_counts.json from an `ncu --set full` capture of scripts/prof_dense.py:
 
     ncu --set full --metrics smsp__inst_executed_pipe_fma.sum,smsp__inst_executed_pipe_alu.sum,smsp__inst_executed_pipe_xu.sum \\
-        --clock-control none --import-source on -k regex:'p2p_moment|dense_pass|wide_pass' -o gpurun_out/r2_configs \\
+        --clock-control none --import-source on -k regex:'p2p_moment|dense_f2|dense_pass|wide_tc|wide_pass' -o gpurun_out/r2_configs \\
         python scripts/prof_dense.py
     python scripts/ncu_inst_counts.py gpurun_out/r2_configs.ncu-rep
 
@@ -20,7 +20,7 @@ KERNELS = [  # key, substring of the kernel name, residuals per launch
     ("p2p_gen2_f32", "p2p_moment2_kernel", 100_000_000),
     ("camera6_central_f32", "dense_f2_kernel<PinholeModel", 50_000_000),
     ("camera15_central_f32", "wide_tc_kernel<PinholeDistortModel", 50_000_000),
-    ("curve_central_f32", "dense_pass_kernel<ExpCurveModel", 10_000_000),
+    ("curve_central_f32", "dense_f2_kernel<ExpCurveModel", 10_000_000),
 ]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "inst": 1.0, "": 1.0,
          "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}  # times in microseconds
