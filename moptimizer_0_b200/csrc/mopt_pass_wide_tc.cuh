@@ -186,22 +186,36 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
   const int64_t ngroups = (a.n + 63) / 64;
   const int64_t wstride = int64_t(gridDim.x) * NW;
   int since_flush = 0;
-  for (int64_t g = int64_t(blockIdx.x) * NW + warp; g < ngroups; g += wstride) {
+  // this lane's two observations of group g; past the end (last group only) the store's last observation is re-read,
+  // its weight is forced to 0 below
+  auto load_obs = [&](int64_t g, F2 (&e)[NS]) {
     const int64_t i0 = g * 64 + 2 * lane;
-    const bool v0 = i0 < a.n, v1 = i0 + 1 < a.n;
-    // ---- 1. this lane's two observations --------------------------------------------------------------------
-    F2 e[NS];
-    if (v1) {
+    if (i0 + 1 < a.n) {
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const float2 t = *reinterpret_cast<const float2*>(sp[s] + i0);
         e[s] = F2(t.x, t.y);
       }
-    } else {  // past the end (last group only): re-read the store's last observation, its weight is forced to 0 below
-      const int64_t j0 = v0 ? i0 : a.n - 1;
+    } else {
+      const int64_t j0 = i0 < a.n ? i0 : a.n - 1;
 #pragma unroll
       for (int s = 0; s < NS; ++s) e[s] = F2(sp[s][j0], sp[s][a.n - 1]);
     }
+  };
+  // The next group's observations are requested before this group's tensor-core phase: the first instruction that
+  // used them was 10 % of all stall samples of the kernel (ncu source page, one FFMA2 waiting for the global loads).
+  F2 e_next[NS];
+  {
+    const int64_t g_first = int64_t(blockIdx.x) * NW + warp;
+    if (g_first < ngroups) load_obs(g_first, e_next);
+  }
+  for (int64_t g = int64_t(blockIdx.x) * NW + warp; g < ngroups; g += wstride) {
+    const int64_t i0 = g * 64 + 2 * lane;
+    const bool v0 = i0 < a.n, v1 = i0 + 1 < a.n;
+    // ---- 1. this lane's two observations --------------------------------------------------------------------
+    F2 e[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) e[s] = e_next[s];
     F2 r[O], tmp[NTMP], s0[SETN];
     load_set(0, s0);
     if constexpr (S1P < P) {
@@ -260,6 +274,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
 #pragma unroll
       for (int o = 0; o < O; ++o) *reinterpret_cast<float2*>(my + (kWideTcCols - 1) * ROW + o * 64) = (sw * r[o]).v;
       __syncwarp();
+      if (g + wstride < ngroups) load_obs(g + wstride, e_next);
       // ---- 2. Gram matrix of the tile on the tensor cores: C += X^T X, 3 x TF32 ------------------------------
       // The tensor core's fp32 accumulation truncates: a chain of n dependent MMAs on one accumulator biases a sum of
       // same-signed products (the diagonal of H) low by ~n * 2^-25 relative (measured: 5.3e-6 / 3.2e-6 / 2.3e-6 of
@@ -297,6 +312,8 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
           for (int q = 0; q < 4; ++q) cs[t][q] += ps[t][q];
       }
       __syncwarp();
+    } else if (g + wstride < ngroups) {
+      load_obs(g + wstride, e_next);  // cost-only pass: no tensor-core phase to put the loads in front of
     }
     if (++since_flush >= FLUSH_GROUPS) {
 #pragma unroll
