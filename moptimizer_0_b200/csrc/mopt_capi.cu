@@ -265,13 +265,19 @@ PassArgs make_args(mopt_ctx* ctx, const mopt_store* st, int slot, int accumulate
 // step fused against 0.3565 ms with the setup kernel in front (round 1's kernel showed no difference,
 // profiles/r1_fused_setup_ab_n2.txt); the packed results are bit-identical either way (bench.py check.vs_single_gpu
 // compares a fused single-GPU context with the sharded ones).  MOPT_FUSED_SETUP=0 never fuses.
-bool can_fuse_setup(const mopt_ctx* ctx, const mopt_problem* p) {
+bool can_fuse_setup(const mopt_ctx* ctx, const mopt_problem* p, const mopt_store* st) {
   static const int env = [] {
     const char* e = getenv("MOPT_FUSED_SETUP");
     return (e && e[0]) ? (e[0] == '0' ? 0 : 1) : -1;
   }();
   if (env == 0) return false;
-  (void)ctx;
+  // Finite differences of a parameter-only builtin model on the packed fp32 kernel (dense_f2_kernel, the condition of
+  // launch_one in mopt_pass_dense.cu): a set is x +- h e_j, every CTA's first warp derives them itself.  (For the camera
+  // models a set costs an so3::Exp and two matrix products per CTA: no gain over the set-up kernel, not fused.)
+  if (p->model == MOPT_MODEL_EXP_CURVE && p->jacobian != MOPT_JAC_ANALYTICAL && st->dtype == MOPT_F32 &&
+      p->compute_dtype == MOPT_F32 && !(p->flags & MOPT_FLAG_GENERIC_KERNEL) && !p->has_covariance &&
+      !st->may_have_invalid && ctx->threads != 1024)
+    return true;
   return p->model == MOPT_MODEL_POINT2POINT && p->jacobian == MOPT_JAC_ANALYTICAL &&
          p->manifold == MOPT_MANIFOLD_ADDITIVE;
 }
@@ -363,7 +369,7 @@ int enqueue_pass(mopt_ctx* ctx, mopt_store* st, const mopt_problem* p, const dou
     MOPT_REQUIRE(x != nullptr, "null parameter vector");
     for (int i = 0; i < P; ++i) xa.v[i] = x[i];
   }
-  if (can_fuse_setup(ctx, p)) {
+  if (can_fuse_setup(ctx, p, st)) {
     MOPT_TRY(launch_pass(ctx, st, p, 0, 0, mode, true, &xa));
   } else {
     setup_kernel<<<1, 32, 0, ctx->stream>>>(&ctx->d_slots[0], xa);

@@ -89,7 +89,15 @@ int launch_one(const PassLaunch& L, const PassArgs& a) {
       // (mopt_ctx_set_launch(.., 1024) keeps dense_pass_kernel for A/B on the same box)
       if (L.affine_fd && L.identity_cov && !a.masked && L.threads != 1024) return launch_f2<M>(L, a);
     }
+    if (a.fused_setup) {  // can_fuse_setup (mopt_capi.cu) mirrors the condition above
+      set_last_error("internal error: fused set-up requested for a kernel that reads the ParamBlock");
+      return MOPT_ERR_CUDA;
+    }
     if (L.affine_fd) return launch_shape<M, ST, CT, NUMERIC, kThreads, kMinB, true>(L, a);
+  }
+  if (a.fused_setup) {
+    set_last_error("internal error: fused set-up requested for a kernel that reads the ParamBlock");
+    return MOPT_ERR_CUDA;
   }
   return launch_shape<M, ST, CT, NUMERIC, kThreads, kMinB>(L, a);
 }

@@ -10,9 +10,18 @@
 #pragma once
 
 #include "mopt_pass_wide_tc.cuh"
+#include "mopt_setup.cuh"
 
 namespace mopt {
 #ifdef __CUDACC__
+
+// model->setup(x) and the finite-difference sets inside the pass kernel (PassArgs::fused_setup; host-driven passes of
+// parameter-only models, where a set is x +- h e_j and the separate one-warp set-up kernel plus its dependent launch
+// are a third of a 10 M-sample step): the CTA's first warp fills a ParamBlock in shared memory exactly as
+// setup_kernel does in global memory.  One copy per translation unit.
+static __device__ __noinline__ void dense_fused_setup(const CostDev* c, XArg x, ParamBlock* pb, int lane) {
+  setup_cost(*c, x.v, pb, lane, 32);
+}
 
 template <class M, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) dense_f2_kernel(const PassArgs a) {
@@ -32,18 +41,25 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_f2_kernel(const PassArgs 
   __shared__ __align__(16) float s_sets[NSETS][SETN];
   __shared__ float s_h[P];
 
+  __shared__ ParamBlock s_pb;  // fused set-up only
+  const ParamBlock* pb = a.pb;
+  if (a.fused_setup) {
+    if (threadIdx.x < 32) dense_fused_setup(a.cost, a.x, &s_pb, threadIdx.x);
+    __syncthreads();
+    pb = &s_pb;
+  }
   const bool central = (a.cost->jacobian == MOPT_JAC_CENTRAL);
   const int nsets = central ? 1 + 2 * P : 1 + P;
   for (int i = threadIdx.x; i < nsets * SETN; i += THREADS) {
     const int si = i / SETN, k = i % SETN;
-    double v = (k < M::SETN) ? a.pb->sets[si][k] : 0.0;
+    double v = (k < M::SETN) ? pb->sets[si][k] : 0.0;
     if (si >= 1 && si <= P && k < M::SETN) {  // D_j = (set(x + h_j e_j) - set_ref) / H_j, in fp64
       const int j = si - 1;
-      v = central ? (v - a.pb->sets[1 + P + j][k]) / a.pb->hstep_cen[j] : (v - a.pb->sets[0][k]) / a.pb->hstep_fwd[j];
+      v = central ? (v - pb->sets[1 + P + j][k]) / pb->hstep_cen[j] : (v - pb->sets[0][k]) / pb->hstep_fwd[j];
     }
     s_sets[si][k] = float(v);
   }
-  for (int i = threadIdx.x; i < P; i += THREADS) s_h[i] = float(central ? a.pb->hstep_cen[i] : a.pb->hstep_fwd[i]);
+  for (int i = threadIdx.x; i < P; i += THREADS) s_h[i] = float(central ? pb->hstep_cen[i] : pb->hstep_fwd[i]);
   const int loss = a.cost->loss;
   const float lossp = float(a.cost->loss_param);
   __syncthreads();
@@ -138,10 +154,11 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_f2_kernel(const PassArgs 
     acc[NRAW - 1] = acc[NRAW - 1] + e2;
   };
 
-  auto do_group = [&](int64_t g) {  // four consecutive observations: two pairs
-    float4 v[NS];
+  auto load_group = [&](int64_t g, float4 (&v)[NS]) {  // four consecutive observations of every stream
 #pragma unroll
     for (int s = 0; s < NS; ++s) v[s] = ld_stream(reinterpret_cast<const float4*>(sp[s]) + g);
+  };
+  auto do_group = [&](const float4 (&v)[NS]) {  // two pairs
     F2 e[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) e[s] = F2(v[s].x, v[s].y);
@@ -151,11 +168,26 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_f2_kernel(const PassArgs 
     do_pair(e, true);
   };
 
+  // Small models (exp curve: 80 registers) run a software pipeline: the next round's loads are issued before this round
+  // is evaluated (ncu: long_scoreboard 36 % of the exp curve's stall time; 41.4 -> 39.5 us per 10 M).  The camera model
+  // sits at its 128-register cap and loses to the extra 20 live registers (0.594 -> 0.636 ms): it loads and evaluates.
+  constexpr bool kPipelined = (P <= 2);
   const int64_t ngroups = a.n / 4;
   const int64_t stride = int64_t(gridDim.x) * THREADS;
   int since_flush = 0;
-  for (int64_t g = int64_t(blockIdx.x) * THREADS + threadIdx.x; g < ngroups; g += stride) {
-    do_group(g);
+  int64_t g = int64_t(blockIdx.x) * THREADS + threadIdx.x;
+  float4 v_next[NS];
+  if (kPipelined && g < ngroups) load_group(g, v_next);
+  for (; g < ngroups; g += stride) {
+    float4 v[NS];
+    if constexpr (kPipelined) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) v[s] = v_next[s];
+      if (g + stride < ngroups) load_group(g + stride, v_next);
+    } else {
+      load_group(g, v);
+    }
+    do_group(v);
     if (++since_flush >= FLUSH_ROUNDS) {
       flush();
       since_flush = 0;
