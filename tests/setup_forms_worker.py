@@ -22,4 +22,16 @@ for dtype in (capi.F64, capi.F32):
                     "lambda_linearize": float(1e-9 * np.max(np.abs(np.diag(H)))).hex(),
                     "lambda_lm": float(r.trace[0, 5]).hex()})
     st.close()
-print(json.dumps(out))
+# exp-curve, finite differences, fp32: the sets are built by the set-up kernel (MOPT_FUSED_SETUP=0) or by every CTA of
+# the pass kernel itself (default) — the caller compares the two runs' bits
+curve = []
+st = capi.Store(ctx, capi.MODEL_EXP_CURVE, 100_003, capi.F32)
+st.generate(seed=1, gt=[0.3, 0.1], lo=(0, 0, 0), hi=(5, 0, 0), n_total=100_003, noise_sigma=0.2)
+for jac in (capi.JAC_FORWARD, capi.JAC_CENTRAL):
+    prob = capi.make_problem(capi.MODEL_EXP_CURVE, jac, capi.F32, loss=capi.LOSS_HUBER, loss_param=0.3)
+    for x0 in ([0.0, 0.0], [0.25, 0.15], [-1.5, 2.0]):
+        H, b, s = ctx.linearize(st, prob, x0)
+        c = ctx.compute_cost(st, prob, x0)
+        curve.append([float(v).hex() for v in list(H.reshape(-1)) + list(b) + [s, c]])
+st.close()
+print(json.dumps({"p2p": out, "curve": curve}))

@@ -18,9 +18,17 @@ def _run(env_extra):
 @pytest.mark.gpu
 @pytest.mark.parametrize("fused", ["1", "0"])
 def test_warp_setup_matches_serial_forms_bit_for_bit(fused):
-    rows = _run({"MOPT_FUSED_SETUP": fused})
+    rows = _run({"MOPT_FUSED_SETUP": fused})["p2p"]
     assert len(rows) == 10
     for r in rows:
         # sum depends on (R, t); lambda_0 = 1e-9 max diag H on a rotational entry, i.e. on the left Jacobian
         assert r["sum_lm"] == r["sum_linearize"], r
         assert r["lambda_lm"] == r["lambda_linearize"], r
+
+
+@pytest.mark.gpu
+def test_fused_finite_difference_setup_matches_setup_kernel_bit_for_bit():
+    """Exp curve, fp32 finite differences: the 1 + 2P sets built inside the pass kernel (PassArgs::fused_setup) and by
+    the set-up kernel in front of it are the same function on the same x."""
+    fused, unfused = _run({})["curve"], _run({"MOPT_FUSED_SETUP": "0"})["curve"]
+    assert len(fused) == 6 and fused == unfused
