@@ -52,7 +52,6 @@ int launch_f2(const PassLaunch& L, const PassArgs& a) {
     case 4: return launch_f2_shape<M, 256, 3>(L, a);
     case 5: return launch_f2_shape<M, 256, 4>(L, a);
     case 6: return launch_f2_shape<M, 256, 6>(L, a);
-    case 7: return launch_f2_shape<M, 512, 2>(L, a);
     default: return launch_f2_shape<M, 256, 2>(L, a);
   }
 }

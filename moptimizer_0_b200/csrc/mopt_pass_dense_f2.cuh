@@ -9,6 +9,8 @@
 // computeHessianNumerical (include/moptimizer/linearization.h:65-124).
 #pragma once
 
+#include <type_traits>
+
 #include "mopt_pass_wide_tc.cuh"
 #include "mopt_setup.cuh"
 
@@ -41,12 +43,16 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_f2_kernel(const PassArgs 
   __shared__ __align__(16) float s_sets[NSETS][SETN];
   __shared__ float s_h[P];
 
-  __shared__ ParamBlock s_pb;  // fused set-up only
+  // fused set-up: parameter-only models (the host asks for it only for those, can_fuse_setup in mopt_capi.cu)
+  constexpr bool kCanFuse = (P <= 2);
+  __shared__ typename std::conditional<kCanFuse, ParamBlock, char>::type s_pb;
   const ParamBlock* pb = a.pb;
-  if (a.fused_setup) {
-    if (threadIdx.x < 32) dense_fused_setup(a.cost, a.x, &s_pb, threadIdx.x);
-    __syncthreads();
-    pb = &s_pb;
+  if constexpr (kCanFuse) {
+    if (a.fused_setup) {
+      if (threadIdx.x < 32) dense_fused_setup(a.cost, a.x, &s_pb, threadIdx.x);
+      __syncthreads();
+      pb = &s_pb;
+    }
   }
   const bool central = (a.cost->jacobian == MOPT_JAC_CENTRAL);
   const int nsets = central ? 1 + 2 * P : 1 + P;
@@ -168,16 +174,32 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_f2_kernel(const PassArgs 
     do_pair(e, true);
   };
 
-  // Small models (exp curve: 80 registers) run a software pipeline: the next round's loads are issued before this round
-  // is evaluated (ncu: long_scoreboard 36 % of the exp curve's stall time; 41.4 -> 39.5 us per 10 M).  The camera model
-  // sits at its 128-register cap and loses to the extra 20 live registers (0.594 -> 0.636 ms): it loads and evaluates.
+  // Hiding the latency of the round's global loads:
+  //   small models (exp curve: 80 registers) run a software pipeline in registers — the next round's loads are issued
+  //     before this round is evaluated (ncu: long_scoreboard 36 % of the exp curve's stall time; 41.4 -> 39.5 us per 10 M);
+  //   the camera model sits at its 128-register cap and loses to 20 more live registers (0.594 -> 0.636 ms), so its
+  //     next round travels global -> shared memory by cp.async (LDGSTS: no registers) into the thread's own slot of a
+  //     double buffer and is picked up with LDS.128 (long_scoreboard was 18 % of its stall time).
   constexpr bool kPipelined = (P <= 2);
+  constexpr bool kStaged = !kPipelined;
+  __shared__ float4 s_stage[kStaged ? 2 : 1][kStaged ? NS : 1][kStaged ? THREADS : 1];
+  auto stage_group = [&](int buf, int64_t gg) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(&s_stage[buf][s][threadIdx.x]));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const float4*>(sp[s]) + gg) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   const int64_t ngroups = a.n / 4;
   const int64_t stride = int64_t(gridDim.x) * THREADS;
   int since_flush = 0;
   int64_t g = int64_t(blockIdx.x) * THREADS + threadIdx.x;
   float4 v_next[NS];
-  if (kPipelined && g < ngroups) load_group(g, v_next);
+  int buf = 0;
+  if (g < ngroups) {
+    if constexpr (kPipelined) load_group(g, v_next); else stage_group(0, g);
+  }
   for (; g < ngroups; g += stride) {
     float4 v[NS];
     if constexpr (kPipelined) {
@@ -185,7 +207,15 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_f2_kernel(const PassArgs 
       for (int s = 0; s < NS; ++s) v[s] = v_next[s];
       if (g + stride < ngroups) load_group(g + stride, v_next);
     } else {
-      load_group(g, v);
+      if (g + stride < ngroups) {
+        stage_group(buf ^ 1, g + stride);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the group just committed has landed
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) v[s] = s_stage[buf][s][threadIdx.x];
+      buf ^= 1;
     }
     do_group(v);
     if (++since_flush >= FLUSH_ROUNDS) {
