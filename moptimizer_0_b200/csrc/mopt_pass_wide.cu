@@ -54,7 +54,13 @@ int launch_tc_flush(const PassLaunch& L, const PassArgs& a) {
   if (need < grid) grid = need;
   if (grid < 1) grid = 1;
   if (grid > kMaxGrid) grid = kMaxGrid;
-  kern<<<int(grid), kTcThreads, smem, L.stream>>>(a);
+  static const bool prefetch = [] {  // MOPT_WIDE_TC_PREFETCH=0: load the observations where they are used (A/B)
+    const char* e = getenv("MOPT_WIDE_TC_PREFETCH");
+    return !(e && e[0] == '0');
+  }();
+  PassArgs aa = a;
+  aa.no_ring = prefetch ? 0 : 1;  // (the field belongs to the point2point ring kernel; unused by this one otherwise)
+  kern<<<int(grid), kTcThreads, smem, L.stream>>>(aa);
   MOPT_CUDA_TRY(cudaGetLastError());
   return MOPT_OK;
 }

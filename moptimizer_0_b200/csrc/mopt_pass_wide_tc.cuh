@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
   F2 e_next[NS];
   {
     const int64_t g_first = int64_t(blockIdx.x) * NW + warp;
-    if (g_first < ngroups) load_obs(g_first, e_next);
+    if (g_first < ngroups && !a.no_ring) load_obs(g_first, e_next);
   }
   for (int64_t g = int64_t(blockIdx.x) * NW + warp; g < ngroups; g += wstride) {
     const int64_t i0 = g * 64 + 2 * lane;
@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
     F2 e[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) e[s] = e_next[s];
+    if (a.no_ring) load_obs(g, e);  // A/B switch (MOPT_WIDE_TC_PREFETCH=0): load at the point of use
     F2 r[O], tmp[NTMP], s0[SETN];
     load_set(0, s0);
     if constexpr (S1P < P) {
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
 #pragma unroll
       for (int o = 0; o < O; ++o) *reinterpret_cast<float2*>(my + (kWideTcCols - 1) * ROW + o * 64) = (sw * r[o]).v;
       __syncwarp();
-      if (g + wstride < ngroups) load_obs(g + wstride, e_next);
+      if (g + wstride < ngroups && !a.no_ring) load_obs(g + wstride, e_next);
       // ---- 2. Gram matrix of the tile on the tensor cores: C += X^T X, 3 x TF32 ------------------------------
       // The tensor core's fp32 accumulation truncates: a chain of n dependent MMAs on one accumulator biases a sum of
       // same-signed products (the diagonal of H) low by ~n * 2^-25 relative (measured: 5.3e-6 / 3.2e-6 / 2.3e-6 of
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wide_tc_kernel(const PassArgs a
           for (int q = 0; q < 4; ++q) cs[t][q] += ps[t][q];
       }
       __syncwarp();
-    } else if (g + wstride < ngroups) {
+    } else if (g + wstride < ngroups && !a.no_ring) {
       load_obs(g + wstride, e_next);  // cost-only pass: no tensor-core phase to put the loads in front of
     }
     if (++since_flush >= FLUSH_GROUPS) {
