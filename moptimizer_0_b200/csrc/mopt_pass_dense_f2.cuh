@@ -92,12 +92,26 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_f2_kernel(const PassArgs 
   };
   // a parameter set as broadcast pairs, re-read at every use (an asm volatile load the compiler cannot hoist: the
   // 1 + 2P sets do not fit in registers next to J and the accumulators)
-  auto load_set = [&](int idx, F2 (&sr)[SETN]) {
+  // (small models — P <= 2, SETN <= 4 — keep all 1 + 2P sets in registers instead: 20 values for the exp curve)
+  constexpr bool kSetsInRegs = (P <= 2 && SETN <= 4);
+  float sreg[kSetsInRegs ? NSETS : 1][kSetsInRegs ? SETN : 1];
+  if constexpr (kSetsInRegs) {
 #pragma unroll
-    for (int k = 0; k < SETN; k += 4) {
-      float t[4];
-      lds16_reload(&s_sets[idx][k], t);
-      sr[k] = F2(t[0]); sr[k + 1] = F2(t[1]); sr[k + 2] = F2(t[2]); sr[k + 3] = F2(t[3]);
+    for (int i = 0; i < NSETS; ++i)
+#pragma unroll
+      for (int k = 0; k < SETN; ++k) sreg[i][k] = (i < nsets) ? s_sets[i][k] : 0.f;
+  }
+  auto load_set = [&](int idx, F2 (&sr)[SETN]) {
+    if constexpr (kSetsInRegs) {
+#pragma unroll
+      for (int k = 0; k < SETN; ++k) sr[k] = F2(sreg[idx][k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < SETN; k += 4) {
+        float t[4];
+        lds16_reload(&s_sets[idx][k], t);
+        sr[k] = F2(t[0]); sr[k + 1] = F2(t[1]); sr[k + 2] = F2(t[2]); sr[k + 3] = F2(t[3]);
+      }
     }
   };
 
