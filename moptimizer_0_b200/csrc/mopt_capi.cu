@@ -793,7 +793,7 @@ int mopt_lm_minimize(mopt_ctx* ctx, int n_costs, mopt_store* const* stores, cons
       const char* e = getenv("MOPT_LM_MONO");
       if (e && e[0] == '0') return int64_t(0);
       const char* m = getenv("MOPT_LM_MONO_MAX");
-      return (m && m[0]) ? int64_t(atoll(m)) : int64_t(1) << 21;
+      return (m && m[0]) ? int64_t(atoll(m)) : int64_t(1) << 22;
     }();
     const mopt_problem& p0 = problems[0];
     const bool moment_path = p0.model == MOPT_MODEL_POINT2POINT &&
