@@ -333,8 +333,10 @@ class Context:
         n = len(stores)
         hs = (C.c_void_p * n)(*[s.handle for s in stores])
         ps = (Problem * n)(*problems)
-        opt = LmOptions()
-        lib().mopt_lm_default_options(C.byref(opt))
+        opt = self.__dict__.get("_lm_options")
+        if opt is None:  # every field the library's defaults set is either overwritten below or left as it is
+            opt = self._lm_options = LmOptions()
+            lib().mopt_lm_default_options(C.byref(opt))
         opt.max_iterations, opt.lm_max_iterations = max_iterations, lm_iterations
         opt.scalar_dtype, opt.speculative = scalar_dtype, 1 if speculative else 0
         opt.flags = LM_STAGNATION_STOP if stagnation_stop else 0
@@ -354,9 +356,17 @@ class LmResult:
         self.executed_iterations = rep.executed_iterations
         self.num_passes = rep.num_passes
         self.final_cost = rep.final_cost
-        n = rep.num_trials
-        self._trials = np.frombuffer(rep, dtype=_TRIAL_DTYPE, count=n, offset=LmReport.trials.offset).copy()
+        # the report object is reused by the context: copy the used part of the trace out as raw bytes now (1 us), parse
+        # it when somebody asks (a small solve is ~90 us; building the arrays eagerly cost 8 us of it)
+        self._raw = C.string_at(C.addressof(rep) + LmReport.trials.offset, rep.num_trials * _TRIAL_DTYPE.itemsize)
+        self._trials_arr = None
         self._trace = None
+
+    @property
+    def _trials(self) -> np.ndarray:
+        if self._trials_arr is None:
+            self._trials_arr = np.frombuffer(self._raw, dtype=_TRIAL_DTYPE)
+        return self._trials_arr
 
     @property
     def trace(self) -> np.ndarray:
